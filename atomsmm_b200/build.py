@@ -1,0 +1,71 @@
+"""
+Build the CUDA engine in-tree:  python -m atomsmm_b200.build [--force] [--verbose]
+
+Every .cu under csrc/ is compiled for sm_100a only (``-gencode arch=compute_100a,code=sm_100a
+-lineinfo``) and linked into atomsmm_b200/libatomsmm_b200.so, which travels with the repository
+snapshot to the GPU box.  nvcc cross-compiles without a GPU.
+"""
+
+import concurrent.futures
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+OBJ = os.path.join(HERE, 'csrc', '_obj')
+LIBRARY = os.path.join(HERE, 'libatomsmm_b200.so')
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+         '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '-Xptxas', '-v']
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cu'))
+
+
+def headers():
+    found = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))]
+    found.append(os.path.join(HERE, '..', 'include', 'atomsmm_b200.h'))
+    return found
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _compile(src, verbose):
+    obj = os.path.join(OBJ, os.path.basename(src)[:-3] + '.o')
+    if _stale(obj, [src] + headers()):
+        cmd = [NVCC] + FLAGS + ['-c', src, '-o', obj]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, proc.stdout, proc.stderr))
+        with open(obj + '.log', 'w') as handle:
+            handle.write(proc.stderr)
+        if verbose:
+            sys.stderr.write(proc.stderr)
+    return obj
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJ):
+            os.remove(os.path.join(OBJ, f))
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as pool:
+        objects = list(pool.map(lambda s: _compile(s, verbose), sources()))
+    if _stale(LIBRARY, objects):
+        cmd = [NVCC, '-shared', '-o', LIBRARY] + objects + ['-gencode', 'arch=compute_100a,code=sm_100a',
+                                                            '-Xcompiler', '-fPIC', '-lcudart']
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError('link failed:\n%s\n%s' % (proc.stdout, proc.stderr))
+    return LIBRARY
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))

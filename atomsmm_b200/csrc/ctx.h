@@ -1,0 +1,173 @@
+// Internal context of the atomsmm_b200 engine (not part of the C ABI).
+//
+// Data layout in HBM (all per-atom arrays are in the engine's *spatial* order: whole molecules
+// contiguous, molecules ordered along a Morton curve over cells; `orig`/`inv` map to and from
+// the caller's numbering):
+//
+//   x, v        double [n][3]   master state, never wrapped (molecules stay whole)
+//   xref        double [n][3]   positions at the last neighbour-list build (skin test)
+//   pos4        float4 [n]      periodic image of x in [0,L) rounded to fp32 (w unused)
+//   par[s]      float4 [n]      per parameter set: {charge, sigma/2, sqrt(epsilon), 0}
+//   massd       double [n]      mass;  invm: float [n] 1/mass (0 for massless)
+//   fbuf[g]     float4 [n]      force of group g (slot 32 = all groups, "f")
+//   perdof[k]   double [n][3]   user per-DOF integrator variables
+//   lists       int [ngroups][cap]  per 8-atom i-group: (excl_mask<<24 | j) entries
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/atomsmm_b200.h"
+#include "program.h"
+
+#define B2_GROUP 8            // atoms per i-group (one warp = 8 i-atoms x 4 j-lanes)
+#define B2_MAX_SETS 4
+#define B2_MAX_LISTS 4
+#define B2_FSLOTS 33          // force buffers: groups 0..31 and 32 = total
+#define B2_MAX_PAIR_PARAMS 16
+
+struct PairParams {           // passed by value to kernels
+    int family;
+    float rc2;                // effective cutoff^2 (min of list cutoff and potential range)
+    double p[B2_MAX_PAIR_PARAMS];
+};
+
+struct PairForce {
+    int family, group, set, list;
+    double cutoff;
+    int nparams;
+    double params[B2_MAX_PAIR_PARAMS];
+    double econst;
+};
+
+struct BondedForce {
+    int family, group, nterms, arity, stride, periodic;
+    int* atoms = nullptr;         // device, caller numbering
+    double* params = nullptr;     // device
+    double gparams[8] = {0};
+    int* code_e = nullptr; int ncode_e = 0;
+    int* code_de = nullptr; int ncode_de = 0;
+    double* consts = nullptr;
+};
+
+struct NList {
+    double cutoff = 0;            // interaction cutoff
+    int cap = 0;                  // entries per group
+    int* entries = nullptr;       // [ngroups][cap]
+    int* counts = nullptr;        // [ngroups]
+    unsigned char* gflags = nullptr;  // [ngroups] bit0: group needs per-pair minimum image
+};
+
+struct b2_context {
+    int device = 0;
+    cudaStream_t stream = 0;
+    cudaStream_t own_stream = 0;
+    std::string err;
+    long long counters[8] = {0};
+
+    // ---- description -----------------------------------------------------------------------
+    int n = 0, ngroups = 0;
+    double box[3] = {0, 0, 0};
+    int periodic = 1;
+    double skin = 0.1;
+    std::vector<double> h_mass;
+    std::vector<int> h_mol;
+    std::vector<std::vector<double>> h_sets;      // each 3*n: q, sigma, eps
+    std::vector<int> h_excl;                      // pairs
+    std::vector<PairForce> pair_forces;
+    std::vector<BondedForce> bonded_forces;
+    bool excl_far = false;                        // some exclusion spans > 31 in index
+
+    // ---- device state ----------------------------------------------------------------------
+    bool have_order = false, have_positions = false;
+    std::vector<int> h_orig;                      // sorted -> caller index
+    double *x = nullptr, *v = nullptr, *xref = nullptr, *xsort = nullptr;
+    float4* pos4 = nullptr;
+    float4* par[B2_MAX_SETS] = {nullptr};
+    double* pard[B2_MAX_SETS] = {nullptr};        // double [n][3]: charge, sigma, epsilon
+    double* massd = nullptr;
+    float* invm = nullptr;
+    int *orig = nullptr, *inv = nullptr;
+    unsigned long long* exmask = nullptr;         // per sorted atom: window mask over caller index
+    int *excl_ptr = nullptr, *excl_idx = nullptr; // CSR by caller index (fallback for wide spans)
+    float4* fbuf[B2_FSLOTS] = {nullptr};
+    long long fvalid[B2_FSLOTS];                  // position version for which fbuf[g] is valid
+    long long pos_version = 1;
+    std::vector<double*> perdof;
+    double* scratch3 = nullptr;                   // [n][3] staging for permuted copies
+
+    // ---- neighbour lists -------------------------------------------------------------------
+    int nlists = 0;
+    NList lists[B2_MAX_LISTS];
+    int ncell[3] = {0, 0, 0}, ncells = 0;
+    double cellsize[3] = {0, 0, 0};
+    int *cell_count = nullptr, *cell_start = nullptr, *cell_atoms = nullptr, *cell_of = nullptr;
+    int* nl_flags = nullptr;     // [0] rebuild needed, [1] overflow, [2] rebuild counter, [3] max count
+    bool lists_built = false;
+
+    // ---- energies --------------------------------------------------------------------------
+    double* d_energy = nullptr;  // [32] energy + [32] virial + [2] dE/dlambda + pad
+    double h_energy[32] = {0}, h_virial[32] = {0}, h_dlambda[2] = {0};
+
+    // ---- integrator program ----------------------------------------------------------------
+    std::vector<b2_op> ops;
+    int *code = nullptr; int ncode = 0;
+    double *consts = nullptr; int nconsts = 0;
+    double *globals = nullptr; int nglobals = 0;
+    double* sum_partial = nullptr;
+    unsigned long long* rng_state = nullptr;      // [0] seed, [1] draw counter
+    bool program_loaded = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graph_ready = false;
+    int eager_steps = 0;
+    long long graph_dpos = 0;
+    unsigned long long graph_entry_mask = 0, graph_exit_mask = 0;
+};
+
+// ---- error helpers --------------------------------------------------------------------------
+int b2_fail(b2_context* ctx, int code, const char* fmt, ...);
+
+#define B2_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return b2_fail(ctx, B2_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, \
+                           cudaGetErrorString(e_));                                            \
+    } while (0)
+
+#define B2_TRY(call)              \
+    do {                          \
+        int r_ = (call);          \
+        if (r_ != B2_OK) return r_; \
+    } while (0)
+
+#define B2_LAUNCH_CHECK()                                                                      \
+    do {                                                                                       \
+        ctx->counters[0]++;                                                                    \
+        cudaError_t e_ = cudaGetLastError();                                                   \
+        if (e_ != cudaSuccess)                                                                 \
+            return b2_fail(ctx, B2_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__, \
+                           cudaGetErrorString(e_));                                            \
+    } while (0)
+
+template <typename T>
+int b2_alloc(b2_context* ctx, T** ptr, size_t count);
+int b2_free_all(b2_context* ctx);
+
+// ---- cross-file entry points (host) ---------------------------------------------------------
+int nl_setup(b2_context* ctx);                        // cells + list allocation for current box
+int nl_prepare(b2_context* ctx, bool force);          // wrap + skin test + conditional rebuild
+int nl_initial_build(b2_context* ctx);                // sized build with capacity fitting (syncs)
+int pair_eval_forces(b2_context* ctx, const PairForce& pf, float4* out, bool accumulate);
+int pair_eval_energy(b2_context* ctx, const PairForce& pf, int group);
+int pair_count_set(b2_context* ctx, const PairForce& pf, long long* count, unsigned long long* checksum,
+                   int* pairs_dev, long long capacity);
+int bonded_eval(b2_context* ctx, const BondedForce& bf, float4* out, bool want_force, bool want_energy);
+int forces_ensure(b2_context* ctx, uint32_t mask, int slot);
+int program_run(b2_context* ctx, int nsteps);
+int program_release(b2_context* ctx);
+int state_permute_to_sorted(b2_context* ctx, const double* user, double* sorted);
+int state_permute_to_user(b2_context* ctx, const double* sorted, double* user);

@@ -1,0 +1,391 @@
+// Pair-tile kernels (K3 of SURVEY 2.1): forces in fp32 on the hot path, energies / virials /
+// dE/dlambda in fp64 at report cadence, and the exact interacting-pair set for parity tests.
+//
+// Replaces the pair loops OpenMM runs for CustomNonbondedForce / NonbondedForce direct space
+// (reference call sites: forces.py:225,153; evaluation through Context.getState, utils.py:164).
+//
+// Mapping: one warp per i-group of 8 spatially adjacent atoms; lane = (i-atom 0..7) x (j-lane
+// 0..3).  The group's j-list is streamed 32 entries at a time: every lane gathers one j atom
+// (float4 position + float4 parameters, coalesced index read), shifts it to the periodic image
+// nearest the group, and stages it in shared memory; the warp then sweeps the 32 staged atoms in
+// 8 steps of 4, each lane accumulating the force on its own i-atom in registers.  Forces are
+// reduced over the 4 j-lanes with two shuffles and written once per atom: no atomics, results
+// are bit-reproducible.  The full (both-directions) list means every pair is evaluated twice;
+// that trades arithmetic for zero scatter traffic.
+#include <math.h>
+
+#include <algorithm>
+
+#include "ctx.h"
+#include "potentials.cuh"
+
+#define FULL 0xffffffffu
+#define WPB 4   // warps per block
+
+template <typename T>
+static PotParams<T> make_params(const PairForce& pf, float* rc2_out) {
+    PotParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.sign = T(1);
+    p.degree = 1;
+    double rc_eff = pf.cutoff;
+    const double* a = pf.params;
+    auto set_switch = [&](bool use, double rs, double rc) {
+        p.rs = T(rs);
+        p.iw = (use && rc > rs) ? T(1.0/(rc - rs)) : T(0);
+    };
+    switch (pf.family) {
+    case B2_PAIR_NEAR: {
+        // variant, rs0, rc0, Kc, sign, use_coulomb
+        const double rs = a[1], rc = a[2];
+        set_switch(true, rs, rc);
+        p.kc = T(a[5] != 0.0 ? a[3] : 0.0);
+        p.sign = T(a[4]);
+        p.inv_rc0 = T(1.0/rc);
+        const double b = rs/(rc - rs);
+        p.b = T(b);
+        p.f12c = T(pow(1 + b, 3)*(pow(b, 6) + 3*pow(b, 5) + (30.0/7)*pow(b, 4) + (25.0/7)*pow(b, 3)
+                                   + (25.0/14)*b*b + 0.5*b + 2.0/33)/pow(b, 9));
+        p.f6c = T(pow(1 + b, 3)/pow(b, 3));
+        p.f1c = T((30*(1 + b))*(b*b*(1 + b)*(1 + b)*log(1/b + 1) - b*b*b - 1.5*b*b - b/3 + 1.0/12));
+        rc_eff = std::min(rc_eff, rc);
+        break;
+    }
+    case B2_PAIR_DAMPED: {
+        // alpha, rswitch, rcut, degree, Kc
+        const double rs = a[1], rc = a[2];
+        const int d = (int)a[3];
+        set_switch(true, rs, rc);
+        p.degree = d;
+        p.rsd = T(pow(rs, d));
+        p.iwd = T(1.0/(pow(rc, d) - pow(rs, d)));
+        p.alpha = T(a[0]);
+        p.tasp = T(2.0*a[0]/sqrt(M_PI));
+        p.kc = T(a[4]);
+        rc_eff = std::min(rc_eff, rc);
+        break;
+    }
+    case B2_PAIR_LJC: {
+        // Kc, coulomb_kind, krf, crf, alpha, use_switch, rswitch, rcut
+        p.kc = T(a[1] != 0.0 ? a[0] : 0.0);
+        p.krf = T(a[2]); p.crf = T(a[3]);
+        p.alpha = T(a[4]); p.tasp = T(2.0*a[4]/sqrt(M_PI));
+        set_switch(a[5] != 0.0, a[6], a[7]);
+        break;
+    }
+    case B2_PAIR_LJ_VIRIAL: {
+        set_switch(a[0] != 0.0, a[1], a[2]);
+        break;
+    }
+    case B2_PAIR_SOFTCORE: {
+        // Kc, lambda_vdw, lambda_coul, use_switch, rswitch, rcut
+        p.kc = T(a[0]); p.lam_v = T(a[1]); p.lam_c = T(a[2]);
+        set_switch(a[3] != 0.0, a[4], a[5]);
+        break;
+    }
+    }
+    *rc2_out = (float)(rc_eff*rc_eff);
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 force kernel
+// ---------------------------------------------------------------------------------------------
+template <class POT, bool MINIMG>
+__device__ __forceinline__ void sweep_chunk(const POT& pot, const float4* __restrict__ sx,
+                                            const float4* __restrict__ sp, int jj, int il, float4 xi,
+                                            float qi, float hsi, float sei, float rc2, float3 box, float3 inv,
+                                            float& fx, float& fy, float& fz) {
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        const int jl = 4*s + jj;
+        const float4 xj = sx[jl];
+        const float4 pj = sp[jl];
+        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        if (MINIMG) {
+            dx -= box.x*rintf(dx*inv.x);
+            dy -= box.y*rintf(dy*inv.y);
+            dz -= box.z*rintf(dz*inv.z);
+        }
+        const float r2 = dx*dx + dy*dy + dz*dz;
+        const unsigned m = (unsigned)__float_as_int(pj.w);
+        if (r2 < rc2 && !((m >> il) & 1u)) {
+            float rF, e;
+            pot.template operator()<false>(r2, qi*pj.x, hsi + pj.y, sei*pj.z, rF, e);
+            const float fr = rF*__frcp_rn(r2);
+            fx += fr*dx; fy += fr*dy; fz += fr*dz;
+        }
+    }
+}
+
+template <class POT>
+__global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const float4* __restrict__ pos4,
+                                                      const float4* __restrict__ par,
+                                                      const int* __restrict__ entries,
+                                                      const int* __restrict__ counts,
+                                                      const unsigned char* __restrict__ gflags, int cap,
+                                                      float4* __restrict__ out, int accumulate, POT pot,
+                                                      float rc2, float3 box, float3 inv) {
+    __shared__ float4 sx[WPB][2][32];
+    __shared__ float4 sp[WPB][2][32];
+    const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    if (warp >= ngroups) return;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int il = lane >> 2, jj = lane & 3;
+    const int i = warp*B2_GROUP + il;
+    const int ic = min(i, n - 1);
+    float4 xi = pos4[ic];
+    const float4 pi = par[ic];
+    // reference point of the group: its first atom
+    const float rx = __shfl_sync(FULL, xi.x, 0), ry = __shfl_sync(FULL, xi.y, 0), rz = __shfl_sync(FULL, xi.z, 0);
+    const bool minimg = gflags[warp] & 1;
+    if (!minimg) {
+        xi.x -= box.x*rintf((xi.x - rx)*inv.x);
+        xi.y -= box.y*rintf((xi.y - ry)*inv.y);
+        xi.z -= box.z*rintf((xi.z - rz)*inv.z);
+    }
+    const int cnt = counts[warp];
+    const int* __restrict__ base = entries + (size_t)warp*cap;
+    const int pad = (int)(0xff000000u | (unsigned)(warp*B2_GROUP));
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    int buf = 0;
+    // software pipeline: gather chunk c+1 while chunk c is being swept
+    int e = lane < cnt ? base[lane] : pad;
+    float4 xj = pos4[e & 0xffffff];
+    float4 pj = par[e & 0xffffff];
+    for (int c0 = 0; c0 < cnt; c0 += 32) {
+        if (!minimg) {
+            xj.x -= box.x*rintf((xj.x - rx)*inv.x);
+            xj.y -= box.y*rintf((xj.y - ry)*inv.y);
+            xj.z -= box.z*rintf((xj.z - rz)*inv.z);
+        }
+        pj.w = __int_as_float((int)((unsigned)e >> 24));
+        sx[wib][buf][lane] = xj;
+        sp[wib][buf][lane] = pj;
+        const int nxt = c0 + 32 + lane;
+        if (c0 + 32 < cnt) {
+            e = nxt < cnt ? base[nxt] : pad;
+            xj = pos4[e & 0xffffff];
+            pj = par[e & 0xffffff];
+        }
+        __syncwarp();
+        if (minimg)
+            sweep_chunk<POT, true>(pot, sx[wib][buf], sp[wib][buf], jj, il, xi, pi.x, pi.y, pi.z, rc2, box, inv, fx, fy, fz);
+        else
+            sweep_chunk<POT, false>(pot, sx[wib][buf], sp[wib][buf], jj, il, xi, pi.x, pi.y, pi.z, rc2, box, inv, fx, fy, fz);
+        buf ^= 1;
+    }
+    fx += __shfl_xor_sync(FULL, fx, 1); fy += __shfl_xor_sync(FULL, fy, 1); fz += __shfl_xor_sync(FULL, fz, 1);
+    fx += __shfl_xor_sync(FULL, fx, 2); fy += __shfl_xor_sync(FULL, fy, 2); fz += __shfl_xor_sync(FULL, fz, 2);
+    if (jj == 0 && i < n) {
+        float4 f = make_float4(fx, fy, fz, 0.f);
+        if (accumulate) {
+            const float4 o = out[i];
+            f.x += o.x; f.y += o.y; f.z += o.z;
+        }
+        out[i] = f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp64 energy / virial / dE/dlambda kernel (same list, per-pair minimum image, double state)
+// ---------------------------------------------------------------------------------------------
+template <class POT, bool SOFT>
+__global__ void __launch_bounds__(32*WPB) k_pair_energy(int n, int ngroups, const double* __restrict__ x,
+                                                       const double* __restrict__ pard,
+                                                       const int* __restrict__ entries,
+                                                       const int* __restrict__ counts, int cap, POT pot,
+                                                       double rc2, double bx, double by, double bz,
+                                                       double* __restrict__ acc /* e, w, dlv, dlc */) {
+    const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    double e_sum = 0, w_sum = 0, dv_sum = 0, dc_sum = 0;
+    if (warp < ngroups) {
+        const int il = lane >> 2, jj = lane & 3;
+        const int i = warp*B2_GROUP + il;
+        const int ic = min(i, n - 1);
+        const double xi = x[3*ic], yi = x[3*ic+1], zi = x[3*ic+2];
+        const double qi = pard[3*ic], si = pard[3*ic+1], ei = pard[3*ic+2];
+        const int cnt = counts[warp];
+        const int* __restrict__ base = entries + (size_t)warp*cap;
+        for (int k = jj; k < cnt; k += 4) {
+            const int en = base[k];
+            const int j = en & 0xffffff;
+            if (((unsigned)en >> (24 + il)) & 1u) continue;
+            double dx = xi - x[3*j], dy = yi - x[3*j+1], dz = zi - x[3*j+2];
+            dx -= bx*rint(dx/bx); dy -= by*rint(dy/by); dz -= bz*rint(dz/bz);
+            const double r2 = dx*dx + dy*dy + dz*dz;
+            if (r2 < rc2) {
+                double rF, e;
+                const double qq = qi*pard[3*j], sig = 0.5*(si + pard[3*j+1]), eps = sqrt(ei*pard[3*j+2]);
+                if constexpr (SOFT) {
+                    double dv, dc;
+                    pot.eval(r2, qq, sig, eps, rF, e, dv, dc);
+                    dv_sum += dv; dc_sum += dc;
+                } else {
+                    pot.template operator()<true>(r2, qq, sig, eps, rF, e);
+                }
+                e_sum += e; w_sum += rF;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        e_sum += __shfl_xor_sync(FULL, e_sum, o);
+        w_sum += __shfl_xor_sync(FULL, w_sum, o);
+        if (SOFT) {
+            dv_sum += __shfl_xor_sync(FULL, dv_sum, o);
+            dc_sum += __shfl_xor_sync(FULL, dc_sum, o);
+        }
+    }
+    if (lane == 0 && warp < ngroups) {
+        // every pair appears in both atoms' lists
+        atomicAdd(&acc[0], 0.5*e_sum);
+        atomicAdd(&acc[1], 0.5*w_sum);
+        if (SOFT) { atomicAdd(&acc[2], 0.5*dv_sum); atomicAdd(&acc[3], 0.5*dc_sum); }
+    }
+}
+
+// exact interacting pair set: i<j (caller numbering), r^2 < rc^2 in float64, not excluded
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30))*0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27))*0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(32*WPB) k_pair_set(int n, int ngroups, const double* __restrict__ x,
+                                                    const int* __restrict__ orig,
+                                                    const int* __restrict__ entries,
+                                                    const int* __restrict__ counts, int cap, double rc2,
+                                                    double bx, double by, double bz,
+                                                    unsigned long long* __restrict__ acc, int* pairs,
+                                                    long long capacity) {
+    const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= ngroups) return;
+    const int il = lane >> 2, jj = lane & 3;
+    const int i = warp*B2_GROUP + il;
+    if (i >= n) return;
+    const double xi = x[3*i], yi = x[3*i+1], zi = x[3*i+2];
+    const int oi = orig[i];
+    const int cnt = counts[warp];
+    const int* __restrict__ base = entries + (size_t)warp*cap;
+    unsigned long long c = 0, h = 0;
+    for (int k = jj; k < cnt; k += 4) {
+        const int en = base[k];
+        const int j = en & 0xffffff;
+        if (((unsigned)en >> (24 + il)) & 1u) continue;
+        const int oj = orig[j];
+        if (oj <= oi) continue;
+        double dx = x[3*j] - xi, dy = x[3*j+1] - yi, dz = x[3*j+2] - zi;
+        dx -= bx*rint(dx/bx); dy -= by*rint(dy/by); dz -= bz*rint(dz/bz);
+        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        if (r2 < rc2) {
+            c++;
+            h += mix64(((unsigned long long)oi << 32) | (unsigned)oj);
+            if (pairs) {
+                unsigned long long slot = atomicAdd(&acc[2], 1ull);
+                if ((long long)slot < capacity) { pairs[2*slot] = oi; pairs[2*slot+1] = oj; }
+            }
+        }
+    }
+    if (c) { atomicAdd(&acc[0], c); atomicAdd(&acc[1], h); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host dispatch
+// ---------------------------------------------------------------------------------------------
+template <class POT>
+static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, float rc2, float4* out, bool accumulate) {
+    const NList& L = ctx->lists[pf.list];
+    const float3 box = make_float3((float)ctx->box[0], (float)ctx->box[1], (float)ctx->box[2]);
+    const float3 inv = make_float3((float)(1.0/ctx->box[0]), (float)(1.0/ctx->box[1]), (float)(1.0/ctx->box[2]));
+    const int blocks = (ctx->ngroups + WPB - 1)/WPB;
+    k_pair_force<POT><<<blocks, 32*WPB, 0, ctx->stream>>>(ctx->n, ctx->ngroups, ctx->pos4, ctx->par[pf.set],
+                                                          L.entries, L.counts, L.gflags, L.cap, out,
+                                                          accumulate ? 1 : 0, pot, rc2, box, inv);
+    ctx->counters[2]++;
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+template <class POT, bool SOFT>
+static int launch_energy(b2_context* ctx, const PairForce& pf, POT pot, double rc2, double* acc) {
+    const NList& L = ctx->lists[pf.list];
+    const int blocks = (ctx->ngroups + WPB - 1)/WPB;
+    k_pair_energy<POT, SOFT><<<blocks, 32*WPB, 0, ctx->stream>>>(ctx->n, ctx->ngroups, ctx->x,
+                                                                  ctx->pard[pf.set], L.entries, L.counts,
+                                                                  L.cap, pot, rc2, ctx->box[0], ctx->box[1],
+                                                                  ctx->box[2], acc);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+#define DISPATCH(T, CALL_LJC, CALL_SOFT)                                                                    \
+    switch (pf.family) {                                                                                    \
+    case B2_PAIR_NEAR: {                                                                                    \
+        const int v = (int)pf.params[0];                                                                    \
+        if (v == 0) { LJCPot<COUL_PLAIN, LJ_STD, SW_ALL, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; }        \
+        else if (v == 1) { LJCPot<COUL_PLAIN, LJ_STD, SW_ALL, SWF_LINEAR, VAR_SHIFT, T> pot{p}; CALL_LJC; }  \
+        else { LJCPot<COUL_PLAIN, LJ_STD, SW_ALL, SWF_LINEAR, VAR_FSWITCH, T> pot{p}; CALL_LJC; }            \
+        break;                                                                                              \
+    }                                                                                                       \
+    case B2_PAIR_DAMPED:                                                                                    \
+        if ((int)pf.params[3] == 1) { LJCPot<COUL_ERFC, LJ_STD, SW_ALL, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; } \
+        else { LJCPot<COUL_ERFC, LJ_STD, SW_ALL, SWF_POWER, VAR_NONE, T> pot{p}; CALL_LJC; }                 \
+        break;                                                                                              \
+    case B2_PAIR_LJC: {                                                                                     \
+        const int ck = (int)pf.params[1];                                                                   \
+        if (ck == 2) { LJCPot<COUL_RF, LJ_STD, SW_LJ, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; }           \
+        else if (ck == 3) { LJCPot<COUL_ERFC, LJ_STD, SW_LJ, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; }    \
+        else { LJCPot<COUL_PLAIN, LJ_STD, SW_LJ, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; }                \
+        break;                                                                                              \
+    }                                                                                                       \
+    case B2_PAIR_LJ_VIRIAL: { LJCPot<COUL_NONE, LJ_VIRIAL, SW_ALL, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; break; } \
+    case B2_PAIR_SOFTCORE: { SoftcorePot<T> pot{p}; CALL_SOFT; break; }                                      \
+    default: return b2_fail(ctx, B2_ERR_UNSUPPORTED, "unknown pair family %d", pf.family);                  \
+    }
+
+int pair_eval_forces(b2_context* ctx, const PairForce& pf, float4* out, bool accumulate) {
+    float rc2;
+    PotParams<float> p = make_params<float>(pf, &rc2);
+    DISPATCH(float, B2_TRY(launch_force(ctx, pf, pot, rc2, out, accumulate)),
+             B2_TRY(launch_force(ctx, pf, pot, rc2, out, accumulate)));
+    return B2_OK;
+}
+
+int pair_eval_energy(b2_context* ctx, const PairForce& pf, int group) {
+    float rc2f;
+    PotParams<double> p = make_params<double>(pf, &rc2f);
+    double rc = pf.cutoff;
+    if (pf.family == B2_PAIR_NEAR) rc = std::min(rc, pf.params[2]);
+    if (pf.family == B2_PAIR_DAMPED) rc = std::min(rc, pf.params[2]);
+    const double rc2 = rc*rc;
+    // accumulator block: [0] e, [1] w, [2] dlv, [3] dlc  (scratch at d_energy+72), folded by caller
+    double* acc = ctx->d_energy + 72;
+    B2_CUDA(cudaMemsetAsync(acc, 0, 4*sizeof(double), ctx->stream));
+    DISPATCH(double, B2_TRY((launch_energy<decltype(pot), false>(ctx, pf, pot, rc2, acc))),
+             B2_TRY((launch_energy<decltype(pot), true>(ctx, pf, pot, rc2, acc))));
+    (void)group;
+    return B2_OK;
+}
+
+int pair_count_set(b2_context* ctx, const PairForce& pf, long long* count, unsigned long long* checksum,
+                   int* pairs_dev, long long capacity) {
+    const NList& L = ctx->lists[pf.list];
+    double rc = pf.cutoff;
+    if (pf.family == B2_PAIR_NEAR || pf.family == B2_PAIR_DAMPED) rc = std::min(rc, pf.params[2]);
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(ctx->d_energy + 76);
+    B2_CUDA(cudaMemsetAsync(acc, 0, 3*sizeof(unsigned long long), ctx->stream));
+    const int blocks = (ctx->ngroups + WPB - 1)/WPB;
+    k_pair_set<<<blocks, 32*WPB, 0, ctx->stream>>>(ctx->n, ctx->ngroups, ctx->x, ctx->orig, L.entries, L.counts,
+                                                    L.cap, rc*rc, ctx->box[0], ctx->box[1], ctx->box[2], acc,
+                                                    pairs_dev, capacity);
+    B2_LAUNCH_CHECK();
+    unsigned long long h[3];
+    B2_CUDA(cudaMemcpyAsync(h, acc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    *count = (long long)h[0];
+    *checksum = h[1];
+    return B2_OK;
+}

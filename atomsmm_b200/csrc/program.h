@@ -1,0 +1,48 @@
+// Lowered integrator program: op records and VM opcodes shared by host and device code.
+// The Python front end (atomsmm_b200/lowering.py, expr.py) emits exactly these numbers.
+#pragma once
+
+struct b2_op {
+    int kind;
+    int a, b, c, d, e, f, g;
+};
+
+enum {
+    // target[dof] = eval(code) for every degree of freedom.
+    //   a: target variable (0 x, 1 v, 2+k user per-DOF k)   b: code offset (ints)   c: code length
+    //   d: 1 if the expression draws random numbers          e: op serial (RNG stream id)
+    B2_OP_PERDOF = 1,
+    // globals[a] = sum over DOFs of eval(code).   b, c as above
+    B2_OP_SUM = 2,
+    // scalar program (assignments to globals, if/while on globals).   b, c as above
+    B2_OP_GLOBAL = 3,
+    // make force slot b valid for the current positions.   a: force-group mask
+    B2_OP_EVAL = 4,
+    // v += g[a] * (s0*f[b] + s1*f[c]) / m    fast kick.  d: packed signs (bit0 s0<0, bit1 s1<0,
+    //   bit2: second term present)
+    B2_OP_KICK = 5,
+    // x += g[a] * v                          fast drift
+    B2_OP_DRIFT = 6,
+    // v *= g[a]                              fast scale
+    B2_OP_SCALE = 7,
+    // UpdateContextState hook (no-op: no barostat / CMMotionRemover in the engine yet)
+    B2_OP_UPDATE_STATE = 8,
+    // energies of groups in mask a -> device energy slots (used by `energy` / deriv(energy,.))
+    B2_OP_ENERGY = 9,
+    // fused RESPA inner loop: see integrate.cu.  a: iterations, b: g-index of kick coefficient,
+    //   c: g-index of drift coefficient, d: force slot of the inner group
+    B2_OP_FUSED_INNER = 10,
+};
+
+// VM opcodes (two ints per instruction: opcode, argument)
+enum {
+    VM_PUSHC = 0, VM_PUSHG = 1, VM_PUSHV = 2, VM_GAUSS = 3, VM_UNIF = 4, VM_ADD = 5, VM_SUB = 6,
+    VM_MUL = 7, VM_DIV = 8, VM_NEG = 9, VM_POW = 10, VM_POWI = 11, VM_SQRT = 12, VM_EXP = 13,
+    VM_LOG = 14, VM_SIN = 15, VM_COS = 16, VM_TAN = 17, VM_ERF = 18, VM_ERFC = 19, VM_ABS = 20,
+    VM_MIN = 21, VM_MAX = 22, VM_STEP = 23, VM_DELTA = 24, VM_SELECT = 25, VM_FLOOR = 26,
+    VM_CEIL = 27, VM_PUSHM = 28, VM_PUSHF = 29, VM_DERIV = 30, VM_STOREG = 31, VM_JMP = 32,
+    VM_JMPZ = 33, VM_CMP = 34, VM_PUSHE = 35,
+};
+
+#define B2_MAX_PERDOF 14
+#define B2_VM_STACK 24

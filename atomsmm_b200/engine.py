@@ -1,0 +1,692 @@
+"""
+``Context`` / ``State``: the execution side of the description layer, bound to the CUDA engine
+through the ctypes C ABI (include/atomsmm_b200.h).
+
+Mirrors the slice of ``openmm.Context`` / ``openmm.State`` that atomsmm and its tests use
+(reference call sites: computers.py:67-88,242-246; utils.py:153-186,219-228;
+tests/test_respa_forces.py:20-26).  State lives in torch CUDA tensors (double [N,3], caller's atom
+order); the library works on device pointers taken from them.  There is NO CPU path: if the
+shared library is missing or no CUDA device is present, construction raises.
+"""
+
+import ctypes
+import math
+import os
+
+import numpy as np
+
+from . import lowering
+from . import mm
+from . import unit
+from .unit import md_value as _md
+
+_LIB = None
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libatomsmm_b200.so')
+
+c_int_p = ctypes.POINTER(ctypes.c_int)
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_void = ctypes.c_void_p
+
+_SIGNATURES = {
+    'b2_create': [ctypes.c_int, ctypes.POINTER(c_void)],
+    'b2_destroy': [c_void],
+    'b2_set_stream': [c_void, c_void],
+    'b2_synchronize': [c_void],
+    'b2_set_box': [c_void, c_double_p, ctypes.c_int],
+    'b2_set_particles': [c_void, ctypes.c_int, c_double_p, c_int_p],
+    'b2_add_param_set': [c_void, c_double_p, c_double_p, c_double_p, c_int_p],
+    'b2_set_exclusions': [c_void, ctypes.c_int, c_int_p],
+    'b2_add_pair_force': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_double_p,
+                          ctypes.c_int, ctypes.c_double, c_int_p],
+    'b2_update_pair_force': [c_void, ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_double],
+    'b2_add_bonded_force': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p, c_double_p, ctypes.c_int,
+                            ctypes.c_int, c_double_p, ctypes.c_int, c_int_p],
+    'b2_add_custom_bonded_force': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p, c_double_p,
+                                   ctypes.c_int, ctypes.c_int, c_int_p, ctypes.c_int, c_int_p, ctypes.c_int,
+                                   c_double_p, ctypes.c_int, c_int_p],
+    'b2_set_skin': [c_void, ctypes.c_double],
+    'b2_set_positions': [c_void, c_void],
+    'b2_set_velocities': [c_void, c_void],
+    'b2_get_positions': [c_void, c_void],
+    'b2_get_velocities': [c_void, c_void],
+    'b2_eval': [c_void, ctypes.c_uint32, ctypes.c_int, c_void, c_double_p, c_double_p],
+    'b2_get_group_energies': [c_void, c_double_p, c_double_p],
+    'b2_get_parameter_derivatives': [c_void, c_double_p],
+    'b2_pair_set': [c_void, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_ulonglong),
+                    c_void, ctypes.c_longlong],
+    'b2_load_program': [c_void, c_int_p, ctypes.c_int, c_int_p, ctypes.c_int, c_double_p, ctypes.c_int,
+                        c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64],
+    'b2_set_globals': [c_void, ctypes.c_int, ctypes.c_int, c_double_p],
+    'b2_get_globals': [c_void, ctypes.c_int, ctypes.c_int, c_double_p],
+    'b2_set_perdof': [c_void, ctypes.c_int, c_void],
+    'b2_get_perdof': [c_void, ctypes.c_int, c_void],
+    'b2_run': [c_void, ctypes.c_int],
+    'b2_get_counters': [c_void, ctypes.POINTER(ctypes.c_longlong)],
+}
+
+
+class EngineError(mm.OpenMMException):
+    pass
+
+
+def library():
+    """Load libatomsmm_b200.so (built in-tree by ``python -m atomsmm_b200.build``)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_LIB_PATH):
+            raise EngineError('CUDA engine library not found at %s: run `python -m atomsmm_b200.build`. '
+                              'There is no CPU fallback.' % _LIB_PATH)
+        lib = ctypes.CDLL(_LIB_PATH)
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_int
+        lib.b2_last_error.argtypes = [c_void]
+        lib.b2_last_error.restype = ctypes.c_char_p
+        lib.b2_version.restype = ctypes.c_char_p
+        _LIB = lib
+    return _LIB
+
+
+def _dptr(array):
+    return np.ascontiguousarray(array, dtype=np.float64).ctypes.data_as(c_double_p)
+
+
+def _iptr(array):
+    return np.ascontiguousarray(array, dtype=np.int32).ctypes.data_as(c_int_p)
+
+
+def _molecules(system):
+    """Connected components of the bond/constraint graph (Context.getMolecules)."""
+    n = system.getNumParticles()
+    parent = list(range(n))
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    def union(a, b):
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            parent[max(ra, rb)] = min(ra, rb)
+    for force in system.getForces():
+        if isinstance(force, mm.HarmonicBondForce):
+            for i, j, _, _ in force._bonds:
+                union(i, j)
+        elif isinstance(force, mm.CustomBondForce):
+            for i, j, _ in force._bonds:
+                union(i, j)
+        elif isinstance(force, mm.HarmonicAngleForce):
+            for i, j, k, _, _ in force._angles:
+                union(i, j)
+                union(j, k)
+        elif isinstance(force, mm.CustomAngleForce):
+            for i, j, k, _ in force._angles:
+                union(i, j)
+                union(j, k)
+        elif isinstance(force, mm.PeriodicTorsionForce):
+            for t in force._torsions:
+                union(t[0], t[1])
+                union(t[1], t[2])
+                union(t[2], t[3])
+    for i, j, _ in system._constraints:
+        union(i, j)
+    roots = {}
+    molecule = np.empty(n, dtype=np.int32)
+    for i in range(n):
+        r = find(i)
+        molecule[i] = roots.setdefault(r, len(roots))
+    groups = [[] for _ in range(len(roots))]
+    for i in range(n):
+        groups[molecule[i]].append(i)
+    return molecule, groups
+
+
+class State(object):
+    def __init__(self, **fields):
+        self.__dict__.update(fields)
+
+    def _vectors(self, array, asNumpy, u):
+        if array is None:
+            raise mm.OpenMMException('Invoked a State getter for data that was not requested')
+        if asNumpy:
+            return unit.Quantity(array.copy(), u)
+        return unit.Quantity([mm.Vec3(*row) for row in array], u)
+
+    def getPositions(self, asNumpy=False):
+        return self._vectors(self._positions, asNumpy, unit.nanometer)
+
+    def getVelocities(self, asNumpy=False):
+        return self._vectors(self._velocities, asNumpy, unit.nanometer/unit.picosecond)
+
+    def getForces(self, asNumpy=False):
+        return self._vectors(self._forces, asNumpy, unit.kilojoule_per_mole/unit.nanometer)
+
+    def getPotentialEnergy(self):
+        if self._potential is None:
+            raise mm.OpenMMException('Invoked getPotentialEnergy() on a State which does not contain energies')
+        return self._potential*unit.kilojoule_per_mole
+
+    def getKineticEnergy(self):
+        if self._kinetic is None:
+            raise mm.OpenMMException('Invoked getKineticEnergy() on a State which does not contain energies')
+        return self._kinetic*unit.kilojoule_per_mole
+
+    def getPeriodicBoxVectors(self, asNumpy=False):
+        b = self._box
+        vectors = [mm.Vec3(b[0], 0, 0), mm.Vec3(0, b[1], 0), mm.Vec3(0, 0, b[2])]
+        if asNumpy:
+            return unit.Quantity(np.array(vectors), unit.nanometer)
+        return unit.Quantity(vectors, unit.nanometer)
+
+    def getPeriodicBoxVolume(self):
+        return float(np.prod(self._box))*unit.nanometer**3
+
+    def getParameters(self):
+        return dict(self._parameters)
+
+    def getEnergyParameterDerivatives(self):
+        return dict(self._derivatives)
+
+    def getTime(self):
+        return self._time*unit.picosecond
+
+
+class Context(object):
+    """Execution context on one B200.  ``properties``: 'DeviceIndex' (default 0 or LOCAL_RANK),
+    'Skin' (neighbour-list skin in nm, default 0.1), 'FastPaths' ('false' routes every per-DOF step
+    through the generic VM)."""
+
+    def __init__(self, system, integrator, platform=None, properties=None):
+        import torch
+        self._torch = torch
+        properties = dict(properties or {})
+        if platform is not None and platform.getName() not in mm.Platform._NAMES:
+            raise mm.OpenMMException('unknown platform %s' % platform.getName())
+        self._lib = library()
+        if not torch.cuda.is_available():
+            raise EngineError('no CUDA device is visible: the atomsmm_b200 engine has no CPU path')
+        index = int(properties.get('DeviceIndex', os.environ.get('LOCAL_RANK', 0)))
+        self._device = torch.device('cuda', index)
+        self._system = system
+        self._integrator = integrator
+        self._n = n = system.getNumParticles()
+        self._time = 0.0
+        self._handle = c_void()
+        self._check(self._lib.b2_create(index, ctypes.byref(self._handle)), None)
+        self._stream = torch.cuda.Stream(device=self._device)
+        self._call('b2_set_stream', c_void(self._stream.cuda_stream))
+        self._skin = float(properties.get('Skin', 0.1))
+        self._fast = str(properties.get('FastPaths', 'true')).lower() != 'false'
+        self._call('b2_set_skin', self._skin)
+        box = _md(system.getDefaultPeriodicBoxVectors())
+        self._box = np.array([box[0][0], box[1][1], box[2][2]], dtype=np.float64)
+        self._periodic = system.usesPeriodicBoundaryConditions()
+        self._parameters = {}
+        for force in system.getForces():
+            if hasattr(force, 'getNumGlobalParameters'):
+                for k in range(force.getNumGlobalParameters()):
+                    self._parameters.setdefault(force.getGlobalParameterName(k), force.getGlobalParameterDefaultValue(k))
+        self._molecule, self._molecule_groups = _molecules(system)
+        self._masses = np.array([_md(system.getParticleMass(i)) for i in range(n)], dtype=np.float64)
+        self._x = torch.zeros((n, 3), dtype=torch.float64, device=self._device)
+        self._buffer = torch.zeros((n, 3), dtype=torch.float64, device=self._device)
+        self._have_positions = False
+        self._pair_handles = {}        # id(force) -> (handle, info)
+        self._describe()
+        self._program = None
+        if integrator is not None:
+            if getattr(integrator, '_context', None) is not None:
+                raise mm.OpenMMException('This Integrator is already bound to a context')
+            integrator._context = self
+            self._load_program()
+
+    # -- plumbing --------------------------------------------------------------------------------
+    def _check(self, code, handle):
+        if code != 0:
+            message = self._lib.b2_last_error(handle)
+            raise EngineError('%s (code %d)' % (message.decode() if message else 'engine error', code))
+
+    def _call(self, name, *args):
+        self._check(getattr(self._lib, name)(self._handle, *args), self._handle)
+
+    def __del__(self):
+        try:
+            if getattr(self, '_handle', None) is not None and self._handle.value:
+                self._lib.b2_destroy(self._handle)
+                self._handle = c_void()
+        except Exception:
+            pass
+
+    # -- description -> C ABI ----------------------------------------------------------------------
+    def _describe(self):
+        system, n = self._system, self._n
+        if system.getNumConstraints() > 0:
+            self._has_constraints = True
+        else:
+            self._has_constraints = False
+        self._call('b2_set_box', _dptr(self._box), 1 if self._periodic else 0)
+        self._call('b2_set_particles', n, _dptr(self._masses), _iptr(self._molecule))
+        exclusions = None
+        self._all_groups = 0
+        volume = float(np.prod(self._box))
+        for force in system.getForces():
+            group = force.getForceGroup()
+            if isinstance(force, mm.CMMotionRemover):
+                continue
+            self._all_groups |= 1 << group
+            if isinstance(force, mm.CustomNonbondedForce):
+                if force.getNumParticles() != n:
+                    raise mm.OpenMMException('CustomNonbondedForce must have exactly as many particles as the System')
+                family, cutoff, params, info = lowering.classify_pair_force(force, self._parameters)
+                table = np.array(force._particles, dtype=np.float64).reshape(n, -1)
+                pairs = frozenset((min(i, j), max(i, j)) for i, j in force._exclusions)
+                exclusions = self._merge_exclusions(exclusions, pairs)
+                set_id = self._param_set(table[:, 0], table[:, 1], table[:, 2])
+                econst = 0.0
+                if force.getUseLongRangeCorrection():
+                    econst = self._custom_lrc(force, family, params, table, cutoff, volume)
+                handle = ctypes.c_int()
+                p = np.array(params, dtype=np.float64)
+                self._call('b2_add_pair_force', family, group, set_id, cutoff, _dptr(p), len(p), econst,
+                           ctypes.byref(handle))
+                self._pair_handles[id(force)] = (handle.value, info, force)
+            elif isinstance(force, mm.NonbondedForce):
+                if force.getNumParticles() == 0:
+                    continue
+                if force.getNumParticles() != n:
+                    raise mm.OpenMMException('NonbondedForce must have exactly as many particles as the System')
+                exclusions = self._describe_nonbonded(force, exclusions, volume)
+            elif isinstance(force, mm.HarmonicBondForce):
+                if force.getNumBonds():
+                    atoms = np.array([[b[0], b[1]] for b in force._bonds], dtype=np.int32)
+                    params = np.array([[b[2], b[3]] for b in force._bonds], dtype=np.float64)
+                    self._add_bonded(lowering.BOND_HARMONIC, group, atoms, params, force.usesPeriodicBoundaryConditions())
+            elif isinstance(force, mm.HarmonicAngleForce):
+                if force.getNumAngles():
+                    atoms = np.array([a[:3] for a in force._angles], dtype=np.int32)
+                    params = np.array([a[3:5] for a in force._angles], dtype=np.float64)
+                    self._add_bonded(lowering.ANGLE_HARMONIC, group, atoms, params, force.usesPeriodicBoundaryConditions())
+            elif isinstance(force, mm.PeriodicTorsionForce):
+                if force.getNumTorsions():
+                    atoms = np.array([t[:4] for t in force._torsions], dtype=np.int32)
+                    params = np.array([[t[4], t[5], t[6]] for t in force._torsions], dtype=np.float64)
+                    self._add_bonded(lowering.TORSION_PERIODIC, group, atoms, params, force.usesPeriodicBoundaryConditions())
+            elif isinstance(force, mm.CustomBondForce):
+                if force.getNumBonds():
+                    atoms = np.array([[b[0], b[1]] for b in force._bonds], dtype=np.int32)
+                    params = np.array([b[2] for b in force._bonds], dtype=np.float64).reshape(len(atoms), -1)
+                    family, gparams, code = lowering.classify_bond_force(force, self._parameters)
+                    periodic = force.usesPeriodicBoundaryConditions()
+                    if family == lowering.BOND_LJC:
+                        params = np.concatenate([params, np.zeros((len(atoms), 1))], axis=1)
+                        self._add_bonded(family, group, atoms, params, periodic, gparams)
+                    else:
+                        self._add_custom(lowering.BOND_CUSTOM, group, atoms, params, periodic, code)
+            elif isinstance(force, mm.CustomAngleForce):
+                if force.getNumAngles():
+                    from . import expr as X
+                    atoms = np.array([a[:3] for a in force._angles], dtype=np.int32)
+                    params = np.array([a[3] for a in force._angles], dtype=np.float64).reshape(len(atoms), -1)
+                    names = [force.getPerAngleParameterName(k) for k in range(force.getNumPerAngleParameters())]
+                    globals_ = {force.getGlobalParameterName(k): self._parameters[force.getGlobalParameterName(k)]
+                                for k in range(force.getNumGlobalParameters())}
+                    code = lowering.compile_custom(X.parse_inlined(force.getEnergyFunction()), 'theta', names, globals_)
+                    self._add_custom(lowering.ANGLE_CUSTOM, group, atoms, params, force.usesPeriodicBoundaryConditions(), code)
+            else:
+                raise lowering.UnsupportedDescription('force class %s is not supported' % type(force).__name__)
+        if exclusions is not None:
+            pairs = np.array(sorted(exclusions), dtype=np.int32).reshape(-1, 2)
+            self._call('b2_set_exclusions', len(pairs), _iptr(pairs))
+
+    @staticmethod
+    def _merge_exclusions(current, new):
+        if current is not None and current != new:
+            raise lowering.UnsupportedDescription('all pair forces of a System must share one exclusion list')
+        return new
+
+    def _param_set(self, q, sigma, eps):
+        set_id = ctypes.c_int()
+        self._call('b2_add_param_set', _dptr(q), _dptr(sigma), _dptr(eps), ctypes.byref(set_id))
+        return set_id.value
+
+    def _add_bonded(self, family, group, atoms, params, periodic, gparams=None):
+        g = np.array(gparams if gparams is not None else [0.0], dtype=np.float64)
+        handle = ctypes.c_int()
+        self._call('b2_add_bonded_force', family, group, len(atoms), _iptr(atoms), _dptr(params), params.shape[1],
+                   1 if periodic else 0, _dptr(g), len(g), ctypes.byref(handle))
+
+    def _add_custom(self, family, group, atoms, params, periodic, code):
+        handle = ctypes.c_int()
+        consts = np.array(code['consts'] if code['consts'] else [0.0], dtype=np.float64)
+        if params.shape[1] == 0:
+            params = np.zeros((len(atoms), 1))
+            stride = 0
+        else:
+            stride = params.shape[1]
+        self._call('b2_add_custom_bonded_force', family, group, len(atoms), _iptr(atoms), _dptr(params), stride,
+                   1 if periodic else 0, _iptr(np.array(code['code_e'] or [0, 0])), code['n_e'],
+                   _iptr(np.array(code['code_de'] or [0, 0])), code['n_de'], _dptr(consts), len(code['consts']),
+                   ctypes.byref(handle))
+
+    def _classes(self, sigma, eps):
+        table = np.stack([sigma, eps], axis=1)
+        classes, counts = np.unique(table, axis=0, return_counts=True)
+        return [tuple(c) for c in classes], [int(c) for c in counts]
+
+    def _custom_lrc(self, force, family, params, table, cutoff, volume):
+        if family != lowering.PAIR_LJ_VIRIAL:
+            raise lowering.UnsupportedDescription('long-range correction is only supported for the LJ families')
+        classes, counts = self._classes(table[:, 1], table[:, 2])
+        rs = force.getSwitchingDistance().value_in_md_units() if force.getUseSwitchingFunction() else None
+        return lowering.long_range_correction(classes, counts,
+                                              lambda r, s, e: 24*e*(2*(s/r)**12 - (s/r)**6), cutoff, rs, volume)
+
+    def _describe_nonbonded(self, force, exclusions, volume):
+        """openmm.NonbondedForce: pair part + exception pairs (+ reciprocal space: not yet)."""
+        NB = mm.NonbondedForce
+        method = force.getNonbondedMethod()
+        n = self._n
+        group = force.getForceGroup()
+        table = np.array(force._particles, dtype=np.float64).reshape(n, 3)
+        kc = 138.935456
+        cutoff = force.getCutoffDistance().value_in_md_units()
+        use_switch = force.getUseSwitchingFunction()
+        rswitch = force.getSwitchingDistance().value_in_md_units()
+        alpha = 0.0
+        if method in (NB.NoCutoff, NB.CutoffNonPeriodic):
+            raise lowering.UnsupportedDescription('NonbondedForce needs a periodic cutoff method on this engine')
+        if method == NB.CutoffPeriodic:
+            es = force.getReactionFieldDielectric()
+            krf = (es - 1)/((2*es + 1)*cutoff**3)
+            crf = 3*es/((2*es + 1)*cutoff)
+            params = [kc, 2.0, krf, crf, 0.0, float(use_switch), rswitch, cutoff]
+        else:
+            a, nx, ny, nz = force._pme
+            tol = force.getEwaldErrorTolerance()
+            alpha = a if a != 0.0 else math.sqrt(-math.log(2*tol))/cutoff
+            params = [kc, 3.0, 0.0, 0.0, alpha, float(use_switch), rswitch, cutoff]
+            self._reciprocal_missing = True
+            rgroup = force.getReciprocalSpaceForceGroup()
+            self._reciprocal_group = group if rgroup < 0 else rgroup
+        pairs = frozenset((min(e[0], e[1]), max(e[0], e[1])) for e in force._exceptions)
+        exclusions = self._merge_exclusions(exclusions, pairs)
+        set_id = self._param_set(table[:, 0], table[:, 1], table[:, 2])
+        econst = 0.0
+        if force.getUseDispersionCorrection():
+            classes, counts = self._classes(table[:, 1], table[:, 2])
+            econst = lowering.long_range_correction(
+                classes, counts, lambda r, s, e: 4*e*((s/r)**12 - (s/r)**6), cutoff, rswitch if use_switch else None, volume)
+        handle = ctypes.c_int()
+        p = np.array(params, dtype=np.float64)
+        self._call('b2_add_pair_force', lowering.PAIR_LJC, group, set_id, cutoff, _dptr(p), len(p), econst,
+                   ctypes.byref(handle))
+        self._pair_handles[id(force)] = (handle.value, dict(name='nonbonded'), force)
+        # exceptions: own LJ + bare Coulomb, and under Ewald the erf correction with particle charges
+        exc = [e for e in force._exceptions if alpha > 0 or e[2] != 0.0 or e[4] != 0.0]
+        if exc:
+            atoms = np.array([[e[0], e[1]] for e in exc], dtype=np.int32)
+            q = table[:, 0]
+            params = np.array([[e[2], e[3], e[4], q[e[0]]*q[e[1]]] for e in exc], dtype=np.float64)
+            self._add_bonded(lowering.BOND_LJC, group, atoms, params, True, [kc, alpha])
+        return exclusions
+
+    # -- integrator ------------------------------------------------------------------------------
+    def _load_program(self):
+        integrator = self._integrator
+        if not isinstance(integrator, mm.CustomIntegrator):
+            self._program = None
+            return
+        if self._has_constraints and integrator.getNumComputations() > 0:
+            raise lowering.UnsupportedDescription('Systems with distance constraints cannot be integrated yet '
+                                                  '(SHAKE/RATTLE/SETTLE are not implemented)')
+        program = lowering.lower_program(integrator, self._all_groups, self._parameters, self._fast)
+        self._program = program
+        ops = program.packed_ops()
+        code = np.array(program.bc.code if program.bc.code else [0, 0], dtype=np.int32)
+        consts = np.array(program.bc.consts if program.bc.consts else [0.0], dtype=np.float64)
+        values = np.array(program.global_values, dtype=np.float64)
+        self._call('b2_load_program', _iptr(ops), len(ops), _iptr(code), len(program.bc.code), _dptr(consts),
+                   len(program.bc.consts), _dptr(values), len(values), len(program.perdof_names),
+                   ctypes.c_uint64(integrator.getRandomNumberSeed() & 0xffffffffffffffff))
+        for k, value in enumerate(integrator._perdof_values):
+            if not np.isscalar(value) and self._have_positions:
+                self._set_perdof(integrator._perdof_names[k], value)
+            elif np.isscalar(value) and value != 0.0 and self._have_positions:
+                self._set_perdof(integrator._perdof_names[k], np.full((self._n, 3), float(value)))
+
+    def _integrator_changed(self):
+        if self._program is not None:
+            self._set_global('dt', self._integrator._dt)
+
+    def _get_global(self, name):
+        out = ctypes.c_double()
+        self._call('b2_get_globals', self._program.gindex(name), 1, ctypes.byref(out))
+        return out.value
+
+    def _set_global(self, name, value):
+        v = ctypes.c_double(float(value))
+        self._call('b2_set_globals', self._program.gindex(name), 1, ctypes.byref(v))
+
+    def _get_perdof(self, name):
+        torch = self._torch
+        with torch.cuda.stream(self._stream):
+            self._call('b2_get_perdof', self._program.perdof_names.index(name), c_void(self._buffer.data_ptr()))
+            self._call('b2_synchronize')
+            return [mm.Vec3(*row) for row in self._buffer.cpu().numpy()]
+
+    def _set_perdof(self, name, array):
+        torch = self._torch
+        if not self._have_positions:
+            return   # applied by _load_program/_after_positions once an order exists
+        with torch.cuda.stream(self._stream):
+            t = torch.as_tensor(np.ascontiguousarray(array, dtype=np.float64)).to(self._device)
+            self._call('b2_set_perdof', self._program.perdof_names.index(name), c_void(t.data_ptr()))
+            self._call('b2_synchronize')
+
+    def _step(self, steps):
+        if self._program is None:
+            raise mm.OpenMMException('this integrator cannot take steps on the B200 engine')
+        if not self._have_positions:
+            raise mm.OpenMMException('Particle positions have not been set')
+        self._call('b2_run', steps)
+        self._time += steps*self._integrator._dt
+
+    def _parameters_changed(self, force):
+        entry = self._pair_handles.get(id(force))
+        if entry is None:
+            raise lowering.UnsupportedDescription('updateParametersInContext is only supported for pair forces')
+        handle, info, _ = entry
+        family, cutoff, params, _ = lowering.classify_pair_force(force, self._parameters)
+        p = np.array(params, dtype=np.float64)
+        self._call('b2_update_pair_force', handle, _dptr(p), len(p), 0.0)
+
+    # -- public API --------------------------------------------------------------------------------
+    def getSystem(self):
+        return self._system
+
+    def getIntegrator(self):
+        return self._integrator
+
+    def getPlatform(self):
+        return mm.Platform('B200')
+
+    def getMolecules(self):
+        return [tuple(g) for g in self._molecule_groups]
+
+    def getParameter(self, name):
+        return self._parameters[name]
+
+    def getParameters(self):
+        return dict(self._parameters)
+
+    def setParameter(self, name, value):
+        if name not in self._parameters:
+            raise mm.OpenMMException('Called setParameter() with invalid parameter name: %s' % name)
+        self._parameters[name] = float(_md(value))
+        for handle, info, force in self._pair_handles.values():
+            if hasattr(force, 'getNumGlobalParameters') and any(
+                    force.getGlobalParameterName(k) == name for k in range(force.getNumGlobalParameters())):
+                family, cutoff, params, _ = lowering.classify_pair_force(force, self._parameters)
+                p = np.array(params, dtype=np.float64)
+                self._call('b2_update_pair_force', handle, _dptr(p), len(p), 0.0)
+        if self._program is not None and name in self._program.global_names:
+            self._set_global(name, self._parameters[name])
+
+    def setPeriodicBoxVectors(self, a, b, c):
+        box = np.array([_md(a)[0], _md(b)[1], _md(c)[2]], dtype=np.float64)
+        if not np.allclose(box, self._box, rtol=0, atol=1e-12):
+            raise lowering.UnsupportedDescription('changing the box of a live context is not supported yet')
+
+    def _upload(self, values, what):
+        torch = self._torch
+        if isinstance(values, torch.Tensor):
+            t = values.to(device=self._device, dtype=torch.float64).reshape(self._n, 3).contiguous()
+        else:
+            array = np.asarray(_md(values), dtype=np.float64).reshape(-1, 3)
+            if array.shape[0] != self._n:
+                raise mm.OpenMMException('Called set%s() on a Context with the wrong number of %s' % (what, what.lower()))
+            t = torch.from_numpy(np.ascontiguousarray(array)).to(self._device, non_blocking=False)
+        return t
+
+    def setPositions(self, positions):
+        torch = self._torch
+        with torch.cuda.stream(self._stream):
+            t = self._upload(positions, 'Positions')
+            self._x.copy_(t)
+            self._call('b2_set_positions', c_void(self._x.data_ptr()))
+            first = not self._have_positions
+            self._have_positions = True
+            if first and self._program is not None:
+                for k, value in enumerate(self._integrator._perdof_values):
+                    if not np.isscalar(value):
+                        self._set_perdof(self._integrator._perdof_names[k], value)
+                    elif value != 0.0:
+                        self._set_perdof(self._integrator._perdof_names[k], np.full((self._n, 3), float(value)))
+
+    def setVelocities(self, velocities):
+        torch = self._torch
+        if not self._have_positions:
+            raise mm.OpenMMException('set positions before velocities on this engine')
+        with torch.cuda.stream(self._stream):
+            t = self._upload(velocities, 'Velocities')
+            self._call('b2_set_velocities', c_void(t.data_ptr()))
+            self._call('b2_synchronize')
+
+    def setVelocitiesToTemperature(self, temperature, randomSeed=None):
+        """Maxwell-Boltzmann velocities (numpy Philox stream; OpenMM's SFMT stream is not
+        reproducible outside OpenMM)."""
+        kT = 8.314472471220217e-3*float(_md(temperature))
+        rng = np.random.Generator(np.random.Philox(randomSeed if randomSeed is not None else None))
+        v = rng.standard_normal((self._n, 3))
+        with np.errstate(divide='ignore'):
+            scale = np.where(self._masses > 0, np.sqrt(kT/np.where(self._masses > 0, self._masses, 1.0)), 0.0)
+        self.setVelocities(v*scale[:, None])
+
+    def setState(self, state):
+        self.setPositions(state.getPositions(asNumpy=True))
+        if state._velocities is not None:
+            self.setVelocities(state.getVelocities(asNumpy=True))
+
+    def reinitialize(self, preserveState=False):
+        raise lowering.UnsupportedDescription('reinitialize() is not supported: create a new Context')
+
+    @staticmethod
+    def _mask(groups):
+        if isinstance(groups, (set, frozenset, list, tuple)):
+            mask = 0
+            for g in groups:
+                mask |= 1 << int(g)
+            return mask
+        mask = int(groups)
+        return 0xffffffff if mask == -1 else mask & 0xffffffff
+
+    def getState(self, getPositions=False, getVelocities=False, getForces=False, getEnergy=False,
+                 getParameters=False, getParameterDerivatives=False, enforcePeriodicBox=False, groups=-1):
+        torch = self._torch
+        mask = self._mask(groups)
+        need_state = getPositions or getForces or getEnergy or getVelocities
+        if need_state and not self._have_positions:
+            raise mm.OpenMMException('Particle positions have not been set')
+        if (getEnergy or getForces) and getattr(self, '_reciprocal_missing', False) and \
+                mask & (1 << self._reciprocal_group):
+            raise lowering.UnsupportedDescription('PME/Ewald reciprocal space is not implemented yet on this engine')
+        fields = dict(_positions=None, _velocities=None, _forces=None, _potential=None, _kinetic=None,
+                      _box=self._box.copy(), _parameters=self._parameters if getParameters else {},
+                      _derivatives={}, _time=self._time)
+        with torch.cuda.stream(self._stream):
+            if getPositions:
+                self._call('b2_get_positions', c_void(self._buffer.data_ptr()))
+                self._call('b2_synchronize')
+                pos = self._buffer.cpu().numpy()
+                if enforcePeriodicBox:
+                    for group in self._molecule_groups:
+                        centre = pos[group].mean(axis=0)
+                        pos[group] -= np.floor(centre/self._box)*self._box
+                fields['_positions'] = pos
+            if getVelocities or getEnergy:
+                self._call('b2_get_velocities', c_void(self._buffer.data_ptr()))
+                self._call('b2_synchronize')
+                vel = self._buffer.cpu().numpy()
+                if getVelocities:
+                    fields['_velocities'] = vel
+                if getEnergy:
+                    fields['_kinetic'] = 0.5*float(np.sum(self._masses[:, None]*vel*vel))
+            flags = (1 if getForces else 0) | (2 if (getEnergy or getParameterDerivatives) else 0)
+            if flags:
+                energy, virial = ctypes.c_double(), ctypes.c_double()
+                self._call('b2_eval', ctypes.c_uint32(mask), flags,
+                           c_void(self._buffer.data_ptr()) if getForces else c_void(),
+                           ctypes.byref(energy), ctypes.byref(virial))
+                self._call('b2_synchronize')
+                if getForces:
+                    fields['_forces'] = self._buffer.cpu().numpy()
+                if getEnergy:
+                    fields['_potential'] = energy.value
+                    fields['_virial'] = virial.value
+                if getParameterDerivatives:
+                    out = (ctypes.c_double*2)()
+                    self._call('b2_get_parameter_derivatives', out)
+                    names = {}
+                    for _, info, force in self._pair_handles.values():
+                        if info.get('name') == 'softcore':
+                            if info.get('lambda_vdw'):
+                                names[info['lambda_vdw']] = out[0]
+                            if info.get('lambda_coul'):
+                                names[info['lambda_coul']] = out[1]
+                    fields['_derivatives'] = names
+        return State(**fields)
+
+    # -- extras used by tests / benchmarks ---------------------------------------------------------
+    def group_energies(self):
+        e = (ctypes.c_double*32)()
+        w = (ctypes.c_double*32)()
+        self._call('b2_get_group_energies', e, w)
+        return np.array(e), np.array(w)
+
+    def pair_set(self, force, want_pairs=False):
+        """(count, checksum[, pairs]) of interacting pairs of a pair force (parity tests)."""
+        torch = self._torch
+        handle = self._pair_handles[id(force)][0]
+        count, checksum = ctypes.c_longlong(), ctypes.c_ulonglong()
+        with torch.cuda.stream(self._stream):
+            self._call('b2_pair_set', handle, ctypes.byref(count), ctypes.byref(checksum), c_void(), 0)
+            if not want_pairs:
+                return count.value, checksum.value
+            pairs = torch.zeros((max(1, count.value), 2), dtype=torch.int32, device=self._device)
+            self._call('b2_pair_set', handle, ctypes.byref(count), ctypes.byref(checksum), c_void(pairs.data_ptr()),
+                       ctypes.c_longlong(pairs.shape[0]))
+            self._call('b2_synchronize')
+            return count.value, checksum.value, pairs.cpu().numpy()[:count.value]
+
+    def counters(self):
+        out = (ctypes.c_longlong*8)()
+        self._call('b2_synchronize')
+        self._call('b2_get_counters', out)
+        return dict(launches=out[0], rebuilds=out[1], pair_launches=out[2], list_capacity=out[3],
+                    list_max=out[4], graph_launches=out[5], kernels_per_step=out[6])
+
+    def synchronize(self):
+        self._call('b2_synchronize')

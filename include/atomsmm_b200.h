@@ -1,0 +1,173 @@
+/*
+ * atomsmm_b200 -- C ABI of the B200-native engine for atomsmm's hot path.
+ *
+ * atomsmm (reference) has no FFI seam of its own: it hands *descriptions* to OpenMM's public
+ * object model and OpenMM executes them.  This header is the seam one level up,
+ * exactly where those descriptions are handed over.  Each entry point cites the reference
+ * interface it replaces (file:line in /root/reference/src/atomsmm unless stated).
+ *
+ * Conventions
+ *   - units: nm, ps, dalton, kJ/mol, elementary charge, K, rad
+ *   - every call returns 0 on success or a negative B2_ERR_* code; b2_last_error() has the text
+ *   - "host" pointers are plain host memory; "dev" pointers are CUDA device pointers (the Python
+ *     side takes them from torch tensors with .data_ptr()); the library never returns memory
+ *     it owns
+ *   - atom indices are the caller's (original) numbering everywhere; the internal spatial
+ *     ordering is never visible
+ *   - one host thread per context; work is enqueued on the context's stream and calls are
+ *     asynchronous unless they return host scalars
+ */
+#ifndef ATOMSMM_B200_H
+#define ATOMSMM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2_context b2_context;
+
+enum {
+    B2_OK = 0,
+    B2_ERR_CUDA = -1,        /* a CUDA runtime call failed */
+    B2_ERR_ARG = -2,         /* invalid argument / call order */
+    B2_ERR_UNSUPPORTED = -3, /* description outside the supported closed set */
+    B2_ERR_OVERFLOW = -4,    /* neighbour-list capacity exceeded during a run */
+    B2_ERR_STATE = -5        /* positions not set, no program loaded, ... */
+};
+
+/* ---- pair-potential families (closed set recognised from atomsmm's energy strings) -------- */
+enum {
+    /* NearNonbondedForce / NearForce._expressions (forces.py:539-567,655-670), also the
+     * "-step(rc0-r)*near" discount of FarNonbondedForce (forces.py:713-722) and RESPASystem
+     * group 31 (systems.py:73).  params: variant(0 none,1 shift,2 force-switch), rs0, rc0, Kc,
+     * sign, use_coulomb */
+    B2_PAIR_NEAR = 1,
+    /* DampedSmoothedForce (forces.py:445-466).  params: alpha, rswitch, rcut, degree, Kc */
+    B2_PAIR_DAMPED = 2,
+    /* openmm.NonbondedForce direct space as configured by _AtomsMM_NonbondedForce
+     * (forces.py:152-190): LJ (optional OpenMM switch) + Coulomb.  params: Kc, coulomb_kind
+     * (0 none, 1 plain, 2 reaction field, 3 erfc/Ewald direct), krf, crf, alpha, use_switch,
+     * rswitch, rcut */
+    B2_PAIR_LJC = 3,
+    /* ComputingSystem dispersion virial "24*epsilon*(2*(sigma/r)^12-(sigma/r)^6)"
+     * (systems.py:894-898).  params: use_switch, rswitch, rcut */
+    B2_PAIR_LJ_VIRIAL = 4,
+    /* SoftcoreForce / SoftcoreLennardJonesForce (forces.py:727-793).  params: Kc, lambda_vdw,
+     * lambda_coul, use_switch, rswitch, rcut, form (0: (1-x)/x^2 ; 1: x*(x-1) with x=1/(..)) */
+    B2_PAIR_SOFTCORE = 5
+};
+
+/* ---- explicit-list (bonded) families ------------------------------------------------------- */
+enum {
+    B2_BOND_HARMONIC = 1,    /* openmm.HarmonicBondForce; per term: r0, k */
+    B2_ANGLE_HARMONIC = 2,   /* openmm.HarmonicAngleForce; per term: theta0, k */
+    B2_TORSION_PERIODIC = 3, /* openmm.PeriodicTorsionForce; per term: n, phase, k */
+    /* NonbondedExceptionsForce "4*epsilon*x*(x-1) + Kc*chargeprod/r" (forces.py:405-407) and
+     * the exception part of openmm.NonbondedForce; per term: chargeprod, sigma, epsilon,
+     * qi*qj (for the Ewald erf correction); globals: Kc, alpha (0 = no Ewald correction) */
+    B2_BOND_LJC = 4,
+    /* any other CustomBondForce / CustomAngleForce energy (NearExceptionForce forces.py:673-680,
+     * redefine_bond/angle systems.py:168,228, ComputingSystem virials systems.py:914,934):
+     * evaluated from bytecode of E and dE/d(r|theta) */
+    B2_BOND_CUSTOM = 5,
+    B2_ANGLE_CUSTOM = 6
+};
+
+/* flags for b2_eval */
+enum { B2_EVAL_FORCES = 1, B2_EVAL_ENERGY = 2 };
+
+/* ---- life cycle ---------------------------------------------------------------------------- */
+/* replaces openmm.Context construction (computers.py:69, utils.py:155,226) */
+int b2_create(int device, b2_context** out);
+int b2_destroy(b2_context* ctx);
+const char* b2_last_error(const b2_context* ctx);
+const char* b2_version(void);
+/* all work is enqueued on this stream (pass torch.cuda.current_stream().cuda_stream) */
+int b2_set_stream(b2_context* ctx, void* cuda_stream);
+int b2_synchronize(b2_context* ctx);
+
+/* ---- system description (host pointers) ---------------------------------------------------- */
+/* System.setDefaultPeriodicBoxVectors / Context.setPeriodicBoxVectors (computers.py:243);
+ * orthorhombic only, like the reference's PressureComputer (computers.py:86-88) */
+int b2_set_box(b2_context* ctx, const double box[3], int periodic);
+/* System.addParticle + Context.getMolecules (computers.py:24): mass[n], molecule id [n] */
+int b2_set_particles(b2_context* ctx, int n, const double* mass, const int* molecule);
+/* CustomNonbondedForce.addParticle as used by importFrom (forces.py:299-301): per-particle
+ * charge, sigma, epsilon.  Returns a parameter-set id shared by the pair forces built from the
+ * same NonbondedForce. */
+int b2_add_param_set(b2_context* ctx, const double* charge, const double* sigma, const double* epsilon,
+                     int* set_id);
+/* CustomNonbondedForce.addExclusion (forces.py:310-312): npairs (i,j) */
+int b2_set_exclusions(b2_context* ctx, int npairs, const int* pairs);
+/* openmm.CustomNonbondedForce / NonbondedForce added to a System (forces.py:35-36,108-110).
+ * energy_constant: position-independent energy of the force (long-range correction). */
+int b2_add_pair_force(b2_context* ctx, int family, int group, int param_set, double cutoff,
+                      const double* params, int nparams, double energy_constant, int* handle);
+/* updateParametersInContext / Context.setParameter for a pair force */
+int b2_update_pair_force(b2_context* ctx, int handle, const double* params, int nparams,
+                         double energy_constant);
+/* HarmonicBondForce / HarmonicAngleForce / PeriodicTorsionForce / CustomBondForce.addBond
+ * (forces.py:384-388).  atoms: arity*nterms indices; params: stride*nterms doubles;
+ * gparams: family globals. */
+int b2_add_bonded_force(b2_context* ctx, int family, int group, int nterms, const int* atoms,
+                        const double* params, int stride, int periodic, const double* gparams,
+                        int ngparams, int* handle);
+/* CustomBondForce / CustomAngleForce with an arbitrary energy string, pre-compiled by the
+ * Python front end to VM bytecode for E(s) and dE/ds (s = r or theta).  Variables: index 0 = s,
+ * 1..stride = per-term parameters. */
+int b2_add_custom_bonded_force(b2_context* ctx, int family, int group, int nterms, const int* atoms,
+                               const double* params, int stride, int periodic,
+                               const int* code_e, int ncode_e, const int* code_de, int ncode_de,
+                               const double* consts, int nconsts, int* handle);
+/* neighbour-list skin (nm); lists are rebuilt when an atom moved more than skin/2 */
+int b2_set_skin(b2_context* ctx, double skin);
+
+/* ---- state (device pointers, double [n][3], caller's atom order) --------------------------- */
+/* Context.setPositions / setVelocities / getState (computers.py:74-84,244-245) */
+int b2_set_positions(b2_context* ctx, const double* x_dev);
+int b2_set_velocities(b2_context* ctx, const double* v_dev);
+int b2_get_positions(b2_context* ctx, double* x_dev);
+int b2_get_velocities(b2_context* ctx, double* v_dev);
+
+/* ---- single-point evaluation --------------------------------------------------------------- */
+/* Context.getState(getEnergy/getForces, groups=mask) (utils.py:164, computers.py:74-81).
+ * forces_dev: double [n][3] or NULL; energy_host/virial_host: sums over the groups in the mask,
+ * or NULL.  The virial is sum over pair-like terms of r.F = -r dE/dr (PressureComputer's
+ * per-pair virial); per-group values via b2_get_group_energies. */
+int b2_eval(b2_context* ctx, uint32_t group_mask, int flags, double* forces_dev,
+            double* energy_host, double* virial_host);
+int b2_get_group_energies(b2_context* ctx, double energy_host[32], double virial_host[32]);
+/* dE/dlambda of the softcore pair forces evaluated by the last b2_eval with B2_EVAL_ENERGY:
+ * out[0] = d/d lambda_vdw, out[1] = d/d lambda_coul (Context.getState(getParameterDerivatives)) */
+int b2_get_parameter_derivatives(b2_context* ctx, double out_host[2]);
+/* number of atom pairs (i<j) inside the cutoff of pair force `handle`, not excluded, and a
+ * 64-bit order-independent checksum of the pair set (parity test: neighbour lists bit-exact).
+ * pairs_dev (int2 [capacity], may be NULL) receives the pairs in caller numbering, unordered. */
+int b2_pair_set(b2_context* ctx, int handle, long long* count_host, unsigned long long* checksum_host,
+                int* pairs_dev, long long capacity);
+
+/* ---- integrator program -------------------------------------------------------------------- */
+/* One lowered CustomIntegrator program (integrators.py:113-145 emit it, integrators.py:163 runs
+ * it).  ops: nops records of B2_OP_WORDS ints (layout in csrc/program.h); code/consts: shared
+ * bytecode and constant pools; globals: initial values of all global variables (index 0 = dt). */
+#define B2_OP_WORDS 8
+int b2_load_program(b2_context* ctx, const int* ops, int nops, const int* code, int ncode,
+                    const double* consts, int nconsts, const double* globals, int nglobals,
+                    int nperdof, uint64_t seed);
+int b2_set_globals(b2_context* ctx, int first, int count, const double* values_host);
+int b2_get_globals(b2_context* ctx, int first, int count, double* values_host);
+/* CustomIntegrator.set/getPerDofVariableByName (integrators.py:155-160); var >= 0 user slot */
+int b2_set_perdof(b2_context* ctx, int var, const double* values_dev);
+int b2_get_perdof(b2_context* ctx, int var, double* values_dev);
+/* CustomIntegrator.step(n) (integrators.py:163).  Asynchronous. */
+int b2_run(b2_context* ctx, int nsteps);
+/* counters: [0] kernel launches since creation, [1] neighbour-list rebuilds, [2] pair-kernel
+ * launches, [3] list capacity (entries per 8-atom group, largest list), [4] largest count seen */
+int b2_get_counters(b2_context* ctx, long long out_host[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
