@@ -26,6 +26,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define B2_API __attribute__((visibility("default")))
+#else
+#define B2_API
+#endif
+
 typedef struct b2_context b2_context;
 
 enum {
@@ -80,72 +86,72 @@ enum { B2_EVAL_FORCES = 1, B2_EVAL_ENERGY = 2 };
 
 /* ---- life cycle ---------------------------------------------------------------------------- */
 /* replaces openmm.Context construction (computers.py:69, utils.py:155,226) */
-int b2_create(int device, b2_context** out);
-int b2_destroy(b2_context* ctx);
-const char* b2_last_error(const b2_context* ctx);
-const char* b2_version(void);
+B2_API int b2_create(int device, b2_context** out);
+B2_API int b2_destroy(b2_context* ctx);
+B2_API const char* b2_last_error(const b2_context* ctx);
+B2_API const char* b2_version(void);
 /* all work is enqueued on this stream (pass torch.cuda.current_stream().cuda_stream) */
-int b2_set_stream(b2_context* ctx, void* cuda_stream);
-int b2_synchronize(b2_context* ctx);
+B2_API int b2_set_stream(b2_context* ctx, void* cuda_stream);
+B2_API int b2_synchronize(b2_context* ctx);
 
 /* ---- system description (host pointers) ---------------------------------------------------- */
 /* System.setDefaultPeriodicBoxVectors / Context.setPeriodicBoxVectors (computers.py:243);
  * orthorhombic only, like the reference's PressureComputer (computers.py:86-88) */
-int b2_set_box(b2_context* ctx, const double box[3], int periodic);
+B2_API int b2_set_box(b2_context* ctx, const double box[3], int periodic);
 /* System.addParticle + Context.getMolecules (computers.py:24): mass[n], molecule id [n] */
-int b2_set_particles(b2_context* ctx, int n, const double* mass, const int* molecule);
+B2_API int b2_set_particles(b2_context* ctx, int n, const double* mass, const int* molecule);
 /* CustomNonbondedForce.addParticle as used by importFrom (forces.py:299-301): per-particle
  * charge, sigma, epsilon.  Returns a parameter-set id shared by the pair forces built from the
  * same NonbondedForce. */
-int b2_add_param_set(b2_context* ctx, const double* charge, const double* sigma, const double* epsilon,
+B2_API int b2_add_param_set(b2_context* ctx, const double* charge, const double* sigma, const double* epsilon,
                      int* set_id);
 /* CustomNonbondedForce.addExclusion (forces.py:310-312): npairs (i,j) */
-int b2_set_exclusions(b2_context* ctx, int npairs, const int* pairs);
+B2_API int b2_set_exclusions(b2_context* ctx, int npairs, const int* pairs);
 /* openmm.CustomNonbondedForce / NonbondedForce added to a System (forces.py:35-36,108-110).
  * energy_constant: position-independent energy of the force (long-range correction). */
-int b2_add_pair_force(b2_context* ctx, int family, int group, int param_set, double cutoff,
+B2_API int b2_add_pair_force(b2_context* ctx, int family, int group, int param_set, double cutoff,
                       const double* params, int nparams, double energy_constant, int* handle);
 /* updateParametersInContext / Context.setParameter for a pair force */
-int b2_update_pair_force(b2_context* ctx, int handle, const double* params, int nparams,
+B2_API int b2_update_pair_force(b2_context* ctx, int handle, const double* params, int nparams,
                          double energy_constant);
 /* HarmonicBondForce / HarmonicAngleForce / PeriodicTorsionForce / CustomBondForce.addBond
  * (forces.py:384-388).  atoms: arity*nterms indices; params: stride*nterms doubles;
  * gparams: family globals. */
-int b2_add_bonded_force(b2_context* ctx, int family, int group, int nterms, const int* atoms,
+B2_API int b2_add_bonded_force(b2_context* ctx, int family, int group, int nterms, const int* atoms,
                         const double* params, int stride, int periodic, const double* gparams,
                         int ngparams, int* handle);
 /* CustomBondForce / CustomAngleForce with an arbitrary energy string, pre-compiled by the
  * Python front end to VM bytecode for E(s) and dE/ds (s = r or theta).  Variables: index 0 = s,
  * 1..stride = per-term parameters. */
-int b2_add_custom_bonded_force(b2_context* ctx, int family, int group, int nterms, const int* atoms,
+B2_API int b2_add_custom_bonded_force(b2_context* ctx, int family, int group, int nterms, const int* atoms,
                                const double* params, int stride, int periodic,
                                const int* code_e, int ncode_e, const int* code_de, int ncode_de,
                                const double* consts, int nconsts, int* handle);
 /* neighbour-list skin (nm); lists are rebuilt when an atom moved more than skin/2 */
-int b2_set_skin(b2_context* ctx, double skin);
+B2_API int b2_set_skin(b2_context* ctx, double skin);
 
 /* ---- state (device pointers, double [n][3], caller's atom order) --------------------------- */
 /* Context.setPositions / setVelocities / getState (computers.py:74-84,244-245) */
-int b2_set_positions(b2_context* ctx, const double* x_dev);
-int b2_set_velocities(b2_context* ctx, const double* v_dev);
-int b2_get_positions(b2_context* ctx, double* x_dev);
-int b2_get_velocities(b2_context* ctx, double* v_dev);
+B2_API int b2_set_positions(b2_context* ctx, const double* x_dev);
+B2_API int b2_set_velocities(b2_context* ctx, const double* v_dev);
+B2_API int b2_get_positions(b2_context* ctx, double* x_dev);
+B2_API int b2_get_velocities(b2_context* ctx, double* v_dev);
 
 /* ---- single-point evaluation --------------------------------------------------------------- */
 /* Context.getState(getEnergy/getForces, groups=mask) (utils.py:164, computers.py:74-81).
  * forces_dev: double [n][3] or NULL; energy_host/virial_host: sums over the groups in the mask,
  * or NULL.  The virial is sum over pair-like terms of r.F = -r dE/dr (PressureComputer's
  * per-pair virial); per-group values via b2_get_group_energies. */
-int b2_eval(b2_context* ctx, uint32_t group_mask, int flags, double* forces_dev,
+B2_API int b2_eval(b2_context* ctx, uint32_t group_mask, int flags, double* forces_dev,
             double* energy_host, double* virial_host);
-int b2_get_group_energies(b2_context* ctx, double energy_host[32], double virial_host[32]);
+B2_API int b2_get_group_energies(b2_context* ctx, double energy_host[32], double virial_host[32]);
 /* dE/dlambda of the softcore pair forces evaluated by the last b2_eval with B2_EVAL_ENERGY:
  * out[0] = d/d lambda_vdw, out[1] = d/d lambda_coul (Context.getState(getParameterDerivatives)) */
-int b2_get_parameter_derivatives(b2_context* ctx, double out_host[2]);
+B2_API int b2_get_parameter_derivatives(b2_context* ctx, double out_host[2]);
 /* number of atom pairs (i<j) inside the cutoff of pair force `handle`, not excluded, and a
  * 64-bit order-independent checksum of the pair set (parity test: neighbour lists bit-exact).
  * pairs_dev (int2 [capacity], may be NULL) receives the pairs in caller numbering, unordered. */
-int b2_pair_set(b2_context* ctx, int handle, long long* count_host, unsigned long long* checksum_host,
+B2_API int b2_pair_set(b2_context* ctx, int handle, long long* count_host, unsigned long long* checksum_host,
                 int* pairs_dev, long long capacity);
 
 /* ---- integrator program -------------------------------------------------------------------- */
@@ -153,19 +159,19 @@ int b2_pair_set(b2_context* ctx, int handle, long long* count_host, unsigned lon
  * it).  ops: nops records of B2_OP_WORDS ints (layout in csrc/program.h); code/consts: shared
  * bytecode and constant pools; globals: initial values of all global variables (index 0 = dt). */
 #define B2_OP_WORDS 8
-int b2_load_program(b2_context* ctx, const int* ops, int nops, const int* code, int ncode,
+B2_API int b2_load_program(b2_context* ctx, const int* ops, int nops, const int* code, int ncode,
                     const double* consts, int nconsts, const double* globals, int nglobals,
                     int nperdof, uint64_t seed);
-int b2_set_globals(b2_context* ctx, int first, int count, const double* values_host);
-int b2_get_globals(b2_context* ctx, int first, int count, double* values_host);
+B2_API int b2_set_globals(b2_context* ctx, int first, int count, const double* values_host);
+B2_API int b2_get_globals(b2_context* ctx, int first, int count, double* values_host);
 /* CustomIntegrator.set/getPerDofVariableByName (integrators.py:155-160); var >= 0 user slot */
-int b2_set_perdof(b2_context* ctx, int var, const double* values_dev);
-int b2_get_perdof(b2_context* ctx, int var, double* values_dev);
+B2_API int b2_set_perdof(b2_context* ctx, int var, const double* values_dev);
+B2_API int b2_get_perdof(b2_context* ctx, int var, double* values_dev);
 /* CustomIntegrator.step(n) (integrators.py:163).  Asynchronous. */
-int b2_run(b2_context* ctx, int nsteps);
+B2_API int b2_run(b2_context* ctx, int nsteps);
 /* counters: [0] kernel launches since creation, [1] neighbour-list rebuilds, [2] pair-kernel
  * launches, [3] list capacity (entries per 8-atom group, largest list), [4] largest count seen */
-int b2_get_counters(b2_context* ctx, long long out_host[8]);
+B2_API int b2_get_counters(b2_context* ctx, long long out_host[8]);
 
 #ifdef __cplusplus
 }
