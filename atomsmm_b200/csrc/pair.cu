@@ -6,8 +6,8 @@
 //
 // Mapping: one warp per i-group of 8 spatially adjacent atoms; lane = (i-atom 0..7) x (j-lane
 // 0..3).  The group's j-list is streamed 32 entries at a time: every lane gathers one j atom
-// (float4 position + float4 parameters, coalesced index read), shifts it to the periodic image
-// nearest the group, and stages it in shared memory; the warp then sweeps the 32 staged atoms in
+// (float64 position + float4 parameters, coalesced index read), forms its minimum-image position
+// relative to the group's first atom in float64, rounds to fp32 and stages it in shared memory; the warp then sweeps the 32 staged atoms in
 // 8 steps of 4, each lane accumulating the force on its own i-atom in registers.  Forces are
 // reduced over the 4 j-lanes with two shuffles and written once per atom: no atomics, results
 // are bit-reproducible.  The full (both-directions) list means every pair is evaluated twice;
@@ -118,14 +118,24 @@ __device__ __forceinline__ void sweep_chunk(const POT& pot, const float4* __rest
     }
 }
 
+// relative position of atom a with respect to the group's reference point, minimum image, computed
+// in float64 from the unwrapped master coordinates and only then rounded: the fp32 error is that of
+// a ~1 nm relative vector (6e-8 nm), independent of the box size.
+__device__ __forceinline__ float3 rel_pos(const double* __restrict__ x, int a, double rx, double ry, double rz,
+                                          double bx, double by, double bz, double ibx, double iby, double ibz) {
+    double dx = x[3*a] - rx, dy = x[3*a+1] - ry, dz = x[3*a+2] - rz;
+    dx -= bx*rint(dx*ibx); dy -= by*rint(dy*iby); dz -= bz*rint(dz*ibz);
+    return make_float3((float)dx, (float)dy, (float)dz);
+}
+
 template <class POT>
-__global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const float4* __restrict__ pos4,
+__global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const double* __restrict__ x,
                                                       const float4* __restrict__ par,
                                                       const int* __restrict__ entries,
                                                       const int* __restrict__ counts,
                                                       const unsigned char* __restrict__ gflags, int cap,
                                                       float4* __restrict__ out, int accumulate, POT pot,
-                                                      float rc2, float3 box, float3 inv) {
+                                                      float rc2, double bx, double by, double bz) {
     __shared__ float4 sx[WPB][2][32];
     __shared__ float4 sp[WPB][2][32];
     const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
@@ -134,38 +144,33 @@ __global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const
     const int il = lane >> 2, jj = lane & 3;
     const int i = warp*B2_GROUP + il;
     const int ic = min(i, n - 1);
-    float4 xi = pos4[ic];
-    const float4 pi = par[ic];
+    const double ibx = 1.0/bx, iby = 1.0/by, ibz = 1.0/bz;
+    const float3 box = make_float3((float)bx, (float)by, (float)bz);
+    const float3 inv = make_float3((float)ibx, (float)iby, (float)ibz);
     // reference point of the group: its first atom
-    const float rx = __shfl_sync(FULL, xi.x, 0), ry = __shfl_sync(FULL, xi.y, 0), rz = __shfl_sync(FULL, xi.z, 0);
+    const int i0 = warp*B2_GROUP;
+    const double rx = x[3*i0], ry = x[3*i0+1], rz = x[3*i0+2];
+    const float3 xr = rel_pos(x, ic, rx, ry, rz, bx, by, bz, ibx, iby, ibz);
+    const float4 xi = make_float4(xr.x, xr.y, xr.z, 0.f);
+    const float4 pi = par[ic];
     const bool minimg = gflags[warp] & 1;
-    if (!minimg) {
-        xi.x -= box.x*rintf((xi.x - rx)*inv.x);
-        xi.y -= box.y*rintf((xi.y - ry)*inv.y);
-        xi.z -= box.z*rintf((xi.z - rz)*inv.z);
-    }
     const int cnt = counts[warp];
     const int* __restrict__ base = entries + (size_t)warp*cap;
-    const int pad = (int)(0xff000000u | (unsigned)(warp*B2_GROUP));
+    const int pad = (int)(0xff000000u | (unsigned)i0);
     float fx = 0.f, fy = 0.f, fz = 0.f;
     int buf = 0;
     // software pipeline: gather chunk c+1 while chunk c is being swept
     int e = lane < cnt ? base[lane] : pad;
-    float4 xj = pos4[e & 0xffffff];
+    float3 xj = rel_pos(x, e & 0xffffff, rx, ry, rz, bx, by, bz, ibx, iby, ibz);
     float4 pj = par[e & 0xffffff];
     for (int c0 = 0; c0 < cnt; c0 += 32) {
-        if (!minimg) {
-            xj.x -= box.x*rintf((xj.x - rx)*inv.x);
-            xj.y -= box.y*rintf((xj.y - ry)*inv.y);
-            xj.z -= box.z*rintf((xj.z - rz)*inv.z);
-        }
         pj.w = __int_as_float((int)((unsigned)e >> 24));
-        sx[wib][buf][lane] = xj;
+        sx[wib][buf][lane] = make_float4(xj.x, xj.y, xj.z, 0.f);
         sp[wib][buf][lane] = pj;
         const int nxt = c0 + 32 + lane;
         if (c0 + 32 < cnt) {
             e = nxt < cnt ? base[nxt] : pad;
-            xj = pos4[e & 0xffffff];
+            xj = rel_pos(x, e & 0xffffff, rx, ry, rz, bx, by, bz, ibx, iby, ibz);
             pj = par[e & 0xffffff];
         }
         __syncwarp();
@@ -298,12 +303,11 @@ __global__ void __launch_bounds__(32*WPB) k_pair_set(int n, int ngroups, const d
 template <class POT>
 static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, float rc2, float4* out, bool accumulate) {
     const NList& L = ctx->lists[pf.list];
-    const float3 box = make_float3((float)ctx->box[0], (float)ctx->box[1], (float)ctx->box[2]);
-    const float3 inv = make_float3((float)(1.0/ctx->box[0]), (float)(1.0/ctx->box[1]), (float)(1.0/ctx->box[2]));
     const int blocks = (ctx->ngroups + WPB - 1)/WPB;
-    k_pair_force<POT><<<blocks, 32*WPB, 0, ctx->stream>>>(ctx->n, ctx->ngroups, ctx->pos4, ctx->par[pf.set],
+    k_pair_force<POT><<<blocks, 32*WPB, 0, ctx->stream>>>(ctx->n, ctx->ngroups, ctx->x, ctx->par[pf.set],
                                                           L.entries, L.counts, L.gflags, L.cap, out,
-                                                          accumulate ? 1 : 0, pot, rc2, box, inv);
+                                                          accumulate ? 1 : 0, pot, rc2, ctx->box[0], ctx->box[1],
+                                                          ctx->box[2]);
     ctx->counters[2]++;
     B2_LAUNCH_CHECK();
     return B2_OK;

@@ -286,7 +286,8 @@ def parse_condition(text):
 OPCODES = dict(
     PUSHC=0, PUSHG=1, PUSHV=2, GAUSS=3, UNIF=4, ADD=5, SUB=6, MUL=7, DIV=8, NEG=9, POW=10, POWI=11,
     SQRT=12, EXP=13, LOG=14, SIN=15, COS=16, TAN=17, ERF=18, ERFC=19, ABS=20, MIN=21, MAX=22,
-    STEP=23, DELTA=24, SELECT=25, FLOOR=26, CEIL=27, PUSHM=28, PUSHF=29, DERIV=30,
+    STEP=23, DELTA=24, SELECT=25, FLOOR=26, CEIL=27, PUSHM=28, PUSHF=29, DERIV=30, STOREG=31, JMP=32,
+    JMPZ=33, CMP=34, PUSHE=35,
 )
 _CALL_OPS = dict(sqrt='SQRT', exp='EXP', log='LOG', sin='SIN', cos='COS', tan='TAN', erf='ERF',
                  erfc='ERFC', abs='ABS', min='MIN', max='MAX', step='STEP', delta='DELTA',

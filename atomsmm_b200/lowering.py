@@ -394,6 +394,7 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
         raise UnsupportedDescription('distance constraints (SHAKE/RATTLE) are not implemented in this engine yet')
     body = _unroll(_tree(steps).body)
     body = _fold_force_copies(body, P)
+    body, dead_stores = _strip_dead_constant_stores(body)
     assigned_globals = _assigned(body)
 
     def resolve_perdof(name):
@@ -575,6 +576,9 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
             raise UnsupportedDescription('unsupported step kind %d' % kind)
     if pending_globals:
         lower_global_run(pending_globals)
+    for name, value in dead_stores.items():
+        if name in P.global_names:
+            prologue.append((P.gindex(name), ('num', value)))
     if prologue:
         start = len(P.bc.code)
         for slot, ast in prologue:
@@ -582,6 +586,33 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
             P.bc.emit('STOREG', slot)
         P.ops.insert(0, [OP_GLOBAL, 0, start, (len(P.bc.code) - start)//2, 0, 0, 0, 0])
     return P
+
+
+def _strip_dead_constant_stores(body):
+    """Loop counters of unrolled loops are assigned constants that nothing reads any more; keep
+    only their final value (written once per step) instead of one tiny kernel per assignment."""
+    reads = set()
+
+    def collect(seq):
+        for item in seq:
+            if isinstance(item, _Block):
+                lhs, _, rhs = X.parse_condition(item.condition)
+                reads.update(X.free_symbols(lhs) | X.free_symbols(rhs))
+                collect(item.body)
+            elif item[2]:
+                main, defs = X.parse(item[2])
+                reads.update(X.free_symbols(X.substitute(main, defs)))
+    collect(body)
+    out, final = [], {}
+    for item in body:
+        if not isinstance(item, _Block) and item[0] == CI.ComputeGlobal and item[1] not in reads:
+            try:
+                final[item[1]] = float(item[2])
+                continue
+            except ValueError:
+                pass
+        out.append(item)
+    return out, final
 
 
 def _as_i32(mask):

@@ -1,0 +1,158 @@
+"""
+ORACLE (test infrastructure only -- see oracle/__init__.py).
+
+Float64 interpreter for CustomIntegrator step programs, restating OpenMM's semantics:
+per-DOF variables x v f f0..f31 m plus user ones, globals (dt first), `gaussian`/`uniform` fresh per
+DOF component in per-DOF steps and once in global steps, massless particles not updated, forces of
+a group re-evaluated whenever positions changed since that group was last evaluated, block
+conditions `lhs op rhs`.  Reference call sites: integrators.py:113-163 (program emission and
+stepping), propagators.py (the programs themselves).
+"""
+
+import re
+
+import numpy as np
+import sympy
+
+from . import refmath
+
+_COND = re.compile(r'^(.*?)(<=|>=|!=|<|>|=)(.*)$')
+_FORCE = re.compile(r'^f([0-9]*)$')
+
+
+class Interpreter(object):
+    def __init__(self, system, integrator, positions, velocities=None, seed=0, parameters=None):
+        self.system = system
+        self.n = system.getNumParticles()
+        self.box = refmath.system_box(system)
+        self.mass = np.array([system.getParticleMass(i).value_in_md_units() for i in range(self.n)])[:, None]
+        self.x = np.array(positions, dtype=np.float64).copy()
+        self.v = np.zeros_like(self.x) if velocities is None else np.array(velocities, dtype=np.float64).copy()
+        self.globals = {'dt': integrator._dt}
+        for k in range(integrator.getNumGlobalVariables()):
+            self.globals[integrator.getGlobalVariableName(k)] = float(integrator._global_values[k])
+        self.parameters = dict(parameters or {})
+        self.perdof = {}
+        for k in range(integrator.getNumPerDofVariables()):
+            value = integrator._perdof_values[k]
+            self.perdof[integrator.getPerDofVariableName(k)] = \
+                np.full((self.n, 3), float(value)) if np.isscalar(value) else np.array(value, dtype=np.float64)
+        self.steps = [tuple(integrator.getComputationStep(k)) for k in range(integrator.getNumComputations())]
+        self.rng = np.random.default_rng(seed)
+        self._force_cache = {}
+        self._version = 0
+        self._compiled = {}
+        self.force_evaluations = 0
+        # block structure: matching end for every block start
+        self._end = {}
+        stack = []
+        for k, (kind, _, _) in enumerate(self.steps):
+            if kind in (6, 7):
+                stack.append(k)
+            elif kind == 8:
+                self._end[stack.pop()] = k
+
+    # ---------------------------------------------------------------------------------------------
+    def forces(self, group):
+        key = 'all' if group is None else group
+        cached = self._force_cache.get(key)
+        if cached is not None and cached[0] == self._version:
+            return cached[1]
+        groups = None if group is None else {group}
+        f = refmath.evaluate_system(self.system, self.x, self.box, groups, self.parameters).forces
+        self.force_evaluations += 1
+        self._force_cache[key] = (self._version, f)
+        return f
+
+    def potential_energy(self, groups=None):
+        return refmath.evaluate_system(self.system, self.x, self.box, groups, self.parameters).energy
+
+    def kinetic_energy(self):
+        return 0.5*float(np.sum(self.mass*self.v*self.v))
+
+    def _compile(self, text):
+        if text not in self._compiled:
+            expression = refmath.parse_energy(text)
+            symbols = sorted(expression.free_symbols, key=lambda s: s.name)
+            self._compiled[text] = ([s.name for s in symbols], refmath._lambdify(symbols, expression))
+        return self._compiled[text]
+
+    def _value(self, name, per_dof):
+        if name == 'x':
+            return self.x
+        if name == 'v':
+            return self.v
+        if name == 'm':
+            return self.mass
+        m = _FORCE.match(name)
+        if m and per_dof:
+            return self.forces(None if m.group(1) == '' else int(m.group(1)))
+        if name in self.perdof and per_dof:
+            return self.perdof[name]
+        if name == 'gaussian':
+            return self.rng.standard_normal((self.n, 3)) if per_dof else float(self.rng.standard_normal())
+        if name in ('uniform', 'random'):
+            return self.rng.random((self.n, 3)) if per_dof else float(self.rng.random())
+        if name in self.globals:
+            return self.globals[name]
+        if name in self.parameters:
+            return self.parameters[name]
+        raise KeyError('unknown variable %r' % name)
+
+    def _evaluate(self, text, per_dof):
+        names, function = self._compile(text)
+        return function(*[self._value(name, per_dof) for name in names])
+
+    def _condition(self, text):
+        depth = 0
+        for i, ch in enumerate(text):
+            depth += ch == '('
+            depth -= ch == ')'
+            if depth == 0 and ch in '<>=!':
+                op = text[i:i+2] if text[i:i+2] in ('<=', '>=', '!=') else ch
+                lhs = float(self._evaluate(text[:i], False))
+                rhs = float(self._evaluate(text[i+len(op):], False))
+                return {'=': lhs == rhs, '<': lhs < rhs, '>': lhs > rhs, '!=': lhs != rhs,
+                        '<=': lhs <= rhs, '>=': lhs >= rhs}[op]
+        raise ValueError('bad condition %r' % text)
+
+    def step(self, count=1):
+        massive = self.mass > 0
+        for _ in range(count):
+            pc = 0
+            loops = []
+            while pc < len(self.steps):
+                kind, variable, expression = self.steps[pc]
+                if kind == 1:      # per DOF
+                    value = np.broadcast_to(self._evaluate(expression, True), (self.n, 3)).astype(np.float64)
+                    if variable == 'x':
+                        self.x = np.where(massive, value, self.x)
+                        self._version += 1
+                    elif variable == 'v':
+                        self.v = np.where(massive, value, self.v)
+                    else:
+                        self.perdof[variable] = value.copy()
+                elif kind == 0:    # global
+                    value = float(self._evaluate(expression, False))
+                    if variable in self.globals:
+                        self.globals[variable] = value
+                    else:
+                        self.parameters[variable] = value
+                elif kind == 2:    # sum
+                    value = np.broadcast_to(self._evaluate(expression, True), (self.n, 3))
+                    self.globals[variable] = float(np.sum(value))
+                elif kind in (3, 4):
+                    raise NotImplementedError('constraints')
+                elif kind == 6:
+                    if not self._condition(expression):
+                        pc = self._end[pc]
+                elif kind == 7:
+                    if self._condition(expression):
+                        loops.append(pc)
+                    else:
+                        pc = self._end[pc]
+                elif kind == 8:
+                    start = [s for s, e in self._end.items() if e == pc][0]
+                    if self.steps[start][0] == 7:
+                        pc = start - 1
+                pc += 1

@@ -88,6 +88,22 @@ def _lambdify(symbols, expression):
     return sympy.lambdify(symbols, expression, modules=[_NUMPY_FUNCS, 'scipy', 'numpy'])
 
 
+_PAIR_CACHE = {}
+
+
+def _pair_functions(text, glob, syms):
+    """(expression, E(r, ...), dE/dr(r, ...)) for an energy string with globals substituted."""
+    key = (text, tuple(sorted(glob.items())), tuple(s.name for s in syms))
+    if key not in _PAIR_CACHE:
+        expression = parse_energy(text).subs({sympy.Symbol(k): v for k, v in glob.items()})
+        unknown = expression.free_symbols - set(syms)
+        if unknown:
+            raise ValueError('unbound symbols %s in %s' % (unknown, text))
+        _PAIR_CACHE[key] = (expression, _lambdify(syms, expression),
+                            _lambdify(syms, sympy.diff(expression, sympy.Symbol('r'))))
+    return _PAIR_CACHE[key]
+
+
 def omm_switch(r, rs, rc):
     """OpenMM built-in switching function and derivative (A4)."""
     t = np.clip((r - rs)/(rc - rs), 0.0, 1.0)
@@ -164,7 +180,6 @@ def _exclusion_filter(n, i, j, excl):
 def eval_custom_nonbonded(force, pos, box, params=None, want_pairs=False):
     n = force.getNumParticles()
     res = Result(n)
-    expression = parse_energy(force.getEnergyFunction())
     names = [force.getPerParticleParameterName(k) for k in range(force.getNumPerParticleParameters())]
     table = np.array([force.getParticleParameters(k) for k in range(n)], dtype=float).reshape(n, len(names))
     glob = {force.getGlobalParameterName(k): force.getGlobalParameterDefaultValue(k)
@@ -172,13 +187,8 @@ def eval_custom_nonbonded(force, pos, box, params=None, want_pairs=False):
     if params:
         glob.update({k: v for k, v in params.items() if k in glob})
     r_sym = sympy.Symbol('r')
-    expression = expression.subs({sympy.Symbol(k): v for k, v in glob.items()})
     syms = [r_sym] + [sympy.Symbol(nm + '1') for nm in names] + [sympy.Symbol(nm + '2') for nm in names]
-    unknown = expression.free_symbols - set(syms)
-    if unknown:
-        raise ValueError('unbound symbols %s in %s' % (unknown, force.getEnergyFunction()))
-    fe = _lambdify(syms, expression)
-    fd = _lambdify(syms, sympy.diff(expression, r_sym))
+    expression, fe, fd = _pair_functions(force.getEnergyFunction(), glob, syms)
     method = force.getNonbondedMethod()
     periodic = method == 2
     cutoff = None if method == 0 else float(force.getCutoffDistance().value_in_md_units())
@@ -231,15 +241,9 @@ def _eval_pairlist_expression(energy_text, names, glob, idx_i, idx_j, table, pos
     res = Result(n)
     if len(idx_i) == 0:
         return res
-    expression = parse_energy(energy_text)
     r_sym = sympy.Symbol('r')
-    expression = expression.subs({sympy.Symbol(k): v for k, v in glob.items()})
     syms = [r_sym] + [sympy.Symbol(nm) for nm in names]
-    unknown = expression.free_symbols - set(syms)
-    if unknown:
-        raise ValueError('unbound symbols %s in %s' % (unknown, energy_text))
-    fe = _lambdify(syms, expression)
-    fd = _lambdify(syms, sympy.diff(expression, r_sym))
+    expression, fe, fd = _pair_functions(energy_text, glob, syms)
     d = pos[idx_j] - pos[idx_i]
     if periodic:
         d = min_image(d, box)
