@@ -652,6 +652,42 @@ extern "C" int b2_run(b2_context* ctx, int nsteps) {
     return program_run(ctx, nsteps);
 }
 
+extern "C" int b2_set_profiling(b2_context* ctx, int on) {
+    if (!ctx) return B2_ERR_ARG;
+    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    ctx->prof_events.clear();
+    ctx->prof_tags.clear();
+    ctx->profiling = on != 0;
+    program_release(ctx);
+    ctx->eager_steps = 0;
+    return B2_OK;
+}
+
+extern "C" int b2_get_profile(b2_context* ctx, int handle, double* total_ms, long long* launches, long long* entries) {
+    if (!ctx || handle < 0 || handle >= (int)ctx->pair_forces.size()) return b2_fail(ctx, B2_ERR_ARG, "bad pair force handle");
+    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    double ms = 0;
+    long long count = 0;
+    for (size_t k = 0; k < ctx->prof_tags.size(); k++) {
+        if (ctx->prof_tags[k] != handle) continue;
+        float t = 0;
+        B2_CUDA(cudaEventElapsedTime(&t, ctx->prof_events[2*k], ctx->prof_events[2*k+1]));
+        ms += t; count++;
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = count;
+    if (entries) {
+        const NList& L = ctx->lists[ctx->pair_forces[handle].list];
+        std::vector<int> c(ctx->ngroups);
+        B2_CUDA(cudaMemcpy(c.data(), L.counts, sizeof(int)*ctx->ngroups, cudaMemcpyDeviceToHost));
+        long long total = 0;
+        for (int v : c) total += v;
+        *entries = total;
+    }
+    return B2_OK;
+}
+
 extern "C" int b2_get_counters(b2_context* ctx, long long out_host[8]) {
     if (!ctx) return B2_ERR_ARG;
     for (int k = 0; k < 8; k++) out_host[k] = ctx->counters[k];

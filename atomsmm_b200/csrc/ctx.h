@@ -108,6 +108,11 @@ struct b2_context {
     int* nl_flags = nullptr;     // [0] rebuild needed, [1] overflow, [2] rebuild counter, [3] max count
     bool lists_built = false;
 
+    // ---- profiling (eager mode only): CUDA-event pairs around every pair-force launch -------
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;         // start, stop, start, stop ...
+    std::vector<int> prof_tags;                   // pair force handle per pair of events
+
     // ---- energies --------------------------------------------------------------------------
     double* d_energy = nullptr;  // [32] energy + [32] virial + [2] dE/dlambda + pad
     double h_energy[32] = {0}, h_virial[32] = {0}, h_dlambda[2] = {0};

@@ -249,7 +249,8 @@ int program_run(b2_context* ctx, int nsteps) {
     // slot it assumed valid at entry is valid now; otherwise one step runs eagerly, which
     // restores the steady-state pattern.  The first step always runs eagerly (it also performs
     // all lazy allocations, which are illegal during capture).
-    static const bool use_graph = getenv("B2_NO_GRAPH") == nullptr;
+    static const bool graph_allowed = getenv("B2_NO_GRAPH") == nullptr;
+    const bool use_graph = graph_allowed && !ctx->profiling;
     for (int done = 0; done < nsteps; done++) {
         const unsigned long long entry = valid_mask(ctx);
         if (use_graph && ctx->graph_ready && (entry & ctx->graph_entry_mask) == ctx->graph_entry_mask) {

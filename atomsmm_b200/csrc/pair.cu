@@ -95,7 +95,8 @@ template <class POT, bool MINIMG>
 __device__ __forceinline__ void sweep_chunk(const POT& pot, const float4* __restrict__ sx,
                                             const float4* __restrict__ sp, int jj, int il, float4 xi,
                                             float qi, float hsi, float sei, float rc2, float3 box, float3 inv,
-                                            float& fx, float& fy, float& fz) {
+                                            double& ax, double& ay, double& az) {
+    float fx = 0.f, fy = 0.f, fz = 0.f;   // fp32 partial sums over one chunk (<= 8 pairs per lane)
 #pragma unroll
     for (int s = 0; s < 8; s++) {
         const int jl = 4*s + jj;
@@ -116,6 +117,7 @@ __device__ __forceinline__ void sweep_chunk(const POT& pot, const float4* __rest
             fx += fr*dx; fy += fr*dy; fz += fr*dz;
         }
     }
+    ax += (double)fx; ay += (double)fy; az += (double)fz;   // fp64 across chunks: no long fp32 sums
 }
 
 // relative position of atom a with respect to the group's reference point, minimum image, computed
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const
     const int cnt = counts[warp];
     const int* __restrict__ base = entries + (size_t)warp*cap;
     const int pad = (int)(0xff000000u | (unsigned)i0);
-    float fx = 0.f, fy = 0.f, fz = 0.f;
+    double fx = 0.0, fy = 0.0, fz = 0.0;
     int buf = 0;
     // software pipeline: gather chunk c+1 while chunk c is being swept
     int e = lane < cnt ? base[lane] : pad;
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const
     fx += __shfl_xor_sync(FULL, fx, 1); fy += __shfl_xor_sync(FULL, fy, 1); fz += __shfl_xor_sync(FULL, fz, 1);
     fx += __shfl_xor_sync(FULL, fx, 2); fy += __shfl_xor_sync(FULL, fy, 2); fz += __shfl_xor_sync(FULL, fz, 2);
     if (jj == 0 && i < n) {
-        float4 f = make_float4(fx, fy, fz, 0.f);
+        float4 f = make_float4((float)fx, (float)fy, (float)fz, 0.f);
         if (accumulate) {
             const float4 o = out[i];
             f.x += o.x; f.y += o.y; f.z += o.z;
@@ -304,10 +306,20 @@ template <class POT>
 static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, float rc2, float4* out, bool accumulate) {
     const NList& L = ctx->lists[pf.list];
     const int blocks = (ctx->ngroups + WPB - 1)/WPB;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->profiling) {
+        cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+        cudaEventRecord(ev0, ctx->stream);
+    }
     k_pair_force<POT><<<blocks, 32*WPB, 0, ctx->stream>>>(ctx->n, ctx->ngroups, ctx->x, ctx->par[pf.set],
                                                           L.entries, L.counts, L.gflags, L.cap, out,
                                                           accumulate ? 1 : 0, pot, rc2, ctx->box[0], ctx->box[1],
                                                           ctx->box[2]);
+    if (ctx->profiling) {
+        cudaEventRecord(ev1, ctx->stream);
+        ctx->prof_events.push_back(ev0); ctx->prof_events.push_back(ev1);
+        ctx->prof_tags.push_back((int)(&pf - ctx->pair_forces.data()));
+    }
     ctx->counters[2]++;
     B2_LAUNCH_CHECK();
     return B2_OK;

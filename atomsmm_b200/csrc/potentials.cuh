@@ -25,6 +25,8 @@ enum { VAR_NONE = 0, VAR_SHIFT = 1, VAR_FSWITCH = 2 };
 
 __device__ __forceinline__ float b2_rsqrt(float x) { return rsqrtf(x); }
 __device__ __forceinline__ double b2_rsqrt(double x) { return 1.0/sqrt(x); }
+__device__ __forceinline__ float b2_rcp(float x) { return __frcp_rn(x); }   // correctly rounded
+__device__ __forceinline__ double b2_rcp(double x) { return 1.0/x; }
 __device__ __forceinline__ float b2_erfc(float x) { return erfcf(x); }
 __device__ __forceinline__ double b2_erfc(double x) { return erfc(x); }
 __device__ __forceinline__ float b2_exp(float x) { return __expf(x); }
@@ -72,9 +74,11 @@ struct LJCPot {
 
     template <bool WANT_E>
     __device__ __forceinline__ void operator()(T r2, T qq, T sig, T eps, T& rF, T& e) const {
+        // (sigma/r)^2 from a correctly rounded 1/r^2: the r^-12 term amplifies any error in 1/r
+        // twelve-fold, so the 2-ulp rsqrt is only used where it enters linearly
         const T rinv = b2_rsqrt(r2);
         const T r = r2*rinv;
-        const T s2 = sig*sig*rinv*rinv;
+        const T s2 = sig*sig*b2_rcp(r2);
         const T s6 = s2*s2*s2;
         T elj, rflj;
         if (LJ == LJ_STD) {

@@ -62,6 +62,9 @@ _SIGNATURES = {
     'b2_get_perdof': [c_void, ctypes.c_int, c_void],
     'b2_run': [c_void, ctypes.c_int],
     'b2_get_counters': [c_void, ctypes.POINTER(ctypes.c_longlong)],
+    'b2_set_profiling': [c_void, ctypes.c_int],
+    'b2_get_profile': [c_void, ctypes.c_int, c_double_p, ctypes.POINTER(ctypes.c_longlong),
+                       ctypes.POINTER(ctypes.c_longlong)],
 }
 
 
@@ -687,6 +690,19 @@ class Context(object):
         self._call('b2_get_counters', out)
         return dict(launches=out[0], rebuilds=out[1], pair_launches=out[2], list_capacity=out[3],
                     list_max=out[4], graph_launches=out[5], kernels_per_step=out[6])
+
+    def set_profiling(self, on):
+        self._call('b2_set_profiling', 1 if on else 0)
+
+    def pair_profile(self):
+        """[(description, group, total_ms, launches, list_entries)] for every pair force."""
+        out = []
+        for handle, info, force in self._pair_handles.values():
+            ms, launches, entries = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_longlong()
+            self._call('b2_get_profile', handle, ctypes.byref(ms), ctypes.byref(launches), ctypes.byref(entries))
+            out.append(dict(name=info.get('name'), group=force.getForceGroup(), total_ms=ms.value,
+                            launches=launches.value, entries=entries.value))
+        return out
 
     def synchronize(self):
         self._call('b2_synchronize')

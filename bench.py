@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""
+Benchmark of the hot path (BASELINE.json metric: atom-steps/s and ns/day; pair-kernel HBM GB/s).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2]
+
+Workload (config.workload): BASELINE config 2 -- the q-SPC-FW water box replicated 4x4x4
+(98 304 atoms, L = 10 nm, +-0.002 nm jitter, seed 1), RESPASystem (near force-switch 0.7/0.5 nm in
+group 1, full LJ + reaction-field Coulomb rc 1.0 nm in group 2, bonded terms in group 0),
+integrator TrotterSuzuki(Respa([4,2,1]), SuzukiYoshida(NoseHoover(300 K, dof, 100 fs), 3)) at 4 fs.
+
+A bench "step" is one call integrator.step(MD_STEPS_PER_CALL) (default 100 outer MD steps): one
+pass of the hot path over one batch.  `value` times K such calls with state resident in HBM;
+`e2e` times the same through the public API with HOST buffers: upload of positions+velocities from
+pinned host memory, the MD steps, download of positions+velocities+energies, every step.
+
+N > 1: the path shards only by domain decomposition (next round) or as independent replicas; this
+bench runs N independent replicas, one per GPU, no data-path collective ("scaling": "weak").
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+MD_STEPS_PER_CALL = 100
+DT_FS = 4.0
+LOOPS = [4, 2, 1]
+
+
+def build_workload(reps):
+    import numpy as np
+    import atomsmm_b200 as atomsmm
+    from atomsmm_b200 import app, unit
+    import systems
+    system, pdb = systems.flexible('q-SPC-FW', app.CutoffPeriodic)
+    respa = atomsmm.RESPASystem(system, 7*unit.angstroms, 5*unit.angstroms)
+    base_pos = systems.positions_of(pdb)
+    box = np.array([2.5, 2.5, 2.5])
+    if reps > 1:
+        big, pos = systems.replicate(respa, base_pos, box, reps)
+    else:
+        big, pos = respa, base_pos
+    n = big.getNumParticles()
+    mass = np.array([big.getParticleMass(i).value_in_md_units() for i in range(n)])
+    rng = np.random.Generator(np.random.Philox(1234))
+    vel = rng.standard_normal((n, 3))*np.sqrt(8.314472471220217e-3*300.0/mass)[:, None]
+    vel -= (mass[:, None]*vel).sum(0)/mass.sum()
+    return big, pos, vel
+
+
+def make_integrator(system):
+    import atomsmm_b200 as atomsmm
+    from atomsmm_b200 import unit
+    dof = atomsmm.countDegreesOfFreedom(system)
+    nh = atomsmm.NoseHooverPropagator(300*unit.kelvin, dof, 100*unit.femtoseconds)
+    return atomsmm.TrotterSuzukiPropagator(atomsmm.RespaPropagator(LOOPS),
+                                           atomsmm.SuzukiYoshidaPropagator(nh, 3)).integrator(DT_FS*unit.femtoseconds), dof
+
+
+class ClockSampler(object):
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, value in zip(names, parts[5:9]):
+                if value.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm)//2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as handle:
+            return float(json.load(handle)['hbm_gbs']), 'measured'
+    return 6650.0, 'fallback'
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the float64 C/OpenMP restatement of the reference algorithm (oracle/c/oracle.c) on
+    all host cores; each step is a bounded sample (a few outer MD steps) of the same workload."""
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import cport
+    system, pos, vel = build_workload(args.reps)
+    n = system.getNumParticles()
+    integrator, dof = make_integrator(system)
+    g = dict(zip([integrator.getGlobalVariableName(k) for k in range(integrator.getNumGlobalVariables())],
+                 integrator._global_values))
+    cores = os.cpu_count()
+    port = cport.CPort(system, threads=cores, verify=False)
+    sample = max(1, args.cpu_md_steps)
+    x, v, p_eta = pos.copy(), vel.copy(), 0.0
+    for _ in range(args.warmup):
+        x, v, p_eta = port.respa(x, v, 1, DT_FS*1e-3, LOOPS[0], LOOPS[1], (1, g['LkT'], g['Q'], p_eta))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        x, v, p_eta = port.respa(x, v, sample, DT_FS*1e-3, LOOPS[0], LOOPS[1], (1, g['LkT'], g['Q'], p_eta))
+    elapsed = time.perf_counter() - t0
+    value = n*sample*args.steps/elapsed
+    line = dict(metric='atom-steps/s', value=value, unit='atom-steps/s', n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3*elapsed/args.steps, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f64', data='synthetic', impl='reference',
+                config=workload_config(args, n, sample),
+                ns_per_day=sample*args.steps*DT_FS*1e-6*86400/elapsed,
+                cpu_baseline=dict(value=value, unit='atom-steps/s', cores=cores, kind='port',
+                                  sample='%d outer MD steps per step of the %d-atom workload, C/OpenMP float64 '
+                                         'restatement of the reference algorithm (OpenMM itself is not installable '
+                                         'offline)' % (sample, n)),
+                e2e=dict(value=value, unit='atom-steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def workload_config(args, n, md_steps):
+    return dict(workload='c2: q-SPC-FW water x%d^3, %d atoms, RESPASystem near 0.7/0.5 nm force-switch + LJ/reaction-field '
+                         '1.0 nm, RESPA [4,2,1] + NoseHoover SY3, dt 4 fs' % (args.reps, n),
+                atoms=n, md_steps_per_step=md_steps, dt_fs=DT_FS, loops=LOOPS, replicas=args.gpus,
+                l2_policy='state and neighbour lists of this workload (~110 MB) do not fit a flush-free L2 reuse '
+                          'pattern: every bench step streams %d MD steps x (lists 2x ~50 MB + state), far beyond '
+                          'the 126 MB L2; no explicit flush' % md_steps)
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--gpus', type=int, default=1)
+    parser.add_argument('--steps', type=int, default=10)
+    parser.add_argument('--warmup', type=int, default=3)
+    parser.add_argument('--impl', default='b200')
+    parser.add_argument('--reps', type=int, default=4, help='replication of the 1 536-atom cell per axis')
+    parser.add_argument('--md-steps', type=int, default=MD_STEPS_PER_CALL)
+    parser.add_argument('--cpu-md-steps', type=int, default=2)
+    parser.add_argument('--no-cpu-baseline', action='store_true')
+    args = parser.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != 'reference' else max(args.warmup, 1)
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from atomsmm_b200 import mm, unit
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the engine has no CPU path')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    system, pos, vel = build_workload(args.reps)
+    n = system.getNumParticles()
+    integrator, dof = make_integrator(system)
+    integrator.setRandomNumberSeed(1 + rank)
+    context = mm.Context(system, integrator, mm.Platform.getPlatformByName('B200'), {'DeviceIndex': local})
+    context.setPositions(pos)
+    context.setVelocities(vel)
+    md = args.md_steps
+    stream = context._stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-state timing ---------------------------------------------------------------------
+    for _ in range(args.warmup):
+        integrator.step(md)
+    context.synchronize()
+    before = context.counters()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        start.record(stream)
+        for _ in range(args.steps):
+            integrator.step(md)
+        stop.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    context.synchronize()
+    elapsed = start.elapsed_time(stop)*1e-3
+    after = context.counters()
+    launches = (after['launches'] - before['launches']) + \
+        (after['graph_launches'] - before['graph_launches'])*after['kernels_per_step']
+    t = torch.tensor([elapsed], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed = float(t.item())
+    value = world*n*md*args.steps/elapsed
+
+    # ---- end to end through the public API with host buffers --------------------------------------
+    host_x = torch.from_numpy(pos.copy()).pin_memory()
+    host_v = torch.from_numpy(vel.copy()).pin_memory()
+    state = context.getState(getPositions=True, getVelocities=True)
+    host_x.copy_(torch.from_numpy(state.getPositions(asNumpy=True).value_in_unit(unit.nanometer)))
+    host_v.copy_(torch.from_numpy(state.getVelocities(asNumpy=True).value_in_unit(unit.nanometer/unit.picosecond)))
+    e2e_steps = max(3, args.steps//2)
+
+    def e2e_step():
+        context.setPositions(host_x)
+        context.setVelocities(host_v)
+        integrator.step(md)
+        s = context.getState(getPositions=True, getVelocities=True, getEnergy=True)
+        host_x.copy_(torch.from_numpy(s._positions))
+        host_v.copy_(torch.from_numpy(s._velocities))
+        return s._potential + s._kinetic
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        energy = e2e_step()
+    barrier()
+    e2e_elapsed = time.perf_counter() - t0
+    t = torch.tensor([e2e_elapsed], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world*n*md*e2e_steps/float(t.item())
+    state_bytes = 2*n*3*8
+
+    # ---- roofline of the dominant kernel: CUDA events around every pair launch, eager pass --------
+    context.set_profiling(True)
+    integrator.step(8)
+    profile = context.pair_profile()
+    context.set_profiling(False)
+    peak, peak_kind = measured_peak()
+    used = [p for p in profile if p['launches'] > 0]
+    dominant = max(used, key=lambda p: p['total_ms'])
+    avg_s = dominant['total_ms']*1e-3/dominant['launches']
+    bytes_per_launch = n*(24 + 16 + 16) + 4*dominant['entries']
+    achieved = bytes_per_launch/avg_s/1e9
+    pair_ms_per_md_step = sum(p['total_ms'] for p in used)/8.0
+    roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved/peak, traffic=None,
+                    peak_kind=peak_kind, kernel='k_pair_force<%s> group %d' % (dominant['name'], dominant['group']),
+                    avg_launch_us=avg_s*1e6, algorithmic_bytes_per_launch=bytes_per_launch,
+                    list_entries=dominant['entries'],
+                    pair_kernels_share_of_step=pair_ms_per_md_step/(1e3*elapsed/(args.steps*md)),
+                    note='pair tiles are fp32-issue bound, not HBM bound (SURVEY 8d): algorithmic bytes = N*(24 B x + '
+                         '16 B params + 16 B force) + 4 B per neighbour-list entry; timed in a separate eager pass '
+                         'of the same step program with CUDA events on the launch stream')
+
+    line = dict(metric='atom-steps/s', value=value, unit='atom-steps/s', n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3*elapsed/args.steps, higher_is_better=True, scaling='weak',
+                vs_baseline=None, dtype='f32 pair forces / f64 state', data='synthetic',
+                config=workload_config(args, n, md), ns_per_day=md*args.steps*DT_FS*1e-6*86400/elapsed,
+                clocks=clocks, gpu_launches=int(launches),
+                e2e=dict(value=e2e_value, unit='atom-steps/s', h2d_bytes_per_step=state_bytes,
+                         d2h_bytes_per_step=state_bytes + 16, final_energy=energy),
+                roofline=roofline, engine=dict(kernels_per_md_step=after['kernels_per_step'],
+                                               list_rebuilds=after['rebuilds'], list_capacity=after['list_capacity']))
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cport
+        cores = os.cpu_count()
+        port = cport.CPort(system, threads=cores, verify=False)
+        g = dict(zip([integrator.getGlobalVariableName(k) for k in range(integrator.getNumGlobalVariables())],
+                     integrator._global_values))
+        x, v, p_eta = port.respa(pos, vel, 1, DT_FS*1e-3, LOOPS[0], LOOPS[1], (1, g['LkT'], g['Q'], 0.0))
+        sample = 4
+        t0 = time.perf_counter()
+        port.respa(x, v, sample, DT_FS*1e-3, LOOPS[0], LOOPS[1], (1, g['LkT'], g['Q'], p_eta))
+        cpu_elapsed = time.perf_counter() - t0
+        line['cpu_baseline'] = dict(value=n*sample/cpu_elapsed, unit='atom-steps/s', cores=cores, kind='port',
+                                    sample='%d outer MD steps of the same %d-atom workload (after 1 warm-up step), '
+                                           'C/OpenMP float64 restatement of the reference algorithm' % (sample, n))
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -173,6 +173,13 @@ B2_API int b2_run(b2_context* ctx, int nsteps);
  * launches, [3] list capacity (entries per 8-atom group, largest list), [4] largest count seen */
 B2_API int b2_get_counters(b2_context* ctx, long long out_host[8]);
 
+/* profiling aid for bench.py: while on, steps run eagerly (no CUDA graph) and every pair-force
+ * launch is bracketed by CUDA events on the context's stream.  b2_get_profile returns the summed
+ * duration and launch count of pair force `handle`, and the current number of list entries it
+ * reads per launch (for the algorithmic-bytes figure). */
+B2_API int b2_set_profiling(b2_context* ctx, int on);
+B2_API int b2_get_profile(b2_context* ctx, int handle, double* total_ms, long long* launches, long long* entries);
+
 #ifdef __cplusplus
 }
 #endif
