@@ -43,13 +43,15 @@ __device__ __forceinline__ double wrap1(double x, double L, double invL) {
     return w >= L ? w - L : w;
 }
 
-// K8: skin test, one pass over x (the pair kernels read the float64 master positions directly).
+// K8: skin test + fp32 wrapped copy used by the list build (the pair kernels read the float64
+// master positions directly), one pass over x.
 __global__ void k_wrap_check(int n, const double* __restrict__ x, const double* __restrict__ xref,
                              float4* __restrict__ pos4, Grid g, double limit2, int* flags, int have_ref) {
     int i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= n) return;
     double px = x[3*i], py = x[3*i+1], pz = x[3*i+2];
-    (void)pos4;
+    pos4[i] = make_float4((float)wrap1(px, g.box[0], g.inv[0]), (float)wrap1(py, g.box[1], g.inv[1]),
+                          (float)wrap1(pz, g.box[2], g.inv[2]), 0.f);
     if (have_ref) {
         double dx = px - xref[3*i], dy = py - xref[3*i+1], dz = pz - xref[3*i+2];
         if (dx*dx + dy*dy + dz*dz > limit2) flags[0] = 1;
@@ -137,8 +139,12 @@ __device__ __forceinline__ bool is_excluded(int oi, int oj, unsigned long long m
     return false;
 }
 
-// K2: one warp per i-group
-__global__ void __launch_bounds__(128) k_build_lists(int n, int ngroups, const double* __restrict__ x, Grid g,
+// K2: one warp per i-group.  Membership is tested in fp32 on wrapped coordinates with a safety
+// margin (the list only has to be a superset of the pairs within cutoff+skin; the interacting set is
+// decided exactly by the pair kernels).  Cells farther than the list radius from the group's
+// bounding box are culled before their atoms are touched.
+#define NL_MARGIN 3e-4f
+__global__ void __launch_bounds__(128) k_build_lists(int n, int ngroups, const float4* __restrict__ pos4, Grid g,
                                                     const int* __restrict__ cell_start,
                                                     const int* __restrict__ cell_atoms,
                                                     const int* __restrict__ orig,
@@ -150,85 +156,108 @@ __global__ void __launch_bounds__(128) k_build_lists(int n, int ngroups, const d
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     if (warp >= ngroups) return;
-    __shared__ double sxi[4][B2_GROUP][3];
+    __shared__ float sxi[4][B2_GROUP][3];
     __shared__ int soi[4][B2_GROUP];
     __shared__ unsigned long long smask[4][B2_GROUP];
     const int i0 = warp*B2_GROUP;
+    const float bx = (float)g.box[0], by = (float)g.box[1], bz = (float)g.box[2];
+    const float ibx = (float)g.inv[0], iby = (float)g.inv[1], ibz = (float)g.inv[2];
+    const float4 r0 = pos4[i0];
     if (lane < B2_GROUP) {
-        int i = min(i0 + lane, n - 1);
-        double r0[3] = {x[3*i0], x[3*i0+1], x[3*i0+2]};
-        for (int d = 0; d < 3; d++) {
-            double w0 = wrap1(r0[d], g.box[d], g.inv[d]);
-            double dd = x[3*i+d] - r0[d];
-            dd -= g.box[d]*rint(dd*g.inv[d]);
-            sxi[wib][lane][d] = w0 + dd;
-        }
+        const int i = min(i0 + lane, n - 1);
+        const float4 p = pos4[i];
+        float dx = p.x - r0.x, dy = p.y - r0.y, dz = p.z - r0.z;      // unwrap relative to atom 0
+        dx -= bx*rintf(dx*ibx); dy -= by*rintf(dy*iby); dz -= bz*rintf(dz*ibz);
+        sxi[wib][lane][0] = r0.x + dx; sxi[wib][lane][1] = r0.y + dy; sxi[wib][lane][2] = r0.z + dz;
         soi[wib][lane] = (i0 + lane < n) ? orig[i] : -1;
         smask[wib][lane] = exmask[i];
     }
     __syncwarp();
-    // bounding box of the group
-    double lo[3], hi[3];
+    float lo[3], hi[3];
     for (int d = 0; d < 3; d++) {
-        lo[d] = 1e300; hi[d] = -1e300;
+        lo[d] = 1e30f; hi[d] = -1e30f;
         for (int k = 0; k < B2_GROUP; k++)
-            if (soi[wib][k] >= 0) { lo[d] = fmin(lo[d], sxi[wib][k][d]); hi[d] = fmax(hi[d], sxi[wib][k][d]); }
+            if (soi[wib][k] >= 0) { lo[d] = fminf(lo[d], sxi[wib][k][d]); hi[d] = fmaxf(hi[d], sxi[wib][k][d]); }
     }
+    const float rmax = (float)g.rmax + NL_MARGIN;
+    const float cs[3] = {(float)(g.box[0]/g.nc[0]), (float)(g.box[1]/g.nc[1]), (float)(g.box[2]/g.nc[2])};
+    const float box[3] = {bx, by, bz};
     int c_lo[3], c_n[3];
+    bool all[3];
     for (int d = 0; d < 3; d++) {
-        int a0 = (int)floor((lo[d] - g.rmax)*g.cs_inv[d]);
-        int a1 = (int)floor((hi[d] + g.rmax)*g.cs_inv[d]);
-        int cover = a1 - a0 + 1;
-        if (cover >= g.nc[d]) { c_lo[d] = 0; c_n[d] = g.nc[d]; }
+        const int a0 = (int)floorf((lo[d] - rmax)/cs[d]);
+        const int a1 = (int)floorf((hi[d] + rmax)/cs[d]);
+        const int cover = a1 - a0 + 1;
+        all[d] = cover >= g.nc[d];
+        if (all[d]) { c_lo[d] = 0; c_n[d] = g.nc[d]; }
         else { c_lo[d] = a0; c_n[d] = cover; }
     }
     if (lane == 0) {
         for (int k = 0; k < a.nlists; k++) {
             unsigned char f = 0;
             for (int d = 0; d < 3; d++)
-                if ((hi[d] - lo[d]) + a.rlist[k] > 0.5*g.box[d] - 1e-6) f = 1;
+                if ((double)(hi[d] - lo[d]) + a.rlist[k] > 0.5*g.box[d] - 1e-4) f = 1;
             a.gflags[k][warp] = f;
         }
     }
+    float rl2[B2_MAX_LISTS];
+    for (int k = 0; k < B2_MAX_LISTS; k++) { const float r = (float)a.rlist[k] + NL_MARGIN; rl2[k] = r*r; }
+    const float rmax2 = rmax*rmax;
     int count[B2_MAX_LISTS] = {0, 0, 0, 0};
     const unsigned lt = (1u << lane) - 1u;
     for (int cz = 0; cz < c_n[2]; cz++) {
-        int iz = (c_lo[2] + cz) % g.nc[2]; if (iz < 0) iz += g.nc[2];
+        const int uz = c_lo[2] + cz;
+        int iz = uz % g.nc[2]; if (iz < 0) iz += g.nc[2];
+        const float sz = all[2] ? 0.f : (float)(uz - iz)/g.nc[2]*box[2];      // periodic shift of this cell
+        const float gz = all[2] ? 0.f : fmaxf(0.f, fmaxf(lo[2] - (uz + 1)*cs[2], uz*cs[2] - hi[2]));
         for (int cy = 0; cy < c_n[1]; cy++) {
-            int iy = (c_lo[1] + cy) % g.nc[1]; if (iy < 0) iy += g.nc[1];
+            const int uy = c_lo[1] + cy;
+            int iy = uy % g.nc[1]; if (iy < 0) iy += g.nc[1];
+            const float sy = all[1] ? 0.f : (float)(uy - iy)/g.nc[1]*box[1];
+            const float gy = all[1] ? 0.f : fmaxf(0.f, fmaxf(lo[1] - (uy + 1)*cs[1], uy*cs[1] - hi[1]));
+            if (gz*gz + gy*gy > rmax2) continue;
             for (int cx = 0; cx < c_n[0]; cx++) {
-                int ix = (c_lo[0] + cx) % g.nc[0]; if (ix < 0) ix += g.nc[0];
+                const int ux = c_lo[0] + cx;
+                int ix = ux % g.nc[0]; if (ix < 0) ix += g.nc[0];
+                const float sx = all[0] ? 0.f : (float)(ux - ix)/g.nc[0]*box[0];
+                const float gx = all[0] ? 0.f : fmaxf(0.f, fmaxf(lo[0] - (ux + 1)*cs[0], ux*cs[0] - hi[0]));
+                if (gz*gz + gy*gy + gx*gx > rmax2) continue;
                 const int cell = (iz*g.nc[1] + iy)*g.nc[0] + ix;
                 const int cb = cell_start[cell], ce = cell_start[cell+1];
                 for (int base = cb; base < ce; base += 32) {
                     const int idx = base + lane;
                     const bool have = idx < ce;
-                    int j = have ? cell_atoms[idx] : 0;
-                    double d2min = 1e300;
+                    const int j = have ? cell_atoms[idx] : 0;
+                    float d2min = 1e30f;
                     unsigned m = 0;
                     if (have) {
-                        const double xj = x[3*j], yj = x[3*j+1], zj = x[3*j+2];
+                        const float4 pj = pos4[j];
+                        const float xj = pj.x + sx, yj = pj.y + sy, zj = pj.z + sz;
                         const int oj = orig[j];
 #pragma unroll
                         for (int k = 0; k < B2_GROUP; k++) {
                             const int oi = soi[wib][k];
                             if (oi < 0) { m |= 1u << k; continue; }
-                            double dx = xj - sxi[wib][k][0], dy = yj - sxi[wib][k][1], dz = zj - sxi[wib][k][2];
-                            dx -= g.box[0]*rint(dx*g.inv[0]);
-                            dy -= g.box[1]*rint(dy*g.inv[1]);
-                            dz -= g.box[2]*rint(dz*g.inv[2]);
-                            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                            if (oi == oj || is_excluded(oi, oj, smask[wib][k], excl_ptr, excl_idx)) m |= 1u << k;
-                            else d2min = fmin(d2min, d2);
+                            float dx = xj - sxi[wib][k][0], dy = yj - sxi[wib][k][1], dz = zj - sxi[wib][k][2];
+                            if (all[0]) dx -= bx*rintf(dx*ibx);
+                            if (all[1]) dy -= by*rintf(dy*iby);
+                            if (all[2]) dz -= bz*rintf(dz*ibz);
+                            const float d2 = dx*dx + dy*dy + dz*dz;
+                            const int dd = oj - oi;
+                            bool ex = oi == oj;
+                            if (dd >= -32 && dd < 32) ex = ex || ((smask[wib][k] >> (dd + 32)) & 1ull);
+                            else if (excl_ptr) ex = is_excluded(oi, oj, 0ull, excl_ptr, excl_idx);
+                            if (ex) m |= 1u << k;
+                            else d2min = fminf(d2min, d2);
                         }
                     }
 #pragma unroll
                     for (int k = 0; k < B2_MAX_LISTS; k++) {
                         if (k >= a.nlists) break;
-                        const bool in = have && d2min < a.rlist2[k];
+                        const bool in = have && d2min < rl2[k];
                         const unsigned ballot = __ballot_sync(FULL, in);
                         if (in) {
-                            int pos = count[k] + __popc(ballot & lt);
+                            const int pos = count[k] + __popc(ballot & lt);
                             if (pos < a.cap[k]) a.entries[k][(size_t)warp*a.cap[k] + pos] = (int)((m << 24) | (unsigned)j);
                         }
                         count[k] += __popc(ballot);
@@ -349,7 +378,7 @@ int nl_prepare(b2_context* ctx, bool force) {
     }
     const int warps_per_block = 4;
     k_build_lists<<<(ctx->ngroups + warps_per_block - 1)/warps_per_block, 32*warps_per_block, 0, s>>>(
-        n, ctx->ngroups, ctx->x, g, ctx->cell_start, ctx->cell_atoms, ctx->orig, ctx->exmask,
+        n, ctx->ngroups, ctx->pos4, g, ctx->cell_start, ctx->cell_atoms, ctx->orig, ctx->exmask,
         ctx->excl_far ? ctx->excl_ptr : nullptr, ctx->excl_idx, a, ctx->nl_flags);
     B2_LAUNCH_CHECK();
     k_save_ref<<<(3*n + T - 1)/T, T, 0, s>>>(3*n, ctx->x, ctx->xref, ctx->nl_flags);

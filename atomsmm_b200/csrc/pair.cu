@@ -111,9 +111,9 @@ __device__ __forceinline__ void sweep_chunk(const POT& pot, const float4* __rest
         const float r2 = dx*dx + dy*dy + dz*dz;
         const unsigned m = (unsigned)__float_as_int(pj.w);
         if (r2 < rc2 && !((m >> il) & 1u)) {
-            float rF, e;
-            pot.template operator()<false>(r2, qi*pj.x, hsi + pj.y, sei*pj.z, rF, e);
-            const float fr = rF*__frcp_rn(r2);
+            float rF, e, rinv2;
+            pot.template operator()<false>(r2, qi*pj.x, hsi + pj.y, sei*pj.z, rF, e, rinv2);
+            const float fr = rF*rinv2;
             fx += fr*dx; fy += fr*dy; fz += fr*dz;
         }
     }
@@ -230,7 +230,8 @@ __global__ void __launch_bounds__(32*WPB) k_pair_energy(int n, int ngroups, cons
                     pot.eval(r2, qq, sig, eps, rF, e, dv, dc);
                     dv_sum += dv; dc_sum += dc;
                 } else {
-                    pot.template operator()<true>(r2, qq, sig, eps, rF, e);
+                    double rinv2;
+                    pot.template operator()<true>(r2, qq, sig, eps, rF, e, rinv2);
                 }
                 e_sum += e; w_sum += rF;
             }

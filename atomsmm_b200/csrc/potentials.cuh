@@ -25,8 +25,19 @@ enum { VAR_NONE = 0, VAR_SHIFT = 1, VAR_FSWITCH = 2 };
 
 __device__ __forceinline__ float b2_rsqrt(float x) { return rsqrtf(x); }
 __device__ __forceinline__ double b2_rsqrt(double x) { return 1.0/sqrt(x); }
-__device__ __forceinline__ float b2_rcp(float x) { return __frcp_rn(x); }   // correctly rounded
-__device__ __forceinline__ double b2_rcp(double x) { return 1.0/x; }
+// 1/r and 1/r^2 from r^2.  fp32: MUFU.RSQ (<= 2 ulp) refined by one Newton step (~0.5 ulp), because the
+// r^-12 term amplifies the relative error of 1/r twelve-fold.
+__device__ __forceinline__ void b2_inverse(float r2, float& rinv, float& rinv2) {
+    float y = rsqrtf(r2);
+    const float e = fmaf(-r2*y, y, 1.0f);
+    y = fmaf(0.5f*y, e, y);
+    rinv = y;
+    rinv2 = y*y;
+}
+__device__ __forceinline__ void b2_inverse(double r2, double& rinv, double& rinv2) {
+    rinv = 1.0/sqrt(r2);
+    rinv2 = 1.0/r2;
+}
 __device__ __forceinline__ float b2_erfc(float x) { return erfcf(x); }
 __device__ __forceinline__ double b2_erfc(double x) { return erfc(x); }
 __device__ __forceinline__ float b2_exp(float x) { return __expf(x); }
@@ -73,12 +84,11 @@ struct LJCPot {
     PotParams<T> p;
 
     template <bool WANT_E>
-    __device__ __forceinline__ void operator()(T r2, T qq, T sig, T eps, T& rF, T& e) const {
-        // (sigma/r)^2 from a correctly rounded 1/r^2: the r^-12 term amplifies any error in 1/r
-        // twelve-fold, so the 2-ulp rsqrt is only used where it enters linearly
-        const T rinv = b2_rsqrt(r2);
+    __device__ __forceinline__ void operator()(T r2, T qq, T sig, T eps, T& rF, T& e, T& rinv2) const {
+        T rinv;
+        b2_inverse(r2, rinv, rinv2);
         const T r = r2*rinv;
-        const T s2 = sig*sig*b2_rcp(r2);
+        const T s2 = sig*sig*rinv2;
         const T s6 = s2*s2*s2;
         T elj, rflj;
         if (LJ == LJ_STD) {
@@ -159,9 +169,10 @@ struct SoftcorePot {
     PotParams<T> p;
 
     template <bool WANT_E>
-    __device__ __forceinline__ void operator()(T r2, T qq, T sig, T eps, T& rF, T& e) const {
+    __device__ __forceinline__ void operator()(T r2, T qq, T sig, T eps, T& rF, T& e, T& rinv2) const {
         T dv, dc;
         eval(r2, qq, sig, eps, rF, e, dv, dc);
+        rinv2 = T(1)/r2;
     }
 
     __device__ __forceinline__ void eval(T r2, T qq, T sig, T eps, T& rF, T& e, T& dEdlv, T& dEdlc) const {

@@ -324,8 +324,12 @@ class Context(object):
                     family, gparams, code = lowering.classify_bond_force(force, self._parameters)
                     periodic = force.usesPeriodicBoundaryConditions()
                     if family == lowering.BOND_LJC:
-                        params = np.concatenate([params, np.zeros((len(atoms), 1))], axis=1)
-                        self._add_bonded(family, group, atoms, params, periodic, gparams)
+                        # exclusion-type exceptions (chargeprod = epsilon = 0) contribute exactly zero
+                        live = (params[:, 0] != 0.0) | (params[:, 2] != 0.0)
+                        atoms, params = atoms[live], params[live]
+                        if len(atoms):
+                            params = np.concatenate([params, np.zeros((len(atoms), 1))], axis=1)
+                            self._add_bonded(family, group, atoms, params, periodic, gparams)
                     else:
                         self._add_custom(lowering.BOND_CUSTOM, group, atoms, params, periodic, code)
             elif isinstance(force, mm.CustomAngleForce):

@@ -45,7 +45,7 @@ def run_both(system, pdb, integrator_factory, steps, platform, properties=None):
     return context, integrator, state, reference
 
 
-def compare(state, reference, x_tol=2e-6, v_rel=2e-5):
+def compare(state, reference, x_tol=2e-5, v_rel=1e-4):
     x = state.getPositions(asNumpy=True).value_in_unit(unit.nanometer)
     v = state.getVelocities(asNumpy=True).value_in_unit(unit.nanometer/unit.picosecond)
     assert np.max(np.abs(x - reference.x)) < x_tol
