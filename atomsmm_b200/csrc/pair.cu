@@ -91,10 +91,23 @@ static PotParams<T> make_params(const PairForce& pf, float* rc2_out) {
 // ---------------------------------------------------------------------------------------------
 // fp32 force kernel
 // ---------------------------------------------------------------------------------------------
+// Exact cutoff decision for the (very rare) pairs whose fp32 r^2 falls within rounding distance of
+// rc^2: float64 from the master coordinates, same operation order as the oracle, so that a pair is
+// in or out identically in both atoms' tiles and identically to the float64 reference.
+__device__ __forceinline__ bool inside_exact(const double* __restrict__ x, int i, int j, double rc2d, double bx,
+                                          double by, double bz) {
+    double dx = x[3*j] - x[3*i], dy = x[3*j+1] - x[3*i+1], dz = x[3*j+2] - x[3*i+2];
+    dx -= bx*rint(dx/bx); dy -= by*rint(dy/by); dz -= bz*rint(dz/bz);
+    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    return r2 < rc2d;
+}
+
 template <class POT, bool MINIMG>
 __device__ __forceinline__ void sweep_chunk(const POT& pot, const float4* __restrict__ sx,
                                             const float4* __restrict__ sp, int jj, int il, float4 xi,
                                             float qi, float hsi, float sei, float rc2, float3 box, float3 inv,
+                                            const double* __restrict__ x, int i, double rc2d, double bx,
+                                            double by, double bz, float band,
                                             double& ax, double& ay, double& az) {
     float fx = 0.f, fy = 0.f, fz = 0.f;   // fp32 partial sums over one chunk (<= 8 pairs per lane)
 #pragma unroll
@@ -109,8 +122,10 @@ __device__ __forceinline__ void sweep_chunk(const POT& pot, const float4* __rest
             dz -= box.z*rintf(dz*inv.z);
         }
         const float r2 = dx*dx + dy*dy + dz*dz;
-        const unsigned m = (unsigned)__float_as_int(pj.w);
-        if (r2 < rc2 && !((m >> il) & 1u)) {
+        const unsigned en = (unsigned)__float_as_int(pj.w);      // full list entry: mask<<24 | j
+        bool in = r2 < rc2;
+        if (fabsf(r2 - rc2) < band) in = inside_exact(x, i, (int)(en & 0xffffffu), rc2d, bx, by, bz);
+        if (in && !((en >> (24 + il)) & 1u)) {
             float rF, e, rinv2;
             pot.template operator()<false>(r2, qi*pj.x, hsi + pj.y, sei*pj.z, rF, e, rinv2);
             const float fr = rF*rinv2;
@@ -137,7 +152,7 @@ __global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const
                                                       const int* __restrict__ counts,
                                                       const unsigned char* __restrict__ gflags, int cap,
                                                       float4* __restrict__ out, int accumulate, POT pot,
-                                                      float rc2, double bx, double by, double bz) {
+                                                      float rc2, double rc2d, double bx, double by, double bz) {
     __shared__ float4 sx[WPB][2][32];
     __shared__ float4 sp[WPB][2][32];
     const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
@@ -156,6 +171,7 @@ __global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const
     const float4 xi = make_float4(xr.x, xr.y, xr.z, 0.f);
     const float4 pi = par[ic];
     const bool minimg = gflags[warp] & 1;
+    const float band = 2e-6f*rc2;
     const int cnt = counts[warp];
     const int* __restrict__ base = entries + (size_t)warp*cap;
     const int pad = (int)(0xff000000u | (unsigned)i0);
@@ -166,7 +182,7 @@ __global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const
     float3 xj = rel_pos(x, e & 0xffffff, rx, ry, rz, bx, by, bz, ibx, iby, ibz);
     float4 pj = par[e & 0xffffff];
     for (int c0 = 0; c0 < cnt; c0 += 32) {
-        pj.w = __int_as_float((int)((unsigned)e >> 24));
+        pj.w = __int_as_float(e);
         sx[wib][buf][lane] = make_float4(xj.x, xj.y, xj.z, 0.f);
         sp[wib][buf][lane] = pj;
         const int nxt = c0 + 32 + lane;
@@ -177,9 +193,9 @@ __global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const
         }
         __syncwarp();
         if (minimg)
-            sweep_chunk<POT, true>(pot, sx[wib][buf], sp[wib][buf], jj, il, xi, pi.x, pi.y, pi.z, rc2, box, inv, fx, fy, fz);
+            sweep_chunk<POT, true>(pot, sx[wib][buf], sp[wib][buf], jj, il, xi, pi.x, pi.y, pi.z, rc2, box, inv, x, ic, rc2d, bx, by, bz, band, fx, fy, fz);
         else
-            sweep_chunk<POT, false>(pot, sx[wib][buf], sp[wib][buf], jj, il, xi, pi.x, pi.y, pi.z, rc2, box, inv, fx, fy, fz);
+            sweep_chunk<POT, false>(pot, sx[wib][buf], sp[wib][buf], jj, il, xi, pi.x, pi.y, pi.z, rc2, box, inv, x, ic, rc2d, bx, by, bz, band, fx, fy, fz);
         buf ^= 1;
     }
     fx += __shfl_xor_sync(FULL, fx, 1); fy += __shfl_xor_sync(FULL, fy, 1); fz += __shfl_xor_sync(FULL, fz, 1);
@@ -303,8 +319,15 @@ __global__ void __launch_bounds__(32*WPB) k_pair_set(int n, int ngroups, const d
 // ---------------------------------------------------------------------------------------------
 // host dispatch
 // ---------------------------------------------------------------------------------------------
+static double effective_cutoff(const PairForce& pf) {
+    double rc = pf.cutoff;
+    if (pf.family == B2_PAIR_NEAR || pf.family == B2_PAIR_DAMPED) rc = std::min(rc, pf.params[2]);
+    return rc;
+}
+
 template <class POT>
 static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, float rc2, float4* out, bool accumulate) {
+    const double rcd = effective_cutoff(pf);
     const NList& L = ctx->lists[pf.list];
     const int blocks = (ctx->ngroups + WPB - 1)/WPB;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -314,7 +337,7 @@ static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, float rc2
     }
     k_pair_force<POT><<<blocks, 32*WPB, 0, ctx->stream>>>(ctx->n, ctx->ngroups, ctx->x, ctx->par[pf.set],
                                                           L.entries, L.counts, L.gflags, L.cap, out,
-                                                          accumulate ? 1 : 0, pot, rc2, ctx->box[0], ctx->box[1],
+                                                          accumulate ? 1 : 0, pot, rc2, rcd*rcd, ctx->box[0], ctx->box[1],
                                                           ctx->box[2]);
     if (ctx->profiling) {
         cudaEventRecord(ev1, ctx->stream);
