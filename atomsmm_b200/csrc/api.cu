@@ -101,7 +101,9 @@ extern "C" int b2_create(int device, b2_context** out) {
     for (int g = 0; g < B2_FSLOTS; g++) ctx->fvalid[g] = -1;
     if (cudaMalloc(&ctx->d_energy, sizeof(double)*96) != cudaSuccess ||
         cudaMalloc(&ctx->rng_state, sizeof(unsigned long long)*4) != cudaSuccess ||
-        cudaMalloc(&ctx->sum_partial, sizeof(double)*1024) != cudaSuccess) {
+        cudaMalloc(&ctx->sum_partial, sizeof(double)*1024) != cudaSuccess ||
+        cudaMalloc(&ctx->band_pairs, sizeof(int)*2*ctx->band_capacity) != cudaSuccess ||
+        cudaMalloc(&ctx->band_count, sizeof(unsigned)) != cudaSuccess) {
         delete ctx;
         return b2_fail(nullptr, B2_ERR_CUDA, "device allocation failed");
     }
@@ -128,8 +130,10 @@ extern "C" int b2_destroy(b2_context* ctx) {
     for (double* p : ctx->perdof) cudaFree(p);
     for (int k = 0; k < B2_MAX_LISTS; k++) { cudaFree(ctx->lists[k].entries); cudaFree(ctx->lists[k].counts); cudaFree(ctx->lists[k].gflags); }
     cudaFree(ctx->cell_count); cudaFree(ctx->cell_start); cudaFree(ctx->cell_atoms); cudaFree(ctx->cell_of);
+    cudaFree(ctx->cpos); cudaFree(ctx->corig);
     cudaFree(ctx->nl_flags); cudaFree(ctx->d_energy); cudaFree(ctx->code); cudaFree(ctx->consts);
     cudaFree(ctx->globals); cudaFree(ctx->sum_partial); cudaFree(ctx->rng_state);
+    cudaFree(ctx->band_pairs); cudaFree(ctx->band_count);
     for (BondedForce& bf : ctx->bonded_forces) free_bonded(bf);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;

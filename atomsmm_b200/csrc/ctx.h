@@ -105,8 +105,15 @@ struct b2_context {
     int ncell[3] = {0, 0, 0}, ncells = 0;
     double cellsize[3] = {0, 0, 0};
     int *cell_count = nullptr, *cell_start = nullptr, *cell_atoms = nullptr, *cell_of = nullptr;
+    float4* cpos = nullptr;      // positions in cell order (w = atom index), for the list build
+    int* corig = nullptr;        // caller index in cell order
     int* nl_flags = nullptr;     // [0] rebuild needed, [1] overflow, [2] rebuild counter, [3] max count
     bool lists_built = false;
+
+    // ---- cutoff-band pairs settled in float64 (pair.cu) -----------------------------------
+    int* band_pairs = nullptr;
+    unsigned* band_count = nullptr;
+    unsigned band_capacity = 1u << 16;
 
     // ---- profiling (eager mode only): CUDA-event pairs around every pair-force launch -------
     bool profiling = false;

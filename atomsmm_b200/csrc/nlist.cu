@@ -128,6 +128,20 @@ __global__ void k_cell_sort(int ncells, const int* cell_start, int* cell_atoms, 
     }
 }
 
+// cell-ordered copies so that the list build streams candidates with coalesced loads
+__global__ void k_cell_pack(int n, const int* __restrict__ cell_atoms, const float4* __restrict__ pos4,
+                            const int* __restrict__ orig, float4* __restrict__ cpos, int* __restrict__ corig,
+                            const int* flags) {
+    if (!flags[0]) return;
+    int k = blockIdx.x*blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int j = cell_atoms[k];
+    float4 p = pos4[j];
+    p.w = __int_as_float(j);
+    cpos[k] = p;
+    corig[k] = orig[j];
+}
+
 __device__ __forceinline__ bool is_excluded(int oi, int oj, unsigned long long mask, const int* excl_ptr,
                                             const int* excl_idx) {
     int d = oj - oi;
@@ -146,7 +160,8 @@ __device__ __forceinline__ bool is_excluded(int oi, int oj, unsigned long long m
 #define NL_MARGIN 3e-4f
 __global__ void __launch_bounds__(128) k_build_lists(int n, int ngroups, const float4* __restrict__ pos4, Grid g,
                                                     const int* __restrict__ cell_start,
-                                                    const int* __restrict__ cell_atoms,
+                                                    const float4* __restrict__ cpos,
+                                                    const int* __restrict__ corig,
                                                     const int* __restrict__ orig,
                                                     const unsigned long long* __restrict__ exmask,
                                                     const int* __restrict__ excl_ptr,
@@ -208,32 +223,44 @@ __global__ void __launch_bounds__(128) k_build_lists(int n, int ngroups, const f
     for (int cz = 0; cz < c_n[2]; cz++) {
         const int uz = c_lo[2] + cz;
         int iz = uz % g.nc[2]; if (iz < 0) iz += g.nc[2];
-        const float sz = all[2] ? 0.f : (float)(uz - iz)/g.nc[2]*box[2];      // periodic shift of this cell
+        const float sz = all[2] ? 0.f : (float)((uz - iz)/g.nc[2])*box[2];      // periodic shift of this cell layer
         const float gz = all[2] ? 0.f : fmaxf(0.f, fmaxf(lo[2] - (uz + 1)*cs[2], uz*cs[2] - hi[2]));
         for (int cy = 0; cy < c_n[1]; cy++) {
             const int uy = c_lo[1] + cy;
             int iy = uy % g.nc[1]; if (iy < 0) iy += g.nc[1];
-            const float sy = all[1] ? 0.f : (float)(uy - iy)/g.nc[1]*box[1];
+            const float sy = all[1] ? 0.f : (float)((uy - iy)/g.nc[1])*box[1];
             const float gy = all[1] ? 0.f : fmaxf(0.f, fmaxf(lo[1] - (uy + 1)*cs[1], uy*cs[1] - hi[1]));
-            if (gz*gz + gy*gy > rmax2) continue;
-            for (int cx = 0; cx < c_n[0]; cx++) {
-                const int ux = c_lo[0] + cx;
-                int ix = ux % g.nc[0]; if (ix < 0) ix += g.nc[0];
-                const float sx = all[0] ? 0.f : (float)(ux - ix)/g.nc[0]*box[0];
-                const float gx = all[0] ? 0.f : fmaxf(0.f, fmaxf(lo[0] - (ux + 1)*cs[0], ux*cs[0] - hi[0]));
-                if (gz*gz + gy*gy + gx*gx > rmax2) continue;
-                const int cell = (iz*g.nc[1] + iy)*g.nc[0] + ix;
-                const int cb = cell_start[cell], ce = cell_start[cell+1];
+            const float rem2 = rmax2 - gz*gz - gy*gy;
+            if (rem2 < 0.f) continue;
+            // trim the x-range of this row of cells to the sphere cross-section, then walk it in runs
+            // of cells that share one periodic shift: a run is a contiguous range of the cell-ordered
+            // arrays
+            int u_first = c_lo[0], u_last = c_lo[0] + c_n[0] - 1;
+            if (!all[0]) {
+                const float reach = sqrtf(rem2);
+                u_first = max(u_first, (int)floorf((lo[0] - reach)/cs[0]));
+                u_last = min(u_last, (int)floorf((hi[0] + reach)/cs[0]));
+            }
+            const int row = (iz*g.nc[1] + iy)*g.nc[0];
+            int u = u_first;
+            while (u <= u_last) {
+                int wrap = u >= 0 ? u/g.nc[0] : -((-u + g.nc[0] - 1)/g.nc[0]);
+                const int ix0 = u - wrap*g.nc[0];
+                const int run_end = min(u_last, u + (g.nc[0] - 1 - ix0));
+                const int ix1 = ix0 + (run_end - u);
+                const float sx = all[0] ? 0.f : (float)wrap*box[0];
+                const int cb = cell_start[row + ix0], ce = cell_start[row + ix1 + 1];
                 for (int base = cb; base < ce; base += 32) {
                     const int idx = base + lane;
                     const bool have = idx < ce;
-                    const int j = have ? cell_atoms[idx] : 0;
                     float d2min = 1e30f;
                     unsigned m = 0;
+                    int j = 0;
                     if (have) {
-                        const float4 pj = pos4[j];
+                        const float4 pj = cpos[idx];
+                        j = __float_as_int(pj.w);
                         const float xj = pj.x + sx, yj = pj.y + sy, zj = pj.z + sz;
-                        const int oj = orig[j];
+                        const int oj = corig[idx];
 #pragma unroll
                         for (int k = 0; k < B2_GROUP; k++) {
                             const int oi = soi[wib][k];
@@ -263,6 +290,7 @@ __global__ void __launch_bounds__(128) k_build_lists(int n, int ngroups, const f
                         count[k] += __popc(ballot);
                     }
                 }
+                u = run_end + 1;
             }
         }
     }
@@ -325,6 +353,8 @@ int nl_setup(b2_context* ctx) {
     if (ctx->cell_atoms == nullptr) {
         B2_CUDA(cudaMalloc(&ctx->cell_atoms, sizeof(int)*ctx->n));
         B2_CUDA(cudaMalloc(&ctx->cell_of, sizeof(int)*ctx->n));
+        B2_CUDA(cudaMalloc(&ctx->cpos, sizeof(float4)*ctx->n));
+        B2_CUDA(cudaMalloc(&ctx->corig, sizeof(int)*ctx->n));
     }
     if (ctx->nl_flags == nullptr) {
         B2_CUDA(cudaMalloc(&ctx->nl_flags, sizeof(int)*8));
@@ -368,6 +398,8 @@ int nl_prepare(b2_context* ctx, bool force) {
     B2_LAUNCH_CHECK();
     k_cell_sort<<<(ctx->ncells + T - 1)/T, T, 0, s>>>(ctx->ncells, ctx->cell_start, ctx->cell_atoms, ctx->nl_flags);
     B2_LAUNCH_CHECK();
+    k_cell_pack<<<(n + T - 1)/T, T, 0, s>>>(n, ctx->cell_atoms, ctx->pos4, ctx->orig, ctx->cpos, ctx->corig, ctx->nl_flags);
+    B2_LAUNCH_CHECK();
     BuildArgs a;
     a.nlists = ctx->nlists;
     for (int k = 0; k < B2_MAX_LISTS; k++) {
@@ -378,7 +410,7 @@ int nl_prepare(b2_context* ctx, bool force) {
     }
     const int warps_per_block = 4;
     k_build_lists<<<(ctx->ngroups + warps_per_block - 1)/warps_per_block, 32*warps_per_block, 0, s>>>(
-        n, ctx->ngroups, ctx->pos4, g, ctx->cell_start, ctx->cell_atoms, ctx->orig, ctx->exmask,
+        n, ctx->ngroups, ctx->pos4, g, ctx->cell_start, ctx->cpos, ctx->corig, ctx->orig, ctx->exmask,
         ctx->excl_far ? ctx->excl_ptr : nullptr, ctx->excl_idx, a, ctx->nl_flags);
     B2_LAUNCH_CHECK();
     k_save_ref<<<(3*n + T - 1)/T, T, 0, s>>>(3*n, ctx->x, ctx->xref, ctx->nl_flags);

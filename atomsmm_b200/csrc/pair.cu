@@ -91,23 +91,22 @@ static PotParams<T> make_params(const PairForce& pf, float* rc2_out) {
 // ---------------------------------------------------------------------------------------------
 // fp32 force kernel
 // ---------------------------------------------------------------------------------------------
-// Exact cutoff decision for the (very rare) pairs whose fp32 r^2 falls within rounding distance of
-// rc^2: float64 from the master coordinates, same operation order as the oracle, so that a pair is
-// in or out identically in both atoms' tiles and identically to the float64 reference.
-__device__ __forceinline__ bool inside_exact(const double* __restrict__ x, int i, int j, double rc2d, double bx,
-                                          double by, double bz) {
-    double dx = x[3*j] - x[3*i], dy = x[3*j+1] - x[3*i+1], dz = x[3*j+2] - x[3*i+2];
-    dx -= bx*rint(dx/bx); dy -= by*rint(dy/by); dz -= bz*rint(dz/bz);
-    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    return r2 < rc2d;
-}
+// Pairs whose fp32 r^2 lies within rounding distance of rc^2 (a few hundred per launch) are not
+// decided here: they are recorded and settled by k_pair_band in float64 from the master
+// coordinates, with the oracle's operation order, so that a pair is in or out identically in both
+// atoms' tiles and identically to the float64 reference (Newton's third law holds exactly even for
+// potentials that are discontinuous at the cutoff, e.g. reaction field).
+struct BandBuffer {
+    int* pairs;          // int2 (sorted i, sorted j)
+    unsigned* count;
+    unsigned capacity;
+};
 
 template <class POT, bool MINIMG>
 __device__ __forceinline__ void sweep_chunk(const POT& pot, const float4* __restrict__ sx,
                                             const float4* __restrict__ sp, int jj, int il, float4 xi,
                                             float qi, float hsi, float sei, float rc2, float3 box, float3 inv,
-                                            const double* __restrict__ x, int i, double rc2d, double bx,
-                                            double by, double bz, float band,
+                                            int i, float rc2_lo, const BandBuffer& bb,
                                             double& ax, double& ay, double& az) {
     float fx = 0.f, fy = 0.f, fz = 0.f;   // fp32 partial sums over one chunk (<= 8 pairs per lane)
 #pragma unroll
@@ -123,9 +122,12 @@ __device__ __forceinline__ void sweep_chunk(const POT& pot, const float4* __rest
         }
         const float r2 = dx*dx + dy*dy + dz*dz;
         const unsigned en = (unsigned)__float_as_int(pj.w);      // full list entry: mask<<24 | j
-        bool in = r2 < rc2;
-        if (fabsf(r2 - rc2) < band) in = inside_exact(x, i, (int)(en & 0xffffffu), rc2d, bx, by, bz);
-        if (in && !((en >> (24 + il)) & 1u)) {
+        if (r2 < rc2 && !((en >> (24 + il)) & 1u)) {      // rc2 here is the OUTER edge of the band
+            if (r2 >= rc2_lo) {
+                const unsigned slot = atomicAdd(bb.count, 1u);
+                if (slot < bb.capacity && i >= 0) { bb.pairs[2*slot] = i; bb.pairs[2*slot+1] = (int)(en & 0xffffffu); }
+                continue;
+            }
             float rF, e, rinv2;
             pot.template operator()<false>(r2, qi*pj.x, hsi + pj.y, sei*pj.z, rF, e, rinv2);
             const float fr = rF*rinv2;
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const
                                                       const int* __restrict__ counts,
                                                       const unsigned char* __restrict__ gflags, int cap,
                                                       float4* __restrict__ out, int accumulate, POT pot,
-                                                      float rc2, double rc2d, double bx, double by, double bz) {
+                                                      float rc2, BandBuffer bb, double bx, double by, double bz) {
     __shared__ float4 sx[WPB][2][32];
     __shared__ float4 sp[WPB][2][32];
     const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const
     const float4 xi = make_float4(xr.x, xr.y, xr.z, 0.f);
     const float4 pi = par[ic];
     const bool minimg = gflags[warp] & 1;
-    const float band = 2e-6f*rc2;
+    const float rc2_lo = rc2*(1.f - 2e-6f), rc2_hi = rc2*(1.f + 2e-6f);
     const int cnt = counts[warp];
     const int* __restrict__ base = entries + (size_t)warp*cap;
     const int pad = (int)(0xff000000u | (unsigned)i0);
@@ -193,9 +195,9 @@ __global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const
         }
         __syncwarp();
         if (minimg)
-            sweep_chunk<POT, true>(pot, sx[wib][buf], sp[wib][buf], jj, il, xi, pi.x, pi.y, pi.z, rc2, box, inv, x, ic, rc2d, bx, by, bz, band, fx, fy, fz);
+            sweep_chunk<POT, true>(pot, sx[wib][buf], sp[wib][buf], jj, il, xi, pi.x, pi.y, pi.z, rc2_hi, box, inv, i < n ? i : -1, rc2_lo, bb, fx, fy, fz);
         else
-            sweep_chunk<POT, false>(pot, sx[wib][buf], sp[wib][buf], jj, il, xi, pi.x, pi.y, pi.z, rc2, box, inv, x, ic, rc2d, bx, by, bz, band, fx, fy, fz);
+            sweep_chunk<POT, false>(pot, sx[wib][buf], sp[wib][buf], jj, il, xi, pi.x, pi.y, pi.z, rc2_hi, box, inv, i < n ? i : -1, rc2_lo, bb, fx, fy, fz);
         buf ^= 1;
     }
     fx += __shfl_xor_sync(FULL, fx, 1); fy += __shfl_xor_sync(FULL, fy, 1); fz += __shfl_xor_sync(FULL, fz, 1);
@@ -207,6 +209,27 @@ __global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const
             f.x += o.x; f.y += o.y; f.z += o.z;
         }
         out[i] = f;
+    }
+}
+
+template <class POTD>
+__global__ void k_pair_band(const double* __restrict__ x, const double* __restrict__ pard, BandBuffer bb, POTD pot,
+                            double rc2d, double bx, double by, double bz, float4* __restrict__ out) {
+    const unsigned total = min(*bb.count, bb.capacity);
+    for (unsigned k = blockIdx.x*blockDim.x + threadIdx.x; k < total; k += gridDim.x*blockDim.x) {
+        const int i = bb.pairs[2*k], j = bb.pairs[2*k+1];
+        double dx = x[3*j] - x[3*i], dy = x[3*j+1] - x[3*i+1], dz = x[3*j+2] - x[3*i+2];
+        dx -= bx*rint(dx/bx); dy -= by*rint(dy/by); dz -= bz*rint(dz/bz);
+        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        if (r2 < rc2d) {
+            double rF, e, rinv2;
+            pot.template operator()<false>(r2, pard[3*i]*pard[3*j], 0.5*(pard[3*i+1] + pard[3*j+1]),
+                                           sqrt(pard[3*i+2]*pard[3*j+2]), rF, e, rinv2);
+            const double fr = -rF*rinv2;        // d points from i to j
+            atomicAdd(&out[i].x, (float)(fr*dx));
+            atomicAdd(&out[i].y, (float)(fr*dy));
+            atomicAdd(&out[i].z, (float)(fr*dz));
+        }
     }
 }
 
@@ -325,9 +348,12 @@ static double effective_cutoff(const PairForce& pf) {
     return rc;
 }
 
-template <class POT>
-static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, float rc2, float4* out, bool accumulate) {
+template <class POT, class POTD>
+static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, POTD potd, float rc2, float4* out,
+                        bool accumulate) {
     const double rcd = effective_cutoff(pf);
+    BandBuffer bb{ctx->band_pairs, ctx->band_count, ctx->band_capacity};
+    B2_CUDA(cudaMemsetAsync(ctx->band_count, 0, sizeof(unsigned), ctx->stream));
     const NList& L = ctx->lists[pf.list];
     const int blocks = (ctx->ngroups + WPB - 1)/WPB;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -337,7 +363,7 @@ static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, float rc2
     }
     k_pair_force<POT><<<blocks, 32*WPB, 0, ctx->stream>>>(ctx->n, ctx->ngroups, ctx->x, ctx->par[pf.set],
                                                           L.entries, L.counts, L.gflags, L.cap, out,
-                                                          accumulate ? 1 : 0, pot, rc2, rcd*rcd, ctx->box[0], ctx->box[1],
+                                                          accumulate ? 1 : 0, pot, rc2, bb, ctx->box[0], ctx->box[1],
                                                           ctx->box[2]);
     if (ctx->profiling) {
         cudaEventRecord(ev1, ctx->stream);
@@ -345,6 +371,9 @@ static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, float rc2
         ctx->prof_tags.push_back((int)(&pf - ctx->pair_forces.data()));
     }
     ctx->counters[2]++;
+    B2_LAUNCH_CHECK();
+    k_pair_band<POTD><<<8, 128, 0, ctx->stream>>>(ctx->x, ctx->pard[pf.set], bb, potd, rcd*rcd, ctx->box[0],
+                                                  ctx->box[1], ctx->box[2], out);
     B2_LAUNCH_CHECK();
     return B2_OK;
 }
@@ -386,11 +415,20 @@ static int launch_energy(b2_context* ctx, const PairForce& pf, POT pot, double r
     default: return b2_fail(ctx, B2_ERR_UNSUPPORTED, "unknown pair family %d", pf.family);                  \
     }
 
+template <class POT>
+struct DoubleOf;
+template <int A, int B, int C, int D, int E>
+struct DoubleOf<LJCPot<A, B, C, D, E, float>> { typedef LJCPot<A, B, C, D, E, double> type; };
+template <>
+struct DoubleOf<SoftcorePot<float>> { typedef SoftcorePot<double> type; };
+
 int pair_eval_forces(b2_context* ctx, const PairForce& pf, float4* out, bool accumulate) {
-    float rc2;
+    float rc2, unused;
     PotParams<float> p = make_params<float>(pf, &rc2);
-    DISPATCH(float, B2_TRY(launch_force(ctx, pf, pot, rc2, out, accumulate)),
-             B2_TRY(launch_force(ctx, pf, pot, rc2, out, accumulate)));
+    PotParams<double> pd = make_params<double>(pf, &unused);
+#define CALL_FORCE { typename DoubleOf<decltype(pot)>::type potd{pd}; B2_TRY(launch_force(ctx, pf, pot, potd, rc2, out, accumulate)); }
+    DISPATCH(float, CALL_FORCE, CALL_FORCE);
+#undef CALL_FORCE
     return B2_OK;
 }
 
