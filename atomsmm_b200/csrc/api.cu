@@ -609,6 +609,7 @@ extern "C" int b2_load_program(b2_context* ctx, const int* ops, int nops, const 
     B2_CUDA(cudaMalloc(&ctx->code, sizeof(int)*std::max(2, ncode)));
     B2_CUDA(cudaMalloc(&ctx->consts, sizeof(double)*std::max(1, nconsts)));
     B2_CUDA(cudaMalloc(&ctx->globals, sizeof(double)*std::max(1, nglobals)));
+    ctx->h_code.assign(code, code + ncode);
     if (ncode) B2_CUDA(cudaMemcpy(ctx->code, code, sizeof(int)*ncode, cudaMemcpyHostToDevice));
     if (nconsts) B2_CUDA(cudaMemcpy(ctx->consts, consts, sizeof(double)*nconsts, cudaMemcpyHostToDevice));
     if (nglobals) B2_CUDA(cudaMemcpy(ctx->globals, globals, sizeof(double)*nglobals, cudaMemcpyHostToDevice));

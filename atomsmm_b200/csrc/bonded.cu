@@ -53,10 +53,8 @@ __device__ __forceinline__ void block_accumulate(double e, double w, double* acc
 
 // two-body families: E(r); force from dE/dr
 template <bool FORCE, bool ENERGY>
-__global__ void k_bond2(BondArgs a, float4* out, double* acc) {
-    const int t = blockIdx.x*blockDim.x + threadIdx.x;
-    double e = 0, w = 0;
-    if (t < a.nterms) {
+__device__ __forceinline__ void term_bond2(const BondArgs& a, int t, float4* out, double& e, double& w) {
+    {
         const int i = a.inv[a.atoms[2*t]], j = a.inv[a.atoms[2*t+1]];
         const double* p = a.params + (size_t)t*a.stride;
         double d[3];
@@ -93,14 +91,11 @@ __global__ void k_bond2(BondArgs a, float4* out, double* acc) {
             add_force(out, j, -s*d[0], -s*d[1], -s*d[2]);
         }
     }
-    if (ENERGY) block_accumulate(e, w, acc);
 }
 
 template <bool FORCE, bool ENERGY>
-__global__ void k_angle(BondArgs a, float4* out, double* acc) {
-    const int t = blockIdx.x*blockDim.x + threadIdx.x;
-    double e = 0;
-    if (t < a.nterms) {
+__device__ __forceinline__ void term_angle(const BondArgs& a, int t, float4* out, double& e) {
+    {
         const int i = a.inv[a.atoms[3*t]], j = a.inv[a.atoms[3*t+1]], k = a.inv[a.atoms[3*t+2]];
         const double* p = a.params + (size_t)t*a.stride;
         double u[3], v[3];
@@ -138,7 +133,6 @@ __global__ void k_angle(BondArgs a, float4* out, double* acc) {
             add_force(out, j, -(fi[0]+fk[0]), -(fi[1]+fk[1]), -(fi[2]+fk[2]));
         }
     }
-    if (ENERGY) block_accumulate(e, 0.0, acc);
 }
 
 __device__ __forceinline__ void cross3(const double (&a)[3], const double (&b)[3], double (&c)[3]) {
@@ -148,10 +142,8 @@ __device__ __forceinline__ void cross3(const double (&a)[3], const double (&b)[3
 }
 
 template <bool FORCE, bool ENERGY>
-__global__ void k_torsion(BondArgs a, float4* out, double* acc) {
-    const int t = blockIdx.x*blockDim.x + threadIdx.x;
-    double e = 0;
-    if (t < a.nterms) {
+__device__ __forceinline__ void term_torsion(const BondArgs& a, int t, float4* out, double& e) {
+    {
         const int a1 = a.inv[a.atoms[4*t]], a2 = a.inv[a.atoms[4*t+1]], a3 = a.inv[a.atoms[4*t+2]],
                   a4 = a.inv[a.atoms[4*t+3]];
         const double* p = a.params + (size_t)t*a.stride;
@@ -187,17 +179,83 @@ __global__ void k_torsion(BondArgs a, float4* out, double* acc) {
             add_force(out, a4, f4[0], f4[1], f4[2]);
         }
     }
-    if (ENERGY) block_accumulate(e, 0.0, acc);
+}
+
+template <bool FORCE, bool ENERGY>
+__global__ void k_bonded(BondArgs a, int arity, float4* out, double* acc) {
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    double e = 0, w = 0;
+    if (t < a.nterms) {
+        if (arity == 2) term_bond2<FORCE, ENERGY>(a, t, out, e, w);
+        else if (arity == 3) term_angle<FORCE, ENERGY>(a, t, out, e);
+        else term_torsion<FORCE, ENERGY>(a, t, out, e);
+    }
+    if (ENERGY) block_accumulate(e, w, acc);
+}
+
+// all explicit-list forces of one force group in a single launch (force path only)
+#define B2_MAX_BATCH 8
+struct BondBatch {
+    int count;
+    int first[B2_MAX_BATCH + 1];     // prefix sums of term counts
+    int arity[B2_MAX_BATCH];
+    BondArgs a[B2_MAX_BATCH];
+};
+
+__global__ void k_bonded_batch(BondBatch b, float4* out) {
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= b.first[b.count]) return;
+    int k = 0;
+    while (t >= b.first[k+1]) k++;
+    double e = 0, w = 0;
+    const int local = t - b.first[k];
+    if (b.arity[k] == 2) term_bond2<true, false>(b.a[k], local, out, e, w);
+    else if (b.arity[k] == 3) term_angle<true, false>(b.a[k], local, out, e);
+    else term_torsion<true, false>(b.a[k], local, out, e);
 }
 
 template <bool FORCE, bool ENERGY>
 static int launch(b2_context* ctx, const BondedForce& bf, const BondArgs& a, float4* out, double* acc) {
     const int T = 128, blocks = (bf.nterms + T - 1)/T;
-    if (bf.arity == 2) k_bond2<FORCE, ENERGY><<<blocks, T, 0, ctx->stream>>>(a, out, acc);
-    else if (bf.arity == 3) k_angle<FORCE, ENERGY><<<blocks, T, 0, ctx->stream>>>(a, out, acc);
-    else k_torsion<FORCE, ENERGY><<<blocks, T, 0, ctx->stream>>>(a, out, acc);
+    k_bonded<FORCE, ENERGY><<<blocks, T, 0, ctx->stream>>>(a, bf.arity, out, acc);
     B2_LAUNCH_CHECK();
     return B2_OK;
+}
+
+static BondArgs make_args(b2_context* ctx, const BondedForce& bf) {
+    BondArgs a;
+    a.nterms = bf.nterms; a.stride = bf.stride; a.periodic = bf.periodic && ctx->periodic; a.family = bf.family;
+    a.atoms = bf.atoms; a.params = bf.params; a.inv = ctx->inv; a.x = ctx->x;
+    for (int k = 0; k < 3; k++) a.box[k] = ctx->box[k];
+    for (int k = 0; k < 8; k++) a.g[k] = bf.gparams[k];
+    a.code_e = bf.code_e; a.ncode_e = bf.ncode_e; a.code_de = bf.code_de; a.ncode_de = bf.ncode_de;
+    a.consts = bf.consts;
+    return a;
+}
+
+// forces of every explicit-list force whose group is in `mask`, accumulated into `out`
+int bonded_eval_forces(b2_context* ctx, uint32_t mask, float4* out) {
+    BondBatch b;
+    b.count = 0;
+    b.first[0] = 0;
+    auto flush = [&]() -> int {
+        if (b.count == 0) return B2_OK;
+        const int T = 128, total = b.first[b.count];
+        k_bonded_batch<<<(total + T - 1)/T, T, 0, ctx->stream>>>(b, out);
+        B2_LAUNCH_CHECK();
+        b.count = 0;
+        return B2_OK;
+    };
+    for (const BondedForce& bf : ctx->bonded_forces) {
+        if (!(mask & (1u << bf.group)) || bf.nterms == 0) continue;
+        if ((bf.family == B2_BOND_CUSTOM || bf.family == B2_ANGLE_CUSTOM) && bf.ncode_de == 0) continue;
+        if (b.count == B2_MAX_BATCH) B2_TRY(flush());
+        b.a[b.count] = make_args(ctx, bf);
+        b.arity[b.count] = bf.arity;
+        b.first[b.count + 1] = b.first[b.count] + bf.nterms;
+        b.count++;
+    }
+    return flush();
 }
 
 // accumulates forces into `out` (atomics) and, if want_energy, e / virial into d_energy+72..73

@@ -127,6 +127,7 @@ struct b2_context {
     // ---- integrator program ----------------------------------------------------------------
     std::vector<b2_op> ops;
     int *code = nullptr; int ncode = 0;
+    std::vector<int> h_code;                      // host copy (kick term tables live in the code pool)
     double *consts = nullptr; int nconsts = 0;
     double *globals = nullptr; int nglobals = 0;
     double* sum_partial = nullptr;
@@ -178,6 +179,7 @@ int pair_eval_energy(b2_context* ctx, const PairForce& pf, int group);
 int pair_count_set(b2_context* ctx, const PairForce& pf, long long* count, unsigned long long* checksum,
                    int* pairs_dev, long long capacity);
 int bonded_eval(b2_context* ctx, const BondedForce& bf, float4* out, bool want_force, bool want_energy);
+int bonded_eval_forces(b2_context* ctx, uint32_t mask, float4* out);
 int forces_ensure(b2_context* ctx, uint32_t mask, int slot);
 int program_run(b2_context* ctx, int nsteps);
 int program_release(b2_context* ctx);

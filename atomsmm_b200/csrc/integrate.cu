@@ -90,29 +90,56 @@ __global__ void k_sum_final(int nblocks, const double* __restrict__ partial, dou
     if (threadIdx.x == 0) globals[target] = sh[0];
 }
 
-__global__ void k_global(const int* __restrict__ code, int len, const double* __restrict__ consts, double* globals,
-                         unsigned long long* rng_state, const double* energies) {
+// scalar program: one warp stages bytecode + constants in shared memory, lane 0 interprets
+#define B2_GLOBAL_SMEM_INTS 2048
+#define B2_GLOBAL_SMEM_CONSTS 256
+__global__ void k_global(const int* __restrict__ code, int len, const double* __restrict__ consts, int nconsts,
+                         double* globals, unsigned long long* rng_state, const double* energies) {
+    __shared__ int scode[B2_GLOBAL_SMEM_INTS];
+    __shared__ double sconsts[B2_GLOBAL_SMEM_CONSTS];
+    const bool staged = 2*len <= B2_GLOBAL_SMEM_INTS && nconsts <= B2_GLOBAL_SMEM_CONSTS;
+    if (staged) {
+        for (int k = threadIdx.x; k < 2*len; k += blockDim.x) scode[k] = code[k];
+        for (int k = threadIdx.x; k < nconsts; k += blockDim.x) sconsts[k] = consts[k];
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     RngStream rng;
     rng.seed = rng_state[0] ^ 0x5851f42d4c957f2dull;
     rng.c0 = 0xffffffffu; rng.c1 = (uint32_t)rng_state[1]; rng.c2 = (uint32_t)(rng_state[1] >> 32); rng.draw = 0;
-    vm_run<1>(code, len, consts, globals, nullptr, 0, nullptr, &rng, energies);
+    vm_run<1>(staged ? scode : code, len, staged ? sconsts : consts, globals, nullptr, 0, nullptr, &rng, energies);
     rng_state[1] += 1ull;
 }
 
-// v += c (s0 f_a + s1 f_b)/m
-__global__ void k_kick(int n, double* __restrict__ v, const float4* __restrict__ fa, const float4* __restrict__ fb,
-                       const float* __restrict__ invm, const double* __restrict__ globals, int gcoef, double s0,
-                       double s1) {
+struct KickArgs {
+    int nterms;
+    const float4* f[B2_MAX_KICK_TERMS];
+    int coef[B2_MAX_KICK_TERMS];
+    float sign[B2_MAX_KICK_TERMS];
+    int drift;                       // global index of the drift coefficient, -1: none
+};
+
+// v += sum_k s_k c_k f_k / m  [ ; x += c_d v ]      one thread per atom
+__global__ void k_kick(int n, double* __restrict__ v, double* __restrict__ x, KickArgs a,
+                       const float* __restrict__ invm, const double* __restrict__ globals) {
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double c = globals[gcoef]*(double)invm[i];
-    float4 f = fa[i];
-    double fx = s0*f.x, fy = s0*f.y, fz = s0*f.z;
-    if (fb) {
-        f = fb[i];
-        fx += s1*f.x; fy += s1*f.y; fz += s1*f.z;
+    const double im = (double)invm[i];
+    if (im == 0.0) return;
+    double ax = 0, ay = 0, az = 0;
+#pragma unroll
+    for (int k = 0; k < B2_MAX_KICK_TERMS; k++) {
+        if (k >= a.nterms) break;
+        const double c = globals[a.coef[k]]*(double)a.sign[k];
+        const float4 f = a.f[k][i];
+        ax += c*f.x; ay += c*f.y; az += c*f.z;
     }
-    v[3*i] += c*fx; v[3*i+1] += c*fy; v[3*i+2] += c*fz;
+    double vx = v[3*i] + im*ax, vy = v[3*i+1] + im*ay, vz = v[3*i+2] + im*az;
+    v[3*i] = vx; v[3*i+1] = vy; v[3*i+2] = vz;
+    if (a.drift >= 0) {
+        const double c = globals[a.drift];
+        x[3*i] += c*vx; x[3*i+1] += c*vy; x[3*i+2] += c*vz;
+    }
 }
 
 __global__ void k_drift(int ndof, double* __restrict__ x, const double* __restrict__ v,
@@ -151,11 +178,7 @@ int forces_ensure(b2_context* ctx, uint32_t mask, int slot) {
         written = true;
     }
     if (!written) B2_CUDA(cudaMemsetAsync(ctx->fbuf[slot], 0, sizeof(float4)*ctx->n, ctx->stream));
-    for (const BondedForce& bf : ctx->bonded_forces) {
-        if (!(mask & (1u << bf.group))) continue;
-        if (bf.family == B2_BOND_CUSTOM && bf.ncode_de == 0) continue;   // energy-only description
-        B2_TRY(bonded_eval(ctx, bf, ctx->fbuf[slot], true, false));
-    }
+    B2_TRY(bonded_eval_forces(ctx, mask, ctx->fbuf[slot]));
     ctx->fvalid[slot] = ctx->pos_version;
     return B2_OK;
 }
@@ -196,15 +219,28 @@ static int run_one_step(b2_context* ctx) {
             break;
         }
         case B2_OP_GLOBAL:
-            k_global<<<1, 1, 0, s>>>(ctx->code + op.b, op.c, ctx->consts, ctx->globals, ctx->rng_state,
-                                      ctx->d_energy);
+            k_global<<<1, 64, 0, s>>>(ctx->code + op.b, op.c, ctx->consts, ctx->nconsts, ctx->globals,
+                                       ctx->rng_state, ctx->d_energy);
             B2_LAUNCH_CHECK();
             break;
         case B2_OP_KICK: {
-            const double s0 = (op.d & 1) ? -1.0 : 1.0, s1 = (op.d & 2) ? -1.0 : 1.0;
-            const float4* fb = (op.d & 4) ? ctx->fbuf[op.c] : nullptr;
-            k_kick<<<(n + T - 1)/T, T, 0, s>>>(n, ctx->v, ctx->fbuf[op.b], fb, ctx->invm, ctx->globals, op.a, s0, s1);
+            KickArgs ka;
+            ka.nterms = op.a;
+            ka.drift = op.c;
+            if (op.a < 1 || op.a > B2_MAX_KICK_TERMS || op.b < 0 || op.b + 3*op.a > (int)ctx->h_code.size())
+                return b2_fail(ctx, B2_ERR_ARG, "malformed kick op");
+            for (int k = 0; k < B2_MAX_KICK_TERMS; k++) {
+                const bool live = k < op.a;
+                const int slot = live ? ctx->h_code[op.b + 3*k] : 0;
+                if (live && (slot < 0 || slot >= B2_FSLOTS || ctx->fbuf[slot] == nullptr))
+                    return b2_fail(ctx, B2_ERR_STATE, "kick uses force slot %d before it was evaluated", slot);
+                ka.f[k] = live ? ctx->fbuf[slot] : nullptr;
+                ka.coef[k] = live ? ctx->h_code[op.b + 3*k + 1] : 0;
+                ka.sign[k] = live ? (float)ctx->h_code[op.b + 3*k + 2] : 0.f;
+            }
+            k_kick<<<(n + T - 1)/T, T, 0, s>>>(n, ctx->v, ctx->x, ka, ctx->invm, ctx->globals);
             B2_LAUNCH_CHECK();
+            if (op.c >= 0) ctx->pos_version++;
             break;
         }
         case B2_OP_DRIFT:

@@ -194,6 +194,13 @@ __global__ void __launch_bounds__(128) k_build_lists(int n, int ngroups, const f
         for (int k = 0; k < B2_GROUP; k++)
             if (soi[wib][k] >= 0) { lo[d] = fminf(lo[d], sxi[wib][k][d]); hi[d] = fmaxf(hi[d], sxi[wib][k][d]); }
     }
+    unsigned padmask = 0;
+    int omin = 0x7fffffff, omax = -1;
+    for (int k = 0; k < B2_GROUP; k++) {
+        const int oi = soi[wib][k];
+        if (oi < 0) padmask |= 1u << k;
+        else { omin = min(omin, oi); omax = max(omax, oi); }
+    }
     const float rmax = (float)g.rmax + NL_MARGIN;
     const float cs[3] = {(float)(g.box[0]/g.nc[0]), (float)(g.box[1]/g.nc[1]), (float)(g.box[2]/g.nc[2])};
     const float box[3] = {bx, by, bz};
@@ -261,21 +268,28 @@ __global__ void __launch_bounds__(128) k_build_lists(int n, int ngroups, const f
                         j = __float_as_int(pj.w);
                         const float xj = pj.x + sx, yj = pj.y + sy, zj = pj.z + sz;
                         const int oj = corig[idx];
+                        // distance to the nearest of the 8 i-atoms (padding slots duplicate a real atom)
 #pragma unroll
                         for (int k = 0; k < B2_GROUP; k++) {
-                            const int oi = soi[wib][k];
-                            if (oi < 0) { m |= 1u << k; continue; }
                             float dx = xj - sxi[wib][k][0], dy = yj - sxi[wib][k][1], dz = zj - sxi[wib][k][2];
                             if (all[0]) dx -= bx*rintf(dx*ibx);
                             if (all[1]) dy -= by*rintf(dy*iby);
                             if (all[2]) dz -= bz*rintf(dz*ibz);
-                            const float d2 = dx*dx + dy*dy + dz*dz;
-                            const int dd = oj - oi;
-                            bool ex = oi == oj;
-                            if (dd >= -32 && dd < 32) ex = ex || ((smask[wib][k] >> (dd + 32)) & 1ull);
-                            else if (excl_ptr) ex = is_excluded(oi, oj, 0ull, excl_ptr, excl_idx);
-                            if (ex) m |= 1u << k;
-                            else d2min = fminf(d2min, d2);
+                            d2min = fminf(d2min, dx*dx + dy*dy + dz*dz);
+                        }
+                        // exclusion mask: only candidates whose caller index is close to the group's
+                        // own index range (same molecule) can be excluded or be the atom itself
+                        m = padmask;
+                        if (excl_ptr != nullptr || (oj >= omin - 32 && oj <= omax + 32)) {
+                            for (int k = 0; k < B2_GROUP; k++) {
+                                const int oi = soi[wib][k];
+                                if (oi < 0) continue;
+                                const int dd = oj - oi;
+                                bool ex = dd == 0;
+                                if (dd >= -32 && dd < 32) ex = ex || ((smask[wib][k] >> (dd + 32)) & 1ull);
+                                else if (excl_ptr) ex = is_excluded(oi, oj, 0ull, excl_ptr, excl_idx);
+                                if (ex) m |= 1u << k;
+                            }
                         }
                     }
 #pragma unroll
@@ -298,7 +312,7 @@ __global__ void __launch_bounds__(128) k_build_lists(int n, int ngroups, const f
         for (int k = 0; k < a.nlists; k++) {
             a.counts[k][warp] = min(count[k], a.cap[k]);
             if (count[k] > a.cap[k]) flags[1] = 1;
-            atomicMax(&flags[3], count[k]);
+            if (count[k] > flags[3]) atomicMax(&flags[3], count[k]);
         }
     }
 }

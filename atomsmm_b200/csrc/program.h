@@ -18,8 +18,9 @@ enum {
     B2_OP_GLOBAL = 3,
     // make force slot b valid for the current positions.   a: force-group mask
     B2_OP_EVAL = 4,
-    // v += g[a] * (s0*f[b] + s1*f[c]) / m    fast kick.  d: packed signs (bit0 s0<0, bit1 s1<0,
-    //   bit2: second term present)
+    // v += sum_k sign_k g[coef_k] f[slot_k] / m, optionally followed by x += g[c] v   (fused
+    // kick[+drift]).  a: number of terms (<= B2_MAX_KICK_TERMS), b: offset in the code pool of the
+    // term table {slot, coef, sign} x a, c: global index of the drift coefficient or -1
     B2_OP_KICK = 5,
     // x += g[a] * v                          fast drift
     B2_OP_DRIFT = 6,
@@ -44,5 +45,6 @@ enum {
     VM_JMPZ = 33, VM_CMP = 34, VM_PUSHE = 35,
 };
 
+#define B2_MAX_KICK_TERMS 6
 #define B2_MAX_PERDOF 14
 #define B2_VM_STACK 24

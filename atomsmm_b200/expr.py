@@ -415,6 +415,44 @@ def _call(name, *args):
     return ('call', name, tuple(args))
 
 
+def simplify(node):
+    """Constant folding and x*1, x+0, x/1 identities (keeps coefficient expressions minimal)."""
+    kind = node[0]
+    if kind in ('num', 'var'):
+        return node
+    if kind == 'call':
+        args = tuple(simplify(a) for a in node[2])
+        if all(a[0] == 'num' for a in args) and node[1] in _FUNCS and node[1] != 'deriv':
+            try:
+                return ('num', float(_FUNCS[node[1]](*[a[1] for a in args])))
+            except (ValueError, OverflowError, ZeroDivisionError):
+                pass
+        return ('call', node[1], args)
+    parts = [simplify(a) for a in node[1:]]
+    if kind == 'add':
+        return _add(*parts)
+    if kind == 'sub':
+        return _sub(*parts)
+    if kind == 'mul':
+        return _mul(*parts)
+    if kind == 'div':
+        a, b = parts
+        if a[0] == 'num' and b[0] == 'num' and b[1] != 0:
+            return ('num', a[1]/b[1])
+        return _div(a, b)
+    if kind == 'neg':
+        return _neg(parts[0])
+    if kind == 'pow':
+        a, b = parts
+        if a[0] == 'num' and b[0] == 'num':
+            try:
+                return ('num', float(a[1]**b[1]))
+            except (ValueError, OverflowError, ZeroDivisionError):
+                pass
+        return _pow(a, b)
+    return (kind,) + tuple(parts)
+
+
 def diff(node, x):
     """d(node)/d(x) for an inlined AST; ``x`` is a variable name."""
     kind = node[0]

@@ -450,6 +450,7 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
 
     def coefficient(ast):
         """Global slot holding the value of a per-DOF-free AST at the time of use."""
+        ast = X.simplify(ast)
         if ast[0] == 'var' and ast[1] in P.global_names:
             return P.gindex(ast[1]), None
         key = X.to_string(ast)
@@ -487,12 +488,10 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
         if kind == 'kick':
             (fa, sa), second = extra
             ensure_forces(ast)
-            flags = (1 if sa < 0 else 0)
-            fb = 0
+            terms = [(fa, slot, 1 if sa > 0 else -1)]
             if second is not None:
-                fb, sb = second
-                flags |= 4 | (2 if sb < 0 else 0)
-            P.op(OP_KICK, slot, fa, fb, flags)
+                terms.append((second[0], slot, 1 if second[1] > 0 else -1))
+            P.ops.append(['KICK', terms, -1])
         elif kind == 'drift':
             P.op(OP_DRIFT, slot)
         else:
@@ -585,7 +584,54 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
             X.compile_ast(ast, resolve_global, P.bc)
             P.bc.emit('STOREG', slot)
         P.ops.insert(0, [OP_GLOBAL, 0, start, (len(P.bc.code) - start)//2, 0, 0, 0, 0])
+    _fuse_kicks(P)
     return P
+
+
+MAX_KICK_TERMS = 6
+
+
+def _fuse_kicks(P):
+    """Peephole over the op list: consecutive kicks (possibly separated by force evaluations, which
+    do not touch velocities) become one multi-term kick, and a drift that directly follows is folded
+    into the same kernel.  Term tables {slot, coefficient, sign} go into the code pool."""
+    out = []
+    pending = None
+
+    def flush():
+        nonlocal pending
+        if pending is not None:
+            terms, drift = pending
+            offset = len(P.bc.code)
+            for slot, coef, sign in terms:
+                P.bc.code += [slot, coef, sign]
+            if len(P.bc.code) % 2:
+                P.bc.code.append(0)
+            out.append([OP_KICK, len(terms), offset, drift, 0, 0, 0, 0])
+            pending = None
+
+    for op in P.ops:
+        if op[0] == 'KICK':
+            if pending is not None and (pending[1] >= 0 or len(pending[0]) + len(op[1]) > MAX_KICK_TERMS):
+                flush()
+            if pending is None:
+                pending = [list(op[1]), -1]
+            else:
+                pending[0].extend(op[1])
+        elif op[0] == OP_EVAL:
+            # evaluating forces neither reads nor writes v; but a drift already folded into the
+            # pending kick changes x, so the evaluation must stay behind it
+            if pending is not None and pending[1] >= 0:
+                flush()
+            out.append(op)
+        elif op[0] == OP_DRIFT and pending is not None and pending[1] < 0:
+            pending[1] = op[1]
+            flush()
+        else:
+            flush()
+            out.append(op)
+    flush()
+    P.ops = out
 
 
 def _strip_dead_constant_stores(body):
