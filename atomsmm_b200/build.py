@@ -60,7 +60,7 @@ def build(force=False, verbose=False):
         objects = list(pool.map(lambda s: _compile(s, verbose), sources()))
     if _stale(LIBRARY, objects):
         cmd = [NVCC, '-shared', '-o', LIBRARY] + objects + ['-gencode', 'arch=compute_100a,code=sm_100a',
-                                                            '-Xcompiler', '-fPIC', '-lcudart']
+                                                            '-Xcompiler', '-fPIC', '-lcudart', '-lcufft']
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError('link failed:\n%s\n%s' % (proc.stdout, proc.stderr))

@@ -11,6 +11,7 @@
 
 #include "ctx.h"
 
+#define PME_MIN_GRID 5
 static thread_local std::string g_last_error;
 
 int b2_fail(b2_context* ctx, int code, const char* fmt, ...) {
@@ -135,6 +136,7 @@ extern "C" int b2_destroy(b2_context* ctx) {
     cudaFree(ctx->globals); cudaFree(ctx->sum_partial); cudaFree(ctx->rng_state);
     cudaFree(ctx->band_pairs); cudaFree(ctx->band_count);
     for (BondedForce& bf : ctx->bonded_forces) free_bonded(bf);
+    for (PmeForce& pm : ctx->pme_forces) pme_release(pm);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return B2_OK;
@@ -353,6 +355,23 @@ extern "C" int b2_add_custom_bonded_force(b2_context* ctx, int family, int group
     return B2_OK;
 }
 
+extern "C" int b2_add_pme(b2_context* ctx, int group, int param_set, double alpha, int nx, int ny, int nz, double kc,
+                          double self_energy, int* handle) {
+    if (!ctx || ctx->n == 0) return b2_fail(ctx, B2_ERR_STATE, "set particles first");
+    if (param_set < 0 || param_set >= (int)ctx->h_sets.size()) return b2_fail(ctx, B2_ERR_ARG, "unknown parameter set");
+    if (nx < PME_MIN_GRID || ny < PME_MIN_GRID || nz < PME_MIN_GRID || !(alpha > 0))
+        return b2_fail(ctx, B2_ERR_ARG, "bad PME parameters");
+    if (!ctx->periodic) return b2_fail(ctx, B2_ERR_UNSUPPORTED, "PME needs a periodic box");
+    PmeForce pf;
+    pf.group = group; pf.set = param_set; pf.alpha = alpha; pf.kc = kc; pf.eself = self_energy;
+    pf.K[0] = nx; pf.K[1] = ny; pf.K[2] = nz;
+    B2_TRY(pme_setup(ctx, pf));
+    ctx->pme_forces.push_back(pf);
+    program_release(ctx);
+    if (handle) *handle = (int)ctx->pme_forces.size() - 1;
+    return B2_OK;
+}
+
 extern "C" int b2_set_skin(b2_context* ctx, double skin) {
     if (!ctx || !(skin >= 0)) return B2_ERR_ARG;
     ctx->skin = skin;
@@ -549,6 +568,13 @@ extern "C" int b2_eval(b2_context* ctx, uint32_t group_mask, int flags, double* 
             if (!(group_mask & (1u << bf.group)) || bf.nterms == 0) continue;
             B2_TRY(bonded_eval(ctx, bf, nullptr, false, true));
             k_fold_energy<<<1, 1, 0, ctx->stream>>>(ctx->d_energy, bf.group, 0.0, 0);
+            B2_LAUNCH_CHECK();
+        }
+        for (PmeForce& pm : ctx->pme_forces) {
+            if (!(group_mask & (1u << pm.group))) continue;
+            B2_CUDA(cudaMemsetAsync(ctx->d_energy + 72, 0, 4*sizeof(double), ctx->stream));
+            B2_TRY(pme_eval(ctx, pm, nullptr, ctx->d_energy + 72));
+            k_fold_energy<<<1, 1, 0, ctx->stream>>>(ctx->d_energy, pm.group, pm.eself, 0);
             B2_LAUNCH_CHECK();
         }
         double h[66];

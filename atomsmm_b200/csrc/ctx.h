@@ -53,6 +53,16 @@ struct BondedForce {
     double* consts = nullptr;
 };
 
+struct PmeForce {
+    int group = 0, set = 0;
+    int K[3] = {0, 0, 0};
+    double alpha = 0, kc = 0, eself = 0;
+    double* grid = nullptr;       // real-space charge / potential grid [nx][ny][nz]
+    void* spectrum = nullptr;     // cufftDoubleComplex [nx][ny][nz/2+1]
+    double* eterm = nullptr;      // influence function on the half spectrum
+    int plan_fwd = -1, plan_inv = -1;
+};
+
 struct NList {
     double cutoff = 0;            // interaction cutoff
     int cap = 0;                  // entries per group
@@ -79,6 +89,7 @@ struct b2_context {
     std::vector<int> h_excl;                      // pairs
     std::vector<PairForce> pair_forces;
     std::vector<BondedForce> bonded_forces;
+    std::vector<PmeForce> pme_forces;
     bool excl_far = false;                        // some exclusion spans > 31 in index
 
     // ---- device state ----------------------------------------------------------------------
@@ -180,6 +191,9 @@ int pair_count_set(b2_context* ctx, const PairForce& pf, long long* count, unsig
                    int* pairs_dev, long long capacity);
 int bonded_eval(b2_context* ctx, const BondedForce& bf, float4* out, bool want_force, bool want_energy);
 int bonded_eval_forces(b2_context* ctx, uint32_t mask, float4* out);
+int pme_setup(b2_context* ctx, PmeForce& pf);
+int pme_eval(b2_context* ctx, PmeForce& pf, float4* out, double* acc);
+void pme_release(PmeForce& pf);
 int forces_ensure(b2_context* ctx, uint32_t mask, int slot);
 int program_run(b2_context* ctx, int nsteps);
 int program_release(b2_context* ctx);

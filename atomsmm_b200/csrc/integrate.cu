@@ -179,6 +179,8 @@ int forces_ensure(b2_context* ctx, uint32_t mask, int slot) {
     }
     if (!written) B2_CUDA(cudaMemsetAsync(ctx->fbuf[slot], 0, sizeof(float4)*ctx->n, ctx->stream));
     B2_TRY(bonded_eval_forces(ctx, mask, ctx->fbuf[slot]));
+    for (PmeForce& pm : ctx->pme_forces)
+        if (mask & (1u << pm.group)) B2_TRY(pme_eval(ctx, pm, ctx->fbuf[slot], nullptr));
     ctx->fvalid[slot] = ctx->pos_version;
     return B2_OK;
 }

@@ -44,6 +44,8 @@ _SIGNATURES = {
     'b2_add_custom_bonded_force': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p, c_double_p,
                                    ctypes.c_int, ctypes.c_int, c_int_p, ctypes.c_int, c_int_p, ctypes.c_int,
                                    c_double_p, ctypes.c_int, c_int_p],
+    'b2_add_pme': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                   ctypes.c_double, ctypes.c_double, c_int_p],
     'b2_set_skin': [c_void, ctypes.c_double],
     'b2_set_positions': [c_void, c_void],
     'b2_set_velocities': [c_void, c_void],
@@ -411,16 +413,29 @@ class Context(object):
             crf = 3*es/((2*es + 1)*cutoff)
             params = [kc, 2.0, krf, crf, 0.0, float(use_switch), rswitch, cutoff]
         else:
+            if method != NB.PME:
+                raise lowering.UnsupportedDescription('only PME is implemented for reciprocal space (not Ewald / LJPME)')
             a, nx, ny, nz = force._pme
             tol = force.getEwaldErrorTolerance()
-            alpha = a if a != 0.0 else math.sqrt(-math.log(2*tol))/cutoff
+            if a != 0.0:
+                alpha, grid = a, [nx, ny, nz]
+            else:
+                # OpenMM's rule; no rounding to FFT-friendly sizes, like the Reference platform
+                alpha = math.sqrt(-math.log(2*tol))/cutoff
+                grid = [max(6, int(math.ceil(2*alpha*L/(3*tol**0.2)))) for L in self._box]
             params = [kc, 3.0, 0.0, 0.0, alpha, float(use_switch), rswitch, cutoff]
-            self._reciprocal_missing = True
             rgroup = force.getReciprocalSpaceForceGroup()
-            self._reciprocal_group = group if rgroup < 0 else rgroup
+            self._pme_request = (group if rgroup < 0 else rgroup, alpha, grid)
         pairs = frozenset((min(e[0], e[1]), max(e[0], e[1])) for e in force._exceptions)
         exclusions = self._merge_exclusions(exclusions, pairs)
         set_id = self._param_set(table[:, 0], table[:, 1], table[:, 2])
+        if alpha > 0:
+            rgroup, _, grid = self._pme_request
+            self._all_groups |= 1 << rgroup
+            handle = ctypes.c_int()
+            self_energy = -kc*alpha/math.sqrt(math.pi)*float(np.sum(table[:, 0]**2))
+            self._call('b2_add_pme', rgroup, set_id, alpha, grid[0], grid[1], grid[2], kc, self_energy,
+                       ctypes.byref(handle))
         econst = 0.0
         if force.getUseDispersionCorrection():
             classes, counts = self._classes(table[:, 1], table[:, 2])
@@ -617,9 +632,6 @@ class Context(object):
         need_state = getPositions or getForces or getEnergy or getVelocities
         if need_state and not self._have_positions:
             raise mm.OpenMMException('Particle positions have not been set')
-        if (getEnergy or getForces) and getattr(self, '_reciprocal_missing', False) and \
-                mask & (1 << self._reciprocal_group):
-            raise lowering.UnsupportedDescription('PME/Ewald reciprocal space is not implemented yet on this engine')
         fields = dict(_positions=None, _velocities=None, _forces=None, _potential=None, _kinetic=None,
                       _box=self._box.copy(), _parameters=self._parameters if getParameters else {},
                       _derivatives={}, _time=self._time)

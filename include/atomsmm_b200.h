@@ -127,6 +127,11 @@ B2_API int b2_add_custom_bonded_force(b2_context* ctx, int family, int group, in
                                const double* params, int stride, int periodic,
                                const int* code_e, int ncode_e, const int* code_de, int ncode_de,
                                const double* consts, int nconsts, int* handle);
+/* Reciprocal space of openmm.NonbondedForce with nonbondedMethod = PME (forces.py:185-187,
+ * systems.py:74-75): smooth PME, order-5 B-splines, grid nx x ny x nz, Ewald parameter alpha.
+ * self_energy = -Kc alpha/sqrt(pi) sum q^2 is added to the group energy. */
+B2_API int b2_add_pme(b2_context* ctx, int group, int param_set, double alpha, int nx, int ny, int nz, double kc,
+                      double self_energy, int* handle);
 /* neighbour-list skin (nm); lists are rebuilt when an atom moved more than skin/2 */
 B2_API int b2_set_skin(b2_context* ctx, double skin);
 

@@ -1,0 +1,170 @@
+"""
+GPU parity tests that need PME reciprocal space: the reference's PressureComputer goldens
+(tests/test_computers.py), the RESPASystem per-force dictionary (tests/test_systems.py:131-152)
+and the Far + Near == PME identity (tests/test_respa_forces.py:41-79), all through the public API.
+"""
+
+import numpy as np
+import pytest
+
+import atomsmm_b200 as atomsmm
+from atomsmm_b200 import app, mm, unit
+
+import systems
+from systems import positions_of
+
+pytestmark = pytest.mark.gpu
+A = unit.angstroms
+
+
+def value(q):
+    return q/q.unit
+
+
+def read_system(case):
+    # reference: tests/test_computers.py:11-19
+    return systems.flexible(case, app.PME)
+
+
+@pytest.mark.parametrize('case,goldens', [
+    ('q-SPC-FW', (-11661.677650154408, -58.64837784125407, -5418.629781093525, -554.9525554206972)),
+    ('emim_BCN4_Jiung2014', (-22827.477810819175, -282.7243180164338, -23272.958585794207, -3283.563262288828))])
+def test_pressure_with_bath_temperature(cuda_platform, case, goldens):
+    # reference: tests/test_computers.py:22-37 and 59-74
+    system, pdb = read_system(case)
+    computer = atomsmm.PressureComputer(system, pdb.topology, cuda_platform, temperature=300*unit.kelvin)
+    context = mm.Context(system, mm.CustomIntegrator(0), cuda_platform)
+    context.setPositions(pdb.positions)
+    state = context.getState(getPositions=True, getVelocities=True, getForces=True)
+    computer.import_configuration(state)
+    assert value(computer.get_atomic_virial()) == pytest.approx(goldens[0])
+    # small difference of large terms: 3e-6 instead of 1e-6
+    assert value(computer.get_atomic_pressure()) == pytest.approx(goldens[1], rel=3e-6)
+    # the molecular virial contracts the fp32 forces of the simulated system with positions
+    assert value(computer.get_molecular_virial(state.getForces())) == pytest.approx(goldens[2], rel=2e-6)
+    assert value(computer.get_molecular_pressure(state.getForces())) == pytest.approx(goldens[3], rel=2e-6)
+
+
+def test_pressure_with_kinetic_temperature(cuda_platform):
+    """tests/test_computers.py:40-56 with our own velocities (OpenMM's random stream is not
+    reproducible): the kinetic part is checked against its definition."""
+    system, pdb = read_system('q-SPC-FW')
+    computer = atomsmm.PressureComputer(system, pdb.topology, cuda_platform)
+    context = mm.Context(system, mm.CustomIntegrator(0), cuda_platform)
+    context.setPositions(pdb.positions)
+    context.setVelocitiesToTemperature(300*unit.kelvin, 1234)
+    state = context.getState(getPositions=True, getVelocities=True, getForces=True)
+    computer.import_configuration(state)
+    assert value(computer.get_atomic_virial()) == pytest.approx(-11661.677650154408)
+    v = state.getVelocities(asNumpy=True).value_in_unit(unit.nanometer/unit.picosecond)
+    mass = np.array([system.getParticleMass(i).value_in_md_units() for i in range(system.getNumParticles())])
+    mvv = float(np.sum(mass[:, None]*v*v))
+    volume = 2.5**3
+    to_atm = 1e3/6.02214179e23/1e-27/101325.0
+    expected = (mvv - 11661.677650154408)/(3*volume)*to_atm
+    assert value(computer.get_atomic_pressure()) == pytest.approx(expected, rel=1e-5)
+
+
+def test_pair_virial_mode(cuda_platform):
+    """pressure_mode='pair': W = sum r.F of every two-body term of the simulated system, equal to
+    the oracle's -sum r dE/dr; for a DampedSmoothedForce system the reference would report only
+    the bonded part."""
+    from oracle import refmath
+    system, pdb, force = systems.water_damped(2)
+    computer = atomsmm.PressureComputer(system, pdb.topology, cuda_platform, temperature=300*unit.kelvin,
+                                        pressure_mode='pair')
+    computer.setPositions(pdb.positions)
+    ref = refmath.evaluate_system(system, positions_of(pdb))
+    assert value(computer.get_atomic_virial()) == pytest.approx(ref.virial, rel=1e-6)
+
+
+def test_respa_system_with_special_bonds(cuda_platform):
+    # reference: tests/test_systems.py:131-152
+    system, pdb = systems.flexible('q-SPC-FW', app.PME)
+    nb = system.getForce(atomsmm.findNonbondedForce(system))
+    nb.setUseSwitchingFunction(True)
+    nb.setSwitchingDistance(9*A)
+    respa_system = atomsmm.RESPASystem(system, 7*A, 5*A)
+    respa_system.redefine_bond(pdb.topology, 'HOH', 'H[1-2]', 'O', 1.05*A)
+    respa_system.redefine_angle(pdb.topology, 'HOH', 'H[1-2]', 'O', 'H[1-2]', 113*unit.degrees)
+    components = atomsmm.splitPotentialEnergy(respa_system, pdb.topology, pdb.positions)
+    potential = dict()
+    potential['HarmonicBondForce'] = 3665.684696323676
+    potential['HarmonicAngleForce'] = 1811.197218501007
+    potential['PeriodicTorsionForce'] = 0.0
+    potential['Real-Space'] = 84694.39953220935
+    potential['Reciprocal-Space'] = -111582.71281220087
+    potential['CustomNonbondedForce'] = -25531.129587235544
+    potential['CustomNonbondedForce(1)'] = 25531.129587235544
+    potential['CustomBondForce'] = 0.0
+    potential['CustomBondForce(1)'] = -1175.253817235862
+    potential['CustomAngleForce'] = -305.0221912655623
+    potential['Total'] = -22891.707373668243
+    for term, val in components.items():
+        assert value(val) == pytest.approx(potential[term], rel=1e-6, abs=1e-9), term
+
+
+@pytest.mark.parametrize('adjustment', [None, 'shift', 'force-switch'])
+def test_far_plus_near_equals_pme(cuda_platform, adjustment):
+    # reference: tests/test_respa_forces.py:41-79
+    rswitch_inner, rcut_inner, rswitch, rcut = 6.5*A, 7.0*A, 9.5*A, 10*A
+    pdb, ff = systems.fixtures.load('q-SPC-FW')
+    system = ff.createSystem(pdb.topology, nonbondedMethod=app.PME)
+    nbforce = atomsmm.hijackForce(system, atomsmm.findNonbondedForce(system))
+    innerforce = atomsmm.NearNonbondedForce(rcut_inner, rswitch_inner, adjustment)
+    innerforce.importFrom(nbforce).addTo(system)
+    outerforce = atomsmm.FarNonbondedForce(innerforce, rcut, rswitch).setForceGroup(2)
+    outerforce.importFrom(nbforce).addTo(system)
+    potential = atomsmm.splitPotentialEnergy(system, pdb.topology, pdb.positions)['Total']
+    refsys = ff.createSystem(pdb.topology, nonbondedMethod=app.PME, nonbondedCutoff=rcut, removeCMMotion=True)
+    force = refsys.getForce(refsys.getNumForces() - 2)
+    force.setUseSwitchingFunction(True)
+    force.setSwitchingDistance(rswitch)
+    refpot = atomsmm.splitPotentialEnergy(refsys, pdb.topology, pdb.positions)['Total']
+    assert value(potential) == pytest.approx(value(refpot))
+
+
+def test_pme_forces_against_oracle(cuda_platform):
+    from oracle import refmath
+    system, pdb = systems.flexible('emim_BCN4_Jiung2014', app.PME)
+    nb = system.getForce(atomsmm.findNonbondedForce(system))
+    nb.setReciprocalSpaceForceGroup(5)
+    context = mm.Context(system, mm.VerletIntegrator(0.0), cuda_platform)
+    context.setPositions(pdb.positions)
+    pos = positions_of(pdb)
+    for groups in ({5}, {0}, None):
+        state = context.getState(getEnergy=True, getForces=True, groups=-1 if groups is None else groups)
+        ref = refmath.evaluate_system(system, pos, groups=groups)
+        assert value(state.getPotentialEnergy()) == pytest.approx(ref.energy, rel=1e-6)
+        f = state.getForces(asNumpy=True).value_in_unit(unit.kilojoules_per_mole/unit.nanometer)
+        assert np.sqrt(np.sum((f - ref.forces)**2)/np.sum(ref.forces**2)) < 1e-5
+
+
+def test_softcore_force_and_lambda_derivative(cuda_platform):
+    """SoftcoreForce (forces.py:761-793) on methane-in-water: energy/forces vs the oracle at
+    lambda_vdw = 0.6, and dE/dlambda_vdw against a central difference of the engine's own energies."""
+    from oracle import refmath
+    pdb, ff = systems.fixtures.load('methane-in-water')
+    system = ff.createSystem(pdb.topology, nonbondedMethod=app.CutoffPeriodic, rigidWater=False)
+    nb = atomsmm.hijackForce(system, atomsmm.findNonbondedForce(system))
+    force = atomsmm.SoftcoreForce(10*A, 9*A)
+    force.importFrom(nb)
+    force.addEnergyParameterDerivative('lambda_vdw')
+    system.addForce(force)
+    context = mm.Context(system, mm.VerletIntegrator(0.0), cuda_platform)
+    context.setPositions(pdb.positions)
+    context.setParameter('lambda_vdw', 0.6)
+    group = {force.getForceGroup()}
+    # the softcore force shares group 0 with the bonded terms: isolate it
+    state = context.getState(getEnergy=True, getForces=True, getParameterDerivatives=True)
+    ref = refmath.evaluate_system(system, positions_of(pdb), params={'lambda_vdw': 0.6})
+    assert value(state.getPotentialEnergy()) == pytest.approx(ref.energy, rel=1e-6)
+    f = state.getForces(asNumpy=True).value_in_unit(unit.kilojoules_per_mole/unit.nanometer)
+    assert np.sqrt(np.sum((f - ref.forces)**2)/np.sum(ref.forces**2)) < 1e-5
+    derivative = state.getEnergyParameterDerivatives()['lambda_vdw']
+    h = 1e-4
+    energies = []
+    for lam in (0.6 + h, 0.6 - h):
+        context.setParameter('lambda_vdw', lam)
+        energies.append(value(context.getState(getEnergy=True).getPotentialEnergy()))
+    assert derivative == pytest.approx((energies[0] - energies[1])/(2*h), rel=1e-5)
