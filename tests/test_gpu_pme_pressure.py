@@ -42,7 +42,8 @@ def test_pressure_with_bath_temperature(cuda_platform, case, goldens):
     assert value(computer.get_atomic_pressure()) == pytest.approx(goldens[1], rel=3e-6)
     # the molecular virial contracts the fp32 forces of the simulated system with positions
     assert value(computer.get_molecular_virial(state.getForces())) == pytest.approx(goldens[2], rel=2e-6)
-    assert value(computer.get_molecular_pressure(state.getForces())) == pytest.approx(goldens[3], rel=2e-6)
+    # P_mol = (3 N_mol kT + W_mol)/3V amplifies the relative error of W_mol ~3.4x (water)
+    assert value(computer.get_molecular_pressure(state.getForces())) == pytest.approx(goldens[3], rel=1e-5)
 
 
 def test_pressure_with_kinetic_temperature(cuda_platform):
@@ -149,6 +150,8 @@ def test_softcore_force_and_lambda_derivative(cuda_platform):
     nb = atomsmm.hijackForce(system, atomsmm.findNonbondedForce(system))
     force = atomsmm.SoftcoreForce(10*A, 9*A)
     force.importFrom(nb)
+    # the long-range correction of a potential with a bare Coulomb term diverges; switch it off
+    force.setUseLongRangeCorrection(False)
     force.addEnergyParameterDerivative('lambda_vdw')
     system.addForce(force)
     context = mm.Context(system, mm.VerletIntegrator(0.0), cuda_platform)
