@@ -123,6 +123,7 @@ extern "C" int b2_destroy(b2_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     program_release(ctx);
+    dist_release(ctx);
     cudaFree(ctx->x); cudaFree(ctx->v); cudaFree(ctx->xref); cudaFree(ctx->xsort); cudaFree(ctx->pos4);
     for (int s = 0; s < B2_MAX_SETS; s++) { cudaFree(ctx->par[s]); cudaFree(ctx->pard[s]); }
     cudaFree(ctx->massd); cudaFree(ctx->invm); cudaFree(ctx->orig); cudaFree(ctx->inv); cudaFree(ctx->exmask);
@@ -500,6 +501,7 @@ extern "C" int b2_set_positions(b2_context* ctx, const double* x_dev) {
         B2_CUDA(cudaStreamSynchronize(ctx->stream));
         B2_TRY(compute_order(ctx, hx));
         B2_TRY(upload_static(ctx));
+        B2_TRY(dist_partition(ctx));
         for (size_t k = 0; k < carried.size(); k++) {
             B2_TRY(state_permute_to_sorted(ctx, tmp[k], carried[k]));
         }
@@ -515,6 +517,7 @@ extern "C" int b2_set_positions(b2_context* ctx, const double* x_dev) {
     }
     ctx->have_positions = true;
     ctx->pos_version++;
+    ctx->x_synced = ctx->pos_version;     // the caller passes the full configuration on every rank
     if (!ctx->lists_built && ctx->nlists > 0) B2_TRY(nl_initial_build(ctx));
     return B2_OK;
 }
@@ -526,11 +529,13 @@ extern "C" int b2_set_velocities(b2_context* ctx, const double* v_dev) {
 
 extern "C" int b2_get_positions(b2_context* ctx, double* x_dev) {
     if (!ctx || !ctx->have_positions) return b2_fail(ctx, B2_ERR_STATE, "positions have not been set");
+    B2_TRY(dist_sync_positions(ctx));
     return state_permute_to_user(ctx, ctx->x, x_dev);
 }
 
 extern "C" int b2_get_velocities(b2_context* ctx, double* v_dev) {
     if (!ctx || !ctx->have_order) return b2_fail(ctx, B2_ERR_STATE, "positions have not been set");
+    B2_TRY(dist_gather3(ctx, ctx->v));
     return state_permute_to_user(ctx, ctx->v, v_dev);
 }
 
@@ -549,6 +554,7 @@ extern "C" int b2_eval(b2_context* ctx, uint32_t group_mask, int flags, double* 
         if (scratch) ctx->fvalid[32] = -1;
         B2_TRY(forces_ensure(ctx, group_mask, slot));
         if (scratch) ctx->fvalid[32] = -1;
+        B2_TRY(dist_gather_forces(ctx, ctx->fbuf[slot]));
         k_scatter_force<<<(n + T - 1)/T, T, 0, ctx->stream>>>(n, ctx->orig, ctx->fbuf[slot], forces_dev);
         B2_LAUNCH_CHECK();
     }
@@ -557,16 +563,21 @@ extern "C" int b2_eval(b2_context* ctx, uint32_t group_mask, int flags, double* 
         bool any_pair = false;
         for (const PairForce& pf : ctx->pair_forces)
             if (group_mask & (1u << pf.group)) any_pair = true;
-        if (any_pair) B2_TRY(nl_prepare(ctx, false));
+        if (any_pair) {
+            B2_TRY(dist_sync_positions(ctx));
+            B2_TRY(nl_prepare(ctx, false));
+        }
         for (const PairForce& pf : ctx->pair_forces) {
             if (!(group_mask & (1u << pf.group))) continue;
             B2_TRY(pair_eval_energy(ctx, pf, pf.group));
+            B2_TRY(dist_allreduce(ctx, ctx->d_energy + 72, 4));
             k_fold_energy<<<1, 1, 0, ctx->stream>>>(ctx->d_energy, pf.group, pf.econst, pf.family == B2_PAIR_SOFTCORE);
             B2_LAUNCH_CHECK();
         }
         for (const BondedForce& bf : ctx->bonded_forces) {
             if (!(group_mask & (1u << bf.group)) || bf.nterms == 0) continue;
             B2_TRY(bonded_eval(ctx, bf, nullptr, false, true));
+            B2_TRY(dist_allreduce(ctx, ctx->d_energy + 72, 4));
             k_fold_energy<<<1, 1, 0, ctx->stream>>>(ctx->d_energy, bf.group, 0.0, 0);
             B2_LAUNCH_CHECK();
         }
@@ -611,6 +622,7 @@ extern "C" int b2_pair_set(b2_context* ctx, int handle, long long* count_host, u
                            int* pairs_dev, long long capacity) {
     if (!ctx || handle < 0 || handle >= (int)ctx->pair_forces.size()) return b2_fail(ctx, B2_ERR_ARG, "bad pair force handle");
     if (!ctx->have_positions) return b2_fail(ctx, B2_ERR_STATE, "positions have not been set");
+    B2_TRY(dist_sync_positions(ctx));
     B2_TRY(nl_prepare(ctx, false));
     return pair_count_set(ctx, ctx->pair_forces[handle], count_host, checksum_host, pairs_dev, capacity);
 }
@@ -675,6 +687,7 @@ extern "C" int b2_set_perdof(b2_context* ctx, int var, const double* values_dev)
 extern "C" int b2_get_perdof(b2_context* ctx, int var, double* values_dev) {
     if (!ctx || var < 0 || var >= (int)ctx->perdof.size()) return b2_fail(ctx, B2_ERR_ARG, "per-DOF variable out of range");
     if (!ctx->have_order) return b2_fail(ctx, B2_ERR_STATE, "set positions first");
+    B2_TRY(dist_gather3(ctx, ctx->perdof[var]));
     return state_permute_to_user(ctx, ctx->perdof[var], values_dev);
 }
 

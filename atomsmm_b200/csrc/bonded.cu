@@ -19,6 +19,7 @@ struct BondArgs {
     const double* params;
     const int* inv;
     const double* x;
+    int a_lo, a_hi;              // owned atoms: a term belongs to the owner of its first atom
     double box[3];
     double g[8];
     const int* code_e; int ncode_e;
@@ -56,6 +57,7 @@ template <bool FORCE, bool ENERGY>
 __device__ __forceinline__ void term_bond2(const BondArgs& a, int t, float4* out, double& e, double& w) {
     {
         const int i = a.inv[a.atoms[2*t]], j = a.inv[a.atoms[2*t+1]];
+        if (i < a.a_lo || i >= a.a_hi) return;
         const double* p = a.params + (size_t)t*a.stride;
         double d[3];
         delta(a, i, j, d);
@@ -97,6 +99,7 @@ template <bool FORCE, bool ENERGY>
 __device__ __forceinline__ void term_angle(const BondArgs& a, int t, float4* out, double& e) {
     {
         const int i = a.inv[a.atoms[3*t]], j = a.inv[a.atoms[3*t+1]], k = a.inv[a.atoms[3*t+2]];
+        if (i < a.a_lo || i >= a.a_hi) return;
         const double* p = a.params + (size_t)t*a.stride;
         double u[3], v[3];
         delta(a, j, i, u);
@@ -146,6 +149,7 @@ __device__ __forceinline__ void term_torsion(const BondArgs& a, int t, float4* o
     {
         const int a1 = a.inv[a.atoms[4*t]], a2 = a.inv[a.atoms[4*t+1]], a3 = a.inv[a.atoms[4*t+2]],
                   a4 = a.inv[a.atoms[4*t+3]];
+        if (a1 < a.a_lo || a1 >= a.a_hi) return;
         const double* p = a.params + (size_t)t*a.stride;
         double F[3], G[3], H[3], A[3], B[3], C[3];
         delta(a, a2, a1, F);   // r1 - r2
@@ -226,6 +230,7 @@ static BondArgs make_args(b2_context* ctx, const BondedForce& bf) {
     BondArgs a;
     a.nterms = bf.nterms; a.stride = bf.stride; a.periodic = bf.periodic && ctx->periodic; a.family = bf.family;
     a.atoms = bf.atoms; a.params = bf.params; a.inv = ctx->inv; a.x = ctx->x;
+    a.a_lo = ctx->a_lo; a.a_hi = ctx->a_hi;
     for (int k = 0; k < 3; k++) a.box[k] = ctx->box[k];
     for (int k = 0; k < 8; k++) a.g[k] = bf.gparams[k];
     a.code_e = bf.code_e; a.ncode_e = bf.ncode_e; a.code_de = bf.code_de; a.ncode_de = bf.ncode_de;
@@ -261,13 +266,7 @@ int bonded_eval_forces(b2_context* ctx, uint32_t mask, float4* out) {
 // accumulates forces into `out` (atomics) and, if want_energy, e / virial into d_energy+72..73
 int bonded_eval(b2_context* ctx, const BondedForce& bf, float4* out, bool want_force, bool want_energy) {
     if (bf.nterms == 0) return B2_OK;
-    BondArgs a;
-    a.nterms = bf.nterms; a.stride = bf.stride; a.periodic = bf.periodic && ctx->periodic; a.family = bf.family;
-    a.atoms = bf.atoms; a.params = bf.params; a.inv = ctx->inv; a.x = ctx->x;
-    for (int k = 0; k < 3; k++) a.box[k] = ctx->box[k];
-    for (int k = 0; k < 8; k++) a.g[k] = bf.gparams[k];
-    a.code_e = bf.code_e; a.ncode_e = bf.ncode_e; a.code_de = bf.code_de; a.ncode_de = bf.ncode_de;
-    a.consts = bf.consts;
+    BondArgs a = make_args(ctx, bf);
     double* acc = ctx->d_energy + 72;
     if (want_energy) B2_CUDA(cudaMemsetAsync(acc, 0, 4*sizeof(double), ctx->stream));
     if (want_force && want_energy) return launch<true, true>(ctx, bf, a, out, acc);

@@ -121,6 +121,13 @@ struct b2_context {
     int* nl_flags = nullptr;     // [0] rebuild needed, [1] overflow, [2] rebuild counter, [3] max count
     bool lists_built = false;
 
+    // ---- domain decomposition (dist.cu) ------------------------------------------------------
+    int rank = 0, nranks = 1;
+    void* comm = nullptr;                         // ncclComm_t
+    std::vector<int> range;                       // ownership boundaries in sorted order, size nranks+1
+    int a_lo = 0, a_hi = 0, g_lo = 0, g_hi = 0;   // owned atoms [a_lo, a_hi), i-groups [g_lo, g_hi)
+    long long x_synced = 0;                       // pos_version for which x is consistent on all ranks
+
     // ---- cutoff-band pairs settled in float64 (pair.cu) -----------------------------------
     int* band_pairs = nullptr;
     unsigned* band_count = nullptr;
@@ -149,6 +156,7 @@ struct b2_context {
     int eager_steps = 0;
     long long graph_dpos = 0;
     unsigned long long graph_entry_mask = 0, graph_exit_mask = 0;
+    bool graph_entry_synced = true, graph_exit_synced = true;   // replicated positions consistent on all ranks
 };
 
 // ---- error helpers --------------------------------------------------------------------------
@@ -194,6 +202,12 @@ int bonded_eval_forces(b2_context* ctx, uint32_t mask, float4* out);
 int pme_setup(b2_context* ctx, PmeForce& pf);
 int pme_eval(b2_context* ctx, PmeForce& pf, float4* out, double* acc);
 void pme_release(PmeForce& pf);
+int dist_partition(b2_context* ctx);
+int dist_sync_positions(b2_context* ctx);
+int dist_gather3(b2_context* ctx, double* array);
+int dist_gather_forces(b2_context* ctx, float4* array);
+int dist_allreduce(b2_context* ctx, double* values, int count);
+void dist_release(b2_context* ctx);
 int forces_ensure(b2_context* ctx, uint32_t mask, int slot);
 int program_run(b2_context* ctx, int nsteps);
 int program_release(b2_context* ctx);

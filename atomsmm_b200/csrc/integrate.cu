@@ -30,11 +30,11 @@ static PerDofTable make_table(b2_context* ctx) {
 
 __global__ void k_step_begin(unsigned long long* rng_state) { rng_state[2] += 1ull; }
 
-__global__ void k_perdof(int ndof, PerDofTable tab, int target, const int* __restrict__ code, int len,
+__global__ void k_perdof(int dof_lo, int dof_hi, PerDofTable tab, int target, const int* __restrict__ code, int len,
                          const double* __restrict__ consts, double* globals,
                          const unsigned long long* __restrict__ rng_state, int serial, int mark_x) {
-    const int dof = blockIdx.x*blockDim.x + threadIdx.x;
-    if (dof >= ndof) return;
+    const int dof = dof_lo + blockIdx.x*blockDim.x + threadIdx.x;
+    if (dof >= dof_hi) return;
     RngStream rng;
     rng.seed = rng_state[0];
     rng.c0 = (uint32_t)dof; rng.c1 = (uint32_t)rng_state[2]; rng.c2 = (uint32_t)serial; rng.draw = 0;
@@ -43,11 +43,11 @@ __global__ void k_perdof(int ndof, PerDofTable tab, int target, const int* __res
     tab.vars[target][dof] = value;
 }
 
-__global__ void k_sum_partial(int ndof, PerDofTable tab, const int* __restrict__ code, int len,
+__global__ void k_sum_partial(int dof_lo, int dof_hi, PerDofTable tab, const int* __restrict__ code, int len,
                               const double* __restrict__ consts, double* globals, double* partial) {
     __shared__ double sh[8];
     double s = 0;
-    for (int dof = blockIdx.x*blockDim.x + threadIdx.x; dof < ndof; dof += gridDim.x*blockDim.x)
+    for (int dof = dof_lo + blockIdx.x*blockDim.x + threadIdx.x; dof < dof_hi; dof += gridDim.x*blockDim.x)
         s += vm_run<0>(code, len, consts, globals, &tab, dof, nullptr, nullptr, nullptr);
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
@@ -60,10 +60,10 @@ __global__ void k_sum_partial(int ndof, PerDofTable tab, const int* __restrict__
 }
 
 // fast path for the ubiquitous  mvv <- sum(m*v*v)
-__global__ void k_mvv_partial(int n, const double* __restrict__ v, const double* __restrict__ mass, double* partial) {
+__global__ void k_mvv_partial(int lo, int hi, const double* __restrict__ v, const double* __restrict__ mass, double* partial) {
     __shared__ double sh[8];
     double s = 0;
-    for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
+    for (int i = lo + blockIdx.x*blockDim.x + threadIdx.x; i < hi; i += gridDim.x*blockDim.x) {
         const double a = v[3*i], b = v[3*i+1], c = v[3*i+2];
         s += mass[i]*(a*a + b*b + c*c);
     }
@@ -120,10 +120,10 @@ struct KickArgs {
 };
 
 // v += sum_k s_k c_k f_k / m  [ ; x += c_d v ]      one thread per atom
-__global__ void k_kick(int n, double* __restrict__ v, double* __restrict__ x, KickArgs a,
+__global__ void k_kick(int lo, int hi, double* __restrict__ v, double* __restrict__ x, KickArgs a,
                        const float* __restrict__ invm, const double* __restrict__ globals) {
-    const int i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int i = lo + blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= hi) return;
     const double im = (double)invm[i];
     if (im == 0.0) return;
     double ax = 0, ay = 0, az = 0;
@@ -142,17 +142,17 @@ __global__ void k_kick(int n, double* __restrict__ v, double* __restrict__ x, Ki
     }
 }
 
-__global__ void k_drift(int ndof, double* __restrict__ x, const double* __restrict__ v,
+__global__ void k_drift(int dof_lo, int dof_hi, double* __restrict__ x, const double* __restrict__ v,
                         const double* __restrict__ mass, const double* __restrict__ globals, int gcoef) {
-    const int d = blockIdx.x*blockDim.x + threadIdx.x;
-    if (d >= ndof) return;
+    const int d = dof_lo + blockIdx.x*blockDim.x + threadIdx.x;
+    if (d >= dof_hi) return;
     if (mass[d/3] == 0.0) return;
     x[d] += globals[gcoef]*v[d];
 }
 
-__global__ void k_scale(int ndof, double* __restrict__ v, const double* __restrict__ globals, int gcoef) {
-    const int d = blockIdx.x*blockDim.x + threadIdx.x;
-    if (d >= ndof) return;
+__global__ void k_scale(int dof_lo, int dof_hi, double* __restrict__ v, const double* __restrict__ globals, int gcoef) {
+    const int d = dof_lo + blockIdx.x*blockDim.x + threadIdx.x;
+    if (d >= dof_hi) return;
     v[d] *= globals[gcoef];
 }
 
@@ -170,7 +170,10 @@ int forces_ensure(b2_context* ctx, uint32_t mask, int slot) {
     bool any_pair = false;
     for (const PairForce& pf : ctx->pair_forces)
         if (mask & (1u << pf.group)) any_pair = true;
-    if (any_pair) B2_TRY(nl_prepare(ctx, false));
+    if (any_pair) {
+        B2_TRY(dist_sync_positions(ctx));
+        B2_TRY(nl_prepare(ctx, false));
+    }
     bool written = false;
     for (const PairForce& pf : ctx->pair_forces) {
         if (!(mask & (1u << pf.group))) continue;
@@ -189,7 +192,8 @@ int forces_ensure(b2_context* ctx, uint32_t mask, int slot) {
 // program execution
 // ---------------------------------------------------------------------------------------------
 static int run_one_step(b2_context* ctx) {
-    const int n = ctx->n, ndof = 3*n, T = 256;
+    const int T = 256;
+    const int lo = ctx->a_lo, hi = ctx->a_hi, n = hi - lo, ndof = 3*n;   // owned range
     cudaStream_t s = ctx->stream;
     k_step_begin<<<1, 1, 0, s>>>(ctx->rng_state);
     B2_LAUNCH_CHECK();
@@ -200,7 +204,7 @@ static int run_one_step(b2_context* ctx) {
             break;
         case B2_OP_PERDOF: {
             PerDofTable tab = make_table(ctx);
-            k_perdof<<<(ndof + T - 1)/T, T, 0, s>>>(ndof, tab, op.a, ctx->code + op.b, op.c, ctx->consts,
+            k_perdof<<<(ndof + T - 1)/T, T, 0, s>>>(3*lo, 3*hi, tab, op.a, ctx->code + op.b, op.c, ctx->consts,
                                                       ctx->globals, ctx->rng_state, op.e, 0);
             B2_LAUNCH_CHECK();
             if (op.a == 0) ctx->pos_version++;
@@ -209,15 +213,16 @@ static int run_one_step(b2_context* ctx) {
         case B2_OP_SUM: {
             const int blocks = 296;
             if (op.d == 1) {
-                k_mvv_partial<<<blocks, T, 0, s>>>(n, ctx->v, ctx->massd, ctx->sum_partial);
+                k_mvv_partial<<<blocks, T, 0, s>>>(lo, hi, ctx->v, ctx->massd, ctx->sum_partial);
             } else {
                 PerDofTable tab = make_table(ctx);
-                k_sum_partial<<<blocks, T, 0, s>>>(ndof, tab, ctx->code + op.b, op.c, ctx->consts, ctx->globals,
+                k_sum_partial<<<blocks, T, 0, s>>>(3*lo, 3*hi, tab, ctx->code + op.b, op.c, ctx->consts, ctx->globals,
                                                     ctx->sum_partial);
             }
             B2_LAUNCH_CHECK();
             k_sum_final<<<1, 256, 0, s>>>(blocks, ctx->sum_partial, ctx->globals, op.a);
             B2_LAUNCH_CHECK();
+            B2_TRY(dist_allreduce(ctx, ctx->globals + op.a, 1));
             break;
         }
         case B2_OP_GLOBAL:
@@ -240,18 +245,18 @@ static int run_one_step(b2_context* ctx) {
                 ka.coef[k] = live ? ctx->h_code[op.b + 3*k + 1] : 0;
                 ka.sign[k] = live ? (float)ctx->h_code[op.b + 3*k + 2] : 0.f;
             }
-            k_kick<<<(n + T - 1)/T, T, 0, s>>>(n, ctx->v, ctx->x, ka, ctx->invm, ctx->globals);
+            k_kick<<<(n + T - 1)/T, T, 0, s>>>(lo, hi, ctx->v, ctx->x, ka, ctx->invm, ctx->globals);
             B2_LAUNCH_CHECK();
             if (op.c >= 0) ctx->pos_version++;
             break;
         }
         case B2_OP_DRIFT:
-            k_drift<<<(ndof + T - 1)/T, T, 0, s>>>(ndof, ctx->x, ctx->v, ctx->massd, ctx->globals, op.a);
+            k_drift<<<(ndof + T - 1)/T, T, 0, s>>>(3*lo, 3*hi, ctx->x, ctx->v, ctx->massd, ctx->globals, op.a);
             B2_LAUNCH_CHECK();
             ctx->pos_version++;
             break;
         case B2_OP_SCALE:
-            k_scale<<<(ndof + T - 1)/T, T, 0, s>>>(ndof, ctx->v, ctx->globals, op.a);
+            k_scale<<<(ndof + T - 1)/T, T, 0, s>>>(3*lo, 3*hi, ctx->v, ctx->globals, op.a);
             B2_LAUNCH_CHECK();
             break;
         case B2_OP_UPDATE_STATE:
@@ -291,10 +296,13 @@ int program_run(b2_context* ctx, int nsteps) {
     const bool use_graph = graph_allowed && !ctx->profiling;
     for (int done = 0; done < nsteps; done++) {
         const unsigned long long entry = valid_mask(ctx);
-        if (use_graph && ctx->graph_ready && (entry & ctx->graph_entry_mask) == ctx->graph_entry_mask) {
+        const bool synced = ctx->x_synced == ctx->pos_version;
+        if (use_graph && ctx->graph_ready && (entry & ctx->graph_entry_mask) == ctx->graph_entry_mask &&
+            (synced || !ctx->graph_entry_synced)) {
             B2_CUDA(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
             ctx->counters[5]++;
             ctx->pos_version += ctx->graph_dpos;
+            if (ctx->graph_exit_synced) ctx->x_synced = ctx->pos_version;
             for (int g = 0; g < B2_FSLOTS; g++)
                 if (ctx->graph_exit_mask & (1ull << g)) ctx->fvalid[g] = ctx->pos_version;
             continue;
@@ -312,6 +320,8 @@ int program_run(b2_context* ctx, int nsteps) {
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) return b2_fail(ctx, B2_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(e));
             ctx->graph_entry_mask = entry;
+            ctx->graph_entry_synced = synced;
+            ctx->graph_exit_synced = ctx->x_synced == ctx->pos_version;
             ctx->graph_exit_mask = valid_mask(ctx);
             ctx->graph_dpos = ctx->pos_version - v0;
             ctx->counters[6] = ctx->counters[0] - launches0;   // kernels per step

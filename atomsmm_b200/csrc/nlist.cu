@@ -158,7 +158,7 @@ __device__ __forceinline__ bool is_excluded(int oi, int oj, unsigned long long m
 // decided exactly by the pair kernels).  Cells farther than the list radius from the group's
 // bounding box are culled before their atoms are touched.
 #define NL_MARGIN 3e-4f
-__global__ void __launch_bounds__(128) k_build_lists(int n, int ngroups, const float4* __restrict__ pos4, Grid g,
+__global__ void __launch_bounds__(128) k_build_lists(int n, int g_lo, int ngroups, const float4* __restrict__ pos4, Grid g,
                                                     const int* __restrict__ cell_start,
                                                     const float4* __restrict__ cpos,
                                                     const int* __restrict__ corig,
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(128) k_build_lists(int n, int ngroups, const f
                                                     const int* __restrict__ excl_ptr,
                                                     const int* __restrict__ excl_idx, BuildArgs a, int* flags) {
     if (!flags[0]) return;
-    const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const int warp = g_lo + ((blockIdx.x*blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     if (warp >= ngroups) return;
@@ -423,8 +423,8 @@ int nl_prepare(b2_context* ctx, bool force) {
         a.entries[k] = L.entries; a.counts[k] = L.counts; a.gflags[k] = L.gflags; a.cap[k] = L.cap;
     }
     const int warps_per_block = 4;
-    k_build_lists<<<(ctx->ngroups + warps_per_block - 1)/warps_per_block, 32*warps_per_block, 0, s>>>(
-        n, ctx->ngroups, ctx->pos4, g, ctx->cell_start, ctx->cpos, ctx->corig, ctx->orig, ctx->exmask,
+    k_build_lists<<<std::max(1, (ctx->g_hi - ctx->g_lo + warps_per_block - 1)/warps_per_block), 32*warps_per_block, 0, s>>>(
+        n, ctx->g_lo, ctx->g_hi, ctx->pos4, g, ctx->cell_start, ctx->cpos, ctx->corig, ctx->orig, ctx->exmask,
         ctx->excl_far ? ctx->excl_ptr : nullptr, ctx->excl_idx, a, ctx->nl_flags);
     B2_LAUNCH_CHECK();
     k_save_ref<<<(3*n + T - 1)/T, T, 0, s>>>(3*n, ctx->x, ctx->xref, ctx->nl_flags);

@@ -148,7 +148,7 @@ __device__ __forceinline__ float3 rel_pos(const double* __restrict__ x, int a, d
 }
 
 template <class POT>
-__global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const double* __restrict__ x,
+__global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int g_lo, int ngroups, const double* __restrict__ x,
                                                       const float4* __restrict__ par,
                                                       const int* __restrict__ entries,
                                                       const int* __restrict__ counts,
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int ngroups, const
                                                       float rc2, BandBuffer bb, double bx, double by, double bz) {
     __shared__ float4 sx[WPB][2][32];
     __shared__ float4 sp[WPB][2][32];
-    const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const int warp = g_lo + ((blockIdx.x*blockDim.x + threadIdx.x) >> 5);
     if (warp >= ngroups) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int il = lane >> 2, jj = lane & 3;
@@ -237,24 +237,26 @@ __global__ void k_pair_band(const double* __restrict__ x, const double* __restri
 // fp64 energy / virial / dE/dlambda kernel (same list, per-pair minimum image, double state)
 // ---------------------------------------------------------------------------------------------
 template <class POT, bool SOFT>
-__global__ void __launch_bounds__(32*WPB) k_pair_energy(int n, int ngroups, const double* __restrict__ x,
+__global__ void __launch_bounds__(32*WPB) k_pair_energy(int n, int g_lo, int ngroups, int a_lo, int a_hi,
+                                                       const double* __restrict__ x,
                                                        const double* __restrict__ pard,
                                                        const int* __restrict__ entries,
                                                        const int* __restrict__ counts, int cap, POT pot,
                                                        double rc2, double bx, double by, double bz,
                                                        double* __restrict__ acc /* e, w, dlv, dlc */) {
-    const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const int warp = g_lo + ((blockIdx.x*blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     double e_sum = 0, w_sum = 0, dv_sum = 0, dc_sum = 0;
     if (warp < ngroups) {
         const int il = lane >> 2, jj = lane & 3;
         const int i = warp*B2_GROUP + il;
         const int ic = min(i, n - 1);
+        const bool mine = i >= a_lo && i < a_hi;
         const double xi = x[3*ic], yi = x[3*ic+1], zi = x[3*ic+2];
         const double qi = pard[3*ic], si = pard[3*ic+1], ei = pard[3*ic+2];
         const int cnt = counts[warp];
         const int* __restrict__ base = entries + (size_t)warp*cap;
-        for (int k = jj; k < cnt; k += 4) {
+        for (int k = jj; k < cnt && mine; k += 4) {
             const int en = base[k];
             const int j = en & 0xffffff;
             if (((unsigned)en >> (24 + il)) & 1u) continue;
@@ -355,13 +357,14 @@ static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, POTD potd
     BandBuffer bb{ctx->band_pairs, ctx->band_count, ctx->band_capacity};
     B2_CUDA(cudaMemsetAsync(ctx->band_count, 0, sizeof(unsigned), ctx->stream));
     const NList& L = ctx->lists[pf.list];
-    const int blocks = (ctx->ngroups + WPB - 1)/WPB;
+    const int blocks = (ctx->g_hi - ctx->g_lo + WPB - 1)/WPB;
+    if (blocks == 0) return B2_OK;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->profiling) {
         cudaEventCreate(&ev0); cudaEventCreate(&ev1);
         cudaEventRecord(ev0, ctx->stream);
     }
-    k_pair_force<POT><<<blocks, 32*WPB, 0, ctx->stream>>>(ctx->n, ctx->ngroups, ctx->x, ctx->par[pf.set],
+    k_pair_force<POT><<<blocks, 32*WPB, 0, ctx->stream>>>(ctx->n, ctx->g_lo, ctx->g_hi, ctx->x, ctx->par[pf.set],
                                                           L.entries, L.counts, L.gflags, L.cap, out,
                                                           accumulate ? 1 : 0, pot, rc2, bb, ctx->box[0], ctx->box[1],
                                                           ctx->box[2]);
@@ -381,8 +384,9 @@ static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, POTD potd
 template <class POT, bool SOFT>
 static int launch_energy(b2_context* ctx, const PairForce& pf, POT pot, double rc2, double* acc) {
     const NList& L = ctx->lists[pf.list];
-    const int blocks = (ctx->ngroups + WPB - 1)/WPB;
-    k_pair_energy<POT, SOFT><<<blocks, 32*WPB, 0, ctx->stream>>>(ctx->n, ctx->ngroups, ctx->x,
+    const int blocks = (ctx->g_hi - ctx->g_lo + WPB - 1)/WPB;
+    if (blocks == 0) return B2_OK;
+    k_pair_energy<POT, SOFT><<<blocks, 32*WPB, 0, ctx->stream>>>(ctx->n, ctx->g_lo, ctx->g_hi, ctx->a_lo, ctx->a_hi, ctx->x,
                                                                   ctx->pard[pf.set], L.entries, L.counts,
                                                                   L.cap, pot, rc2, ctx->box[0], ctx->box[1],
                                                                   ctx->box[2], acc);
@@ -450,6 +454,7 @@ int pair_eval_energy(b2_context* ctx, const PairForce& pf, int group) {
 
 int pair_count_set(b2_context* ctx, const PairForce& pf, long long* count, unsigned long long* checksum,
                    int* pairs_dev, long long capacity) {
+    if (ctx->nranks > 1) return b2_fail(ctx, B2_ERR_UNSUPPORTED, "pair-set extraction is a single-GPU diagnostic");
     const NList& L = ctx->lists[pf.list];
     double rc = pf.cutoff;
     if (pf.family == B2_PAIR_NEAR || pf.family == B2_PAIR_DAMPED) rc = std::min(rc, pf.params[2]);

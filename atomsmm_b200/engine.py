@@ -67,6 +67,10 @@ _SIGNATURES = {
     'b2_set_profiling': [c_void, ctypes.c_int],
     'b2_get_profile': [c_void, ctypes.c_int, c_double_p, ctypes.POINTER(ctypes.c_longlong),
                        ctypes.POINTER(ctypes.c_longlong)],
+    'b2_comm_unique_id': [ctypes.c_char_p],
+    'b2_comm_init': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_char_p],
+    'b2_partition_ranges': [ctypes.c_int, c_int_p, ctypes.c_int, c_int_p],
+    'b2_comm_info': [c_void, c_int_p, c_int_p, c_int_p, c_int_p, ctypes.POINTER(ctypes.c_longlong)],
 }
 
 
@@ -99,6 +103,25 @@ def _dptr(array):
 
 def _iptr(array):
     return np.ascontiguousarray(array, dtype=np.int32).ctypes.data_as(c_int_p)
+
+
+def partition_ranges(molecule_sorted, nranks):
+    """Ownership boundaries (length nranks+1) of the spatial decomposition: cuts fall on the
+    molecule boundaries nearest to k*n/nranks.  Pure host logic of the C library (no GPU)."""
+    mol = np.ascontiguousarray(molecule_sorted, dtype=np.int32)
+    out = np.zeros(nranks + 1, dtype=np.int32)
+    code = library().b2_partition_ranges(len(mol), _iptr(mol), int(nranks), out.ctypes.data_as(c_int_p))
+    if code != 0:
+        raise EngineError('b2_partition_ranges failed (code %d)' % code)
+    return out
+
+
+def broadcast_bytes(payload, src=0, group=None):
+    """Broadcast a bytes object from rank ``src`` over torch.distributed (gloo or nccl)."""
+    import torch.distributed as dist
+    box = [payload if dist.get_rank(group) == src else None]
+    dist.broadcast_object_list(box, src=src, group=group)
+    return box[0]
 
 
 def _molecules(system):
@@ -202,7 +225,9 @@ class State(object):
 class Context(object):
     """Execution context on one B200.  ``properties``: 'DeviceIndex' (default 0 or LOCAL_RANK),
     'Skin' (neighbour-list skin in nm, default 0.1), 'FastPaths' ('false' routes every per-DOF step
-    through the generic VM)."""
+    through the generic VM), 'DomainDecomposition' ('true': the ranks of the initialised
+    torch.distributed world integrate ONE system together, each owning a spatial range of whole
+    molecules; every rank must make the same calls with the same arguments)."""
 
     def __init__(self, system, integrator, platform=None, properties=None):
         import torch
@@ -241,6 +266,9 @@ class Context(object):
         self._have_positions = False
         self._pair_handles = {}        # id(force) -> (handle, info)
         self._describe()
+        self._rank, self._nranks = 0, 1
+        if str(properties.get('DomainDecomposition', 'false')).lower() == 'true':
+            self._join_world()
         self._program = None
         if integrator is not None:
             if getattr(integrator, '_context', None) is not None:
@@ -264,6 +292,28 @@ class Context(object):
                 self._handle = c_void()
         except Exception:
             pass
+
+    def _join_world(self):
+        import torch.distributed as dist
+        torch = self._torch
+        if not dist.is_initialized():
+            raise EngineError('DomainDecomposition needs an initialised torch.distributed process group')
+        self._rank, self._nranks = dist.get_rank(), dist.get_world_size()
+        if self._nranks == 1:
+            return
+        torch.cuda.set_device(self._device)
+        ident = ctypes.create_string_buffer(128)
+        if self._rank == 0:
+            self._check(self._lib.b2_comm_unique_id(ident), None)
+        payload = broadcast_bytes(ident.raw if self._rank == 0 else None)
+        self._call('b2_comm_init', self._nranks, self._rank, ctypes.create_string_buffer(payload, 128))
+
+    def comm_info(self):
+        rank, nranks, lo, hi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        exchanges = ctypes.c_longlong()
+        self._call('b2_comm_info', ctypes.byref(rank), ctypes.byref(nranks), ctypes.byref(lo), ctypes.byref(hi),
+                   ctypes.byref(exchanges))
+        return dict(rank=rank.value, nranks=nranks.value, lo=lo.value, hi=hi.value, exchanges=exchanges.value)
 
     # -- description -> C ABI ----------------------------------------------------------------------
     def _describe(self):
@@ -601,6 +651,10 @@ class Context(object):
         """Maxwell-Boltzmann velocities (numpy Philox stream; OpenMM's SFMT stream is not
         reproducible outside OpenMM)."""
         kT = 8.314472471220217e-3*float(_md(temperature))
+        if self._nranks > 1:    # every rank must draw the same velocities
+            import pickle
+            seed = randomSeed if randomSeed is not None else int(np.random.SeedSequence().entropy % (1 << 63))
+            randomSeed = pickle.loads(broadcast_bytes(pickle.dumps(seed) if self._rank == 0 else None))
         rng = np.random.Generator(np.random.Philox(randomSeed if randomSeed is not None else None))
         v = rng.standard_normal((self._n, 3))
         with np.errstate(divide='ignore'):

@@ -185,6 +185,22 @@ B2_API int b2_get_counters(b2_context* ctx, long long out_host[8]);
 B2_API int b2_set_profiling(b2_context* ctx, int on);
 B2_API int b2_get_profile(b2_context* ctx, int handle, double* total_ms, long long* launches, long long* entries);
 
+/* ---- multi-GPU: spatial decomposition of ONE system over the GPUs of a node ---------------- *
+ * The reference is single-process; these calls are the engine's own.  One process
+ * (one context) per GPU.  Rank 0 obtains a 128-byte NCCL id, the host side broadcasts it (e.g.
+ * torch.distributed), and every rank calls b2_comm_init BEFORE b2_set_positions.  Afterwards every
+ * rank makes the same calls with the same (full-system) arguments; each rank integrates the atoms
+ * of its ownership range and the getters return the full, gathered state on every rank. */
+B2_API int b2_comm_unique_id(char out128[128]);
+B2_API int b2_comm_init(b2_context* ctx, int nranks, int rank, const char id128[128]);
+/* Pure host helper (no GPU needed): the ownership ranges the engine uses.  molecule_sorted[n] is the
+ * molecule id of each atom in the engine's spatial order; out_ranges[nranks+1] receives boundaries
+ * that fall on molecule boundaries nearest to k*n/nranks. */
+B2_API int b2_partition_ranges(int n, const int* molecule_sorted, int nranks, int* out_ranges);
+/* ownership range [lo, hi) of this rank in the engine's spatial order, and the number of
+ * position exchanges performed so far */
+B2_API int b2_comm_info(b2_context* ctx, int* rank, int* nranks, int* lo, int* hi, long long* exchanges);
+
 #ifdef __cplusplus
 }
 #endif

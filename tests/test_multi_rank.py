@@ -1,0 +1,178 @@
+"""
+The N > 1 path.
+
+CPU (gloo, world_size 2): the host-side logic of the spatial decomposition -- ownership ranges from
+the C library's pure-host entry point, the communicator-id broadcast, and the max-over-ranks /
+sum-over-ranks aggregation the benchmark uses.
+
+GPU (NCCL, world_size 2, skipped on a single-GPU box): ONE RESPA water system integrated by two
+ranks with domain decomposition must reproduce the single-GPU trajectory and single-point
+forces/energies.  The reference is single-process, so the single-GPU engine -- itself
+checked against the oracle in test_gpu_*.py -- is the comparison.
+"""
+
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _init(rank, world, port, backend):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group(backend, rank=rank, world_size=world)
+    return dist
+
+
+def _sorted_molecules(seed, nmol):
+    rng = np.random.default_rng(seed)
+    sizes = rng.integers(1, 20, size=nmol)
+    return np.repeat(np.arange(nmol), sizes)
+
+
+def _host_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    from atomsmm_b200 import engine
+    dist = _init(rank, world, port, 'gloo')
+    try:
+        # the id broadcast used by Context._join_world
+        payload = bytes(range(128)) if rank == 0 else None
+        assert engine.broadcast_bytes(payload) == bytes(range(128))
+        # every rank derives the same ownership ranges; together they tile [0, n) in whole molecules
+        mol = _sorted_molecules(7, 500)
+        ranges = engine.partition_ranges(mol, world)
+        gathered = [None]*world
+        dist.all_gather_object(gathered, ranges.tolist())
+        assert all(g == gathered[0] for g in gathered)
+        lo, hi = int(ranges[rank]), int(ranges[rank + 1])
+        owned = torch.zeros(len(mol), dtype=torch.int64)
+        owned[lo:hi] = 1
+        dist.all_reduce(owned)
+        assert bool((owned == 1).all())
+        for cut in ranges[1:-1]:
+            assert mol[cut] != mol[cut - 1]
+        # aggregation used by bench.py: time = max over ranks, work = sum over ranks
+        t = torch.tensor([1.0 + rank], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert float(t) == float(world)
+        out.put((rank, 'ok'))
+    except Exception as error:    # pragma: no cover
+        out.put((rank, repr(error)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_host_logic_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_host_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, 'ok'), (1, 'ok')], results
+
+
+@pytest.mark.parametrize('nranks', [1, 2, 3, 8])
+def test_partition_properties(nranks):
+    sys.path.insert(0, ROOT)
+    from atomsmm_b200 import engine
+    mol = _sorted_molecules(3, 1000)
+    n = len(mol)
+    ranges = engine.partition_ranges(mol, nranks)
+    assert ranges[0] == 0 and ranges[-1] == n
+    assert np.all(np.diff(ranges) >= 0)
+    for k in range(1, nranks):
+        cut = ranges[k]
+        assert cut == 0 or cut == n or mol[cut] != mol[cut - 1]
+        assert abs(cut - n*k//nranks) < 20      # never farther than one molecule from the even split
+    # degenerate: one giant molecule cannot be split
+    ranges = engine.partition_ranges(np.zeros(100, dtype=np.int32), 4)
+    assert set(ranges.tolist()) <= {0, 100}
+
+
+def _dd_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import torch
+    torch.cuda.set_device(rank)
+    dist = _init(rank, world, port, 'nccl')
+    try:
+        import atomsmm_b200 as atomsmm
+        from atomsmm_b200 import mm, unit
+        import systems
+        fs, K = unit.femtoseconds, unit.kelvin
+        respa, pdb = systems.respa_water()
+        pos = systems.positions_of(pdb)
+        big, bigpos = systems.replicate(respa, pos, np.array([2.5, 2.5, 2.5]), 2)
+        n = big.getNumParticles()
+        mass = np.array([big.getParticleMass(i).value_in_md_units() for i in range(n)])
+        rng = np.random.default_rng(5)
+        vel = rng.standard_normal((n, 3))*np.sqrt(8.314472471220217e-3*300/mass)[:, None]
+
+        def factory():
+            dof = atomsmm.countDegreesOfFreedom(big)
+            nh = atomsmm.NoseHooverPropagator(300*K, dof, 100*fs)
+            return atomsmm.TrotterSuzukiPropagator(atomsmm.RespaPropagator([4, 2, 1]),
+                                                   atomsmm.SuzukiYoshidaPropagator(nh, 3)).integrator(4*fs)
+
+        def run(properties, steps):
+            integrator = factory()
+            context = mm.Context(big, integrator, mm.Platform.getPlatformByName('B200'), properties)
+            context.setPositions(bigpos)
+            context.setVelocities(vel)
+            first = context.getState(getForces=True, getEnergy=True)
+            integrator.step(steps)
+            last = context.getState(getPositions=True, getVelocities=True, getEnergy=True)
+            return context, first, last
+
+        single, f1, s1 = run({'DeviceIndex': rank}, 12)
+        shared, f2, s2 = run({'DeviceIndex': rank, 'DomainDecomposition': 'true'}, 12)
+        info = shared.comm_info()
+        assert info['nranks'] == world and info['hi'] > info['lo'] and info['exchanges'] > 0
+        fa, fb = f1._forces, f2._forces
+        assert np.sqrt(np.sum((fa - fb)**2)/np.sum(fa**2)) < 1e-6
+        assert abs(f1._potential - f2._potential) <= 1e-9*abs(f1._potential)
+        assert np.max(np.abs(s1._positions - s2._positions)) < 1e-6
+        assert np.sqrt(np.sum((s1._velocities - s2._velocities)**2)/np.sum(s1._velocities**2)) < 1e-5
+        assert abs(s1._potential - s2._potential) <= 1e-6*abs(s1._potential)
+        assert abs(s1._kinetic - s2._kinetic) <= 1e-6*abs(s1._kinetic)
+        out.put((rank, 'ok'))
+    except Exception as error:
+        import traceback
+        out.put((rank, traceback.format_exc() + repr(error)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_domain_decomposition_matches_single_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dd_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, 'ok'), (1, 'ok')], results
