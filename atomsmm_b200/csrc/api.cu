@@ -103,6 +103,7 @@ extern "C" int b2_create(int device, b2_context** out) {
     if (cudaMalloc(&ctx->d_energy, sizeof(double)*96) != cudaSuccess ||
         cudaMalloc(&ctx->rng_state, sizeof(unsigned long long)*4) != cudaSuccess ||
         cudaMalloc(&ctx->sum_partial, sizeof(double)*1024) != cudaSuccess ||
+        cudaMalloc(&ctx->ticket, sizeof(unsigned)*4) != cudaSuccess ||
         cudaMalloc(&ctx->band_pairs, sizeof(int)*2*ctx->band_capacity) != cudaSuccess ||
         cudaMalloc(&ctx->band_count, sizeof(unsigned)) != cudaSuccess) {
         delete ctx;
@@ -110,6 +111,8 @@ extern "C" int b2_create(int device, b2_context** out) {
     }
     cudaMemset(ctx->d_energy, 0, sizeof(double)*96);
     cudaMemset(ctx->rng_state, 0, sizeof(unsigned long long)*4);
+    cudaMemset(ctx->ticket, 0, sizeof(unsigned)*4);
+    ctx->sum_partial_size = 1024;
     *out = ctx;
     return B2_OK;
 }
@@ -135,7 +138,8 @@ extern "C" int b2_destroy(b2_context* ctx) {
     cudaFree(ctx->cpos); cudaFree(ctx->corig);
     cudaFree(ctx->nl_flags); cudaFree(ctx->d_energy); cudaFree(ctx->code); cudaFree(ctx->consts);
     cudaFree(ctx->globals); cudaFree(ctx->sum_partial); cudaFree(ctx->rng_state);
-    cudaFree(ctx->band_pairs); cudaFree(ctx->band_count);
+    cudaFree(ctx->band_pairs); cudaFree(ctx->band_count); cudaFree(ctx->ticket);
+    cudaFree(ctx->chunk_start); cudaFree(ctx->chunk_term_ptr); cudaFree(ctx->chunk_terms);
     for (BondedForce& bf : ctx->bonded_forces) free_bonded(bf);
     for (PmeForce& pm : ctx->pme_forces) pme_release(pm);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -302,6 +306,7 @@ static int add_bonded_common(b2_context* ctx, BondedForce& bf, const int* atoms,
     for (int k = 0; k < arity*bf.nterms; k++)
         if (atoms[k] < 0 || atoms[k] >= ctx->n) return b2_fail(ctx, B2_ERR_ARG, "bonded atom index out of range");
     if (bf.nterms > 0) {
+        bf.h_atoms.assign(atoms, atoms + (size_t)arity*bf.nterms);
         B2_CUDA(cudaMalloc(&bf.atoms, sizeof(int)*arity*bf.nterms));
         B2_CUDA(cudaMemcpy(bf.atoms, atoms, sizeof(int)*arity*bf.nterms, cudaMemcpyHostToDevice));
         const size_t np = (size_t)std::max(1, bf.stride)*bf.nterms;
@@ -327,6 +332,7 @@ extern "C" int b2_add_bonded_force(b2_context* ctx, int family, int group, int n
     for (int k = 0; k < ngparams; k++) bf.gparams[k] = gparams[k];
     B2_TRY(add_bonded_common(ctx, bf, atoms, params));
     ctx->bonded_forces.push_back(bf);
+    ctx->inner_built = false;
     program_release(ctx);
     if (handle) *handle = (int)ctx->bonded_forces.size() - 1;
     return B2_OK;
@@ -351,6 +357,7 @@ extern "C" int b2_add_custom_bonded_force(b2_context* ctx, int family, int group
     if (ncode_de) B2_CUDA(cudaMemcpy(bf.code_de, code_de, sizeof(int)*2*ncode_de, cudaMemcpyHostToDevice));
     if (nconsts) B2_CUDA(cudaMemcpy(bf.consts, consts, sizeof(double)*nconsts, cudaMemcpyHostToDevice));
     ctx->bonded_forces.push_back(bf);
+    ctx->inner_built = false;
     program_release(ctx);
     if (handle) *handle = (int)ctx->bonded_forces.size() - 1;
     return B2_OK;
@@ -502,6 +509,7 @@ extern "C" int b2_set_positions(b2_context* ctx, const double* x_dev) {
         B2_TRY(compute_order(ctx, hx));
         B2_TRY(upload_static(ctx));
         B2_TRY(dist_partition(ctx));
+        ctx->inner_built = false;
         for (size_t k = 0; k < carried.size(); k++) {
             B2_TRY(state_permute_to_sorted(ctx, tmp[k], carried[k]));
         }

@@ -1,0 +1,214 @@
+// Per-term device functions of the explicit-list (bonded) families, shared by the stand-alone
+// bonded kernels (bonded.cu) and the fused RESPA inner-loop kernel (integrate.cu).
+//
+// GEO abstracts where positions come from and where forces go:
+//   GlobalGeo  master positions in HBM (sorted order), fp32 atomics into a force buffer
+//   LocalGeo   a molecule chunk staged in shared memory, fp64 atomics into shared memory
+#pragma once
+
+#include <math.h>
+
+#include "ctx.h"
+#include "vm.cuh"
+
+struct BondArgs {
+    int nterms, stride, periodic, family;
+    const int* atoms;
+    const double* params;
+    const int* inv;
+    int a_lo, a_hi;              // owned atoms: a term belongs to the owner of its first atom
+    double box[3];
+    double g[8];
+    const int* code_e; int ncode_e;
+    const int* code_de; int ncode_de;
+    const double* consts;
+};
+
+struct GlobalGeo {
+    const double* x;
+    float4* out;
+    __device__ __forceinline__ double pos(int i, int k) const { return x[3*i+k]; }
+    __device__ __forceinline__ void add(int i, double fx, double fy, double fz) const {
+        atomicAdd(&out[i].x, (float)fx);
+        atomicAdd(&out[i].y, (float)fy);
+        atomicAdd(&out[i].z, (float)fz);
+    }
+};
+
+struct LocalGeo {
+    const double* xs;     // [chunk][3] shared memory
+    double* fs;           // [chunk][3] shared memory
+    int base;             // sorted index of the chunk's first atom
+    __device__ __forceinline__ double pos(int i, int k) const { return xs[3*(i - base)+k]; }
+    __device__ __forceinline__ void add(int i, double fx, double fy, double fz) const {
+        atomicAdd(&fs[3*(i - base)], fx);
+        atomicAdd(&fs[3*(i - base)+1], fy);
+        atomicAdd(&fs[3*(i - base)+2], fz);
+    }
+};
+
+template <class GEO>
+__device__ __forceinline__ void delta(const BondArgs& a, const GEO& geo, int i, int j, double (&d)[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        d[k] = geo.pos(j, k) - geo.pos(i, k);
+        if (a.periodic) d[k] -= a.box[k]*rint(d[k]/a.box[k]);
+    }
+}
+
+__device__ __forceinline__ void block_accumulate(double e, double w, double* acc) {
+    for (int o = 16; o > 0; o >>= 1) {
+        e += __shfl_xor_sync(0xffffffffu, e, o);
+        w += __shfl_xor_sync(0xffffffffu, w, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (e != 0.0) atomicAdd(&acc[0], e);
+        if (w != 0.0) atomicAdd(&acc[1], w);
+    }
+}
+
+// two-body families: E(r); force from dE/dr
+template <bool FORCE, bool ENERGY, class GEO>
+__device__ __forceinline__ void term_bond2(const BondArgs& a, int t, const GEO& geo, double& e, double& w) {
+    {
+        const int i = a.inv[a.atoms[2*t]], j = a.inv[a.atoms[2*t+1]];
+        if (i < a.a_lo || i >= a.a_hi) return;
+        const double* p = a.params + (size_t)t*a.stride;
+        double d[3];
+        delta(a, geo, i, j, d);
+        const double r2 = d[0]*d[0] + d[1]*d[1] + d[2]*d[2];
+        const double r = sqrt(r2);
+        double dedr = 0;
+        if (a.family == B2_BOND_HARMONIC) {
+            const double dr = r - p[0];
+            e = 0.5*p[1]*dr*dr;
+            dedr = p[1]*dr;
+        } else if (a.family == B2_BOND_LJC) {
+            const double qq = p[0], sig = p[1], eps = p[2];
+            const double s2 = sig*sig/r2, s6 = s2*s2*s2;
+            e = 4*eps*s6*(s6 - 1) + a.g[0]*qq/r;
+            dedr = -(24*eps*s6*(2*s6 - 1) + a.g[0]*qq/r)/r;
+            if (a.g[1] > 0) {
+                const double al = a.g[1], kq = a.g[0]*p[3];
+                const double er = erf(al*r);
+                e -= kq*er/r;
+                dedr -= kq*(2*al/sqrt(M_PI)*exp(-al*al*r2)/r - er/r2);
+            }
+        } else {
+            double vars[10];
+            vars[0] = r;
+            for (int k = 0; k < a.stride && k < 9; k++) vars[1+k] = p[k];
+            if (ENERGY) e = vm_run<2>(a.code_e, a.ncode_e, a.consts, nullptr, nullptr, 0, vars, nullptr, nullptr);
+            dedr = vm_run<2>(a.code_de, a.ncode_de, a.consts, nullptr, nullptr, 0, vars, nullptr, nullptr);
+        }
+        w = -dedr*r;
+        if (FORCE) {
+            const double s = dedr/r;   // force on j = -dE/dr * d/r
+            geo.add(i, s*d[0], s*d[1], s*d[2]);
+            geo.add(j, -s*d[0], -s*d[1], -s*d[2]);
+        }
+    }
+}
+
+template <bool FORCE, bool ENERGY, class GEO>
+__device__ __forceinline__ void term_angle(const BondArgs& a, int t, const GEO& geo, double& e) {
+    {
+        const int i = a.inv[a.atoms[3*t]], j = a.inv[a.atoms[3*t+1]], k = a.inv[a.atoms[3*t+2]];
+        if (i < a.a_lo || i >= a.a_hi) return;
+        const double* p = a.params + (size_t)t*a.stride;
+        double u[3], v[3];
+        delta(a, geo, j, i, u);
+        delta(a, geo, j, k, v);
+        const double ru2 = u[0]*u[0] + u[1]*u[1] + u[2]*u[2], rv2 = v[0]*v[0] + v[1]*v[1] + v[2]*v[2];
+        const double ru = sqrt(ru2), rv = sqrt(rv2);
+        double c = (u[0]*v[0] + u[1]*v[1] + u[2]*v[2])/(ru*rv);
+        c = fmin(1.0, fmax(-1.0, c));
+        const double theta = acos(c);
+        double dedt;
+        if (a.family == B2_ANGLE_HARMONIC) {
+            const double dt = theta - p[0];
+            e = 0.5*p[1]*dt*dt;
+            dedt = p[1]*dt;
+        } else {
+            double vars[10];
+            vars[0] = theta;
+            for (int q = 0; q < a.stride && q < 9; q++) vars[1+q] = p[q];
+            if (ENERGY) e = vm_run<2>(a.code_e, a.ncode_e, a.consts, nullptr, nullptr, 0, vars, nullptr, nullptr);
+            dedt = vm_run<2>(a.code_de, a.ncode_de, a.consts, nullptr, nullptr, 0, vars, nullptr, nullptr);
+        }
+        if (FORCE) {
+            const double s = sqrt(fmax(1.0 - c*c, 1e-30));
+            // d theta/d r_i = -(v/(ru rv) - c u/ru^2)/s
+            double fi[3], fk[3];
+            for (int q = 0; q < 3; q++) {
+                const double dti = -(v[q]/(ru*rv) - c*u[q]/ru2)/s;
+                const double dtk = -(u[q]/(ru*rv) - c*v[q]/rv2)/s;
+                fi[q] = -dedt*dti;
+                fk[q] = -dedt*dtk;
+            }
+            geo.add(i, fi[0], fi[1], fi[2]);
+            geo.add(k, fk[0], fk[1], fk[2]);
+            geo.add(j, -(fi[0]+fk[0]), -(fi[1]+fk[1]), -(fi[2]+fk[2]));
+        }
+    }
+}
+
+__device__ __forceinline__ void cross3(const double (&a)[3], const double (&b)[3], double (&c)[3]) {
+    c[0] = a[1]*b[2] - a[2]*b[1];
+    c[1] = a[2]*b[0] - a[0]*b[2];
+    c[2] = a[0]*b[1] - a[1]*b[0];
+}
+
+template <bool FORCE, bool ENERGY, class GEO>
+__device__ __forceinline__ void term_torsion(const BondArgs& a, int t, const GEO& geo, double& e) {
+    {
+        const int a1 = a.inv[a.atoms[4*t]], a2 = a.inv[a.atoms[4*t+1]], a3 = a.inv[a.atoms[4*t+2]],
+                  a4 = a.inv[a.atoms[4*t+3]];
+        if (a1 < a.a_lo || a1 >= a.a_hi) return;
+        const double* p = a.params + (size_t)t*a.stride;
+        double F[3], G[3], H[3], A[3], B[3], C[3];
+        delta(a, geo, a2, a1, F);   // r1 - r2
+        delta(a, geo, a3, a2, G);   // r2 - r3
+        delta(a, geo, a3, a4, H);   // r4 - r3
+        cross3(F, G, A);
+        cross3(H, G, B);
+        cross3(B, A, C);
+        const double A2 = A[0]*A[0] + A[1]*A[1] + A[2]*A[2], B2 = B[0]*B[0] + B[1]*B[1] + B[2]*B[2];
+        const double G2 = G[0]*G[0] + G[1]*G[1] + G[2]*G[2], gn = sqrt(G2);
+        const double norm = sqrt(A2*B2);
+        const double cosphi = (A[0]*B[0] + A[1]*B[1] + A[2]*B[2])/norm;
+        const double sinphi = (C[0]*G[0] + C[1]*G[1] + C[2]*G[2])/(norm*gn);
+        const double phi = atan2(sinphi, cosphi);
+        const double n = p[0], phase = p[1], k = p[2];
+        e = k*(1.0 + cos(n*phi - phase));
+        if (FORCE) {
+            const double dedphi = -k*n*sin(n*phi - phase);
+            const double fg = F[0]*G[0] + F[1]*G[1] + F[2]*G[2], hg = H[0]*G[0] + H[1]*G[1] + H[2]*G[2];
+            double f1[3], f2[3], f3[3], f4[3];
+            for (int q = 0; q < 3; q++) {
+                const double d1 = -gn/A2*A[q];
+                const double d4 = gn/B2*B[q];
+                const double d2 = gn/A2*A[q] + fg/(A2*gn)*A[q] - hg/(B2*gn)*B[q];
+                const double d3 = -gn/B2*B[q] - fg/(A2*gn)*A[q] + hg/(B2*gn)*B[q];
+                f1[q] = -dedphi*d1; f2[q] = -dedphi*d2; f3[q] = -dedphi*d3; f4[q] = -dedphi*d4;
+            }
+            geo.add(a1, f1[0], f1[1], f1[2]);
+            geo.add(a2, f2[0], f2[1], f2[2]);
+            geo.add(a3, f3[0], f3[1], f3[2]);
+            geo.add(a4, f4[0], f4[1], f4[2]);
+        }
+    }
+}
+
+
+// all explicit-list forces of one force group in a single launch (force path only)
+#define B2_MAX_BATCH 8
+struct BondBatch {
+    int count;
+    int first[B2_MAX_BATCH + 1];     // prefix sums of term counts
+    int arity[B2_MAX_BATCH];
+    BondArgs a[B2_MAX_BATCH];
+};
+
+
+BondArgs bonded_make_args(b2_context* ctx, const BondedForce& bf);

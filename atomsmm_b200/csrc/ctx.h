@@ -28,6 +28,8 @@
 #define B2_MAX_LISTS 4
 #define B2_FSLOTS 33          // force buffers: groups 0..31 and 32 = total
 #define B2_MAX_PAIR_PARAMS 16
+#define B2_CHUNK 128           // atoms per molecule chunk of the fused inner-loop kernel
+#define B2_INNER_MAX_FORCES 16
 
 struct PairParams {           // passed by value to kernels
     int family;
@@ -46,6 +48,7 @@ struct PairForce {
 struct BondedForce {
     int family, group, nterms, arity, stride, periodic;
     int* atoms = nullptr;         // device, caller numbering
+    std::vector<int> h_atoms;     // host copy (chunk construction)
     double* params = nullptr;     // device
     double gparams[8] = {0};
     int* code_e = nullptr; int ncode_e = 0;
@@ -128,6 +131,12 @@ struct b2_context {
     int a_lo = 0, a_hi = 0, g_lo = 0, g_hi = 0;   // owned atoms [a_lo, a_hi), i-groups [g_lo, g_hi)
     long long x_synced = 0;                       // pos_version for which x is consistent on all ranks
 
+    // ---- fused RESPA inner loop (integrate.cu) ----------------------------------------------
+    bool inner_built = false, inner_ok = false;
+    int nchunks = 0;
+    int *chunk_start = nullptr, *chunk_term_ptr = nullptr;
+    int2* chunk_terms = nullptr;
+
     // ---- cutoff-band pairs settled in float64 (pair.cu) -----------------------------------
     int* band_pairs = nullptr;
     unsigned* band_count = nullptr;
@@ -148,7 +157,9 @@ struct b2_context {
     std::vector<int> h_code;                      // host copy (kick term tables live in the code pool)
     double *consts = nullptr; int nconsts = 0;
     double *globals = nullptr; int nglobals = 0;
-    double* sum_partial = nullptr;
+    double* sum_partial = nullptr;                // per-block partial sums (sized by ensure_partials)
+    int sum_partial_size = 0;
+    unsigned* ticket = nullptr;                   // last-block-done counter of the velocity kernel
     unsigned long long* rng_state = nullptr;      // [0] seed, [1] draw counter
     bool program_loaded = false;
     cudaGraphExec_t graph_exec = nullptr;
@@ -209,6 +220,7 @@ int dist_gather_forces(b2_context* ctx, float4* array);
 int dist_allreduce(b2_context* ctx, double* values, int count);
 void dist_release(b2_context* ctx);
 int forces_ensure(b2_context* ctx, uint32_t mask, int slot);
+int inner_prepare(b2_context* ctx);
 int program_run(b2_context* ctx, int nsteps);
 int program_release(b2_context* ctx);
 int state_permute_to_sorted(b2_context* ctx, const double* user, double* sorted);

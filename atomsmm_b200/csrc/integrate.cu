@@ -12,8 +12,9 @@
 //   * the whole step is captured once into a CUDA graph and replayed.
 #include <math.h>
 
-#include "ctx.h"
-#include "vm.cuh"
+#include <algorithm>
+
+#include "bonded.cuh"
 
 #define FULL 0xffffffffu
 
@@ -117,28 +118,91 @@ struct KickArgs {
     int coef[B2_MAX_KICK_TERMS];
     float sign[B2_MAX_KICK_TERMS];
     int drift;                       // global index of the drift coefficient, -1: none
+    int prescale;                    // global index of a factor applied to v first, -1: none
+    int mvv;                         // global index receiving sum(m*v*v) of the new velocities, -1: none
+    int code_len;                    // scalar program run once after the sum (0: none)
 };
 
-// v += sum_k s_k c_k f_k / m  [ ; x += c_d v ]      one thread per atom
-__global__ void k_kick(int lo, int hi, double* __restrict__ v, double* __restrict__ x, KickArgs a,
-                       const float* __restrict__ invm, const double* __restrict__ globals) {
+__device__ void run_scalar_program(const int* __restrict__ code, int len, const double* __restrict__ consts,
+                                   double* globals, unsigned long long* rng_state, const double* energies) {
+    RngStream rng;
+    rng.seed = rng_state[0] ^ 0x5851f42d4c957f2dull;
+    rng.c0 = 0xffffffffu; rng.c1 = (uint32_t)rng_state[1]; rng.c2 = (uint32_t)(rng_state[1] >> 32); rng.draw = 0;
+    vm_run<1>(code, len, consts, globals, nullptr, 0, nullptr, &rng, energies);
+    rng_state[1] += 1ull;
+}
+
+// The velocity kernel: v <- s*v + sum_k s_k c_k f_k/m ; [x += c_d v] ; [mvv <- sum(m v.v) ; scalar
+// program].  One thread per owned atom.  The reduction is deterministic: fixed tree inside a block,
+// per-block partials summed in index order by the last block to finish, which then also runs the
+// scalar program that consumes the sum (a Nose-Hoover update), so a thermostat block is ONE launch.
+template <bool MVV>
+__global__ void __launch_bounds__(256) k_vel(int lo, int hi, double* __restrict__ v, double* __restrict__ x, KickArgs a,
+                                             const double* __restrict__ mass, double* globals,
+                                             double* __restrict__ partial, unsigned* __restrict__ ticket,
+                                             const int* __restrict__ code, const double* __restrict__ consts,
+                                             unsigned long long* rng_state, const double* energies) {
     const int i = lo + blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= hi) return;
-    const double im = (double)invm[i];
-    if (im == 0.0) return;
-    double ax = 0, ay = 0, az = 0;
+    double mvv = 0;
+    if (i < hi) {
+        const double m = mass[i];
+        if (m != 0.0) {
+            double vx = v[3*i], vy = v[3*i+1], vz = v[3*i+2];
+            if (a.prescale >= 0) {
+                const double s = globals[a.prescale];
+                vx *= s; vy *= s; vz *= s;
+            }
+            if (a.nterms > 0) {
+                double ax = 0, ay = 0, az = 0;
 #pragma unroll
-    for (int k = 0; k < B2_MAX_KICK_TERMS; k++) {
-        if (k >= a.nterms) break;
-        const double c = globals[a.coef[k]]*(double)a.sign[k];
-        const float4 f = a.f[k][i];
-        ax += c*f.x; ay += c*f.y; az += c*f.z;
+                for (int k = 0; k < B2_MAX_KICK_TERMS; k++) {
+                    if (k < a.nterms) {
+                        const float4 f = a.f[k][i];
+                        const double c = (double)a.sign[k]*globals[a.coef[k]];
+                        ax += c*(double)f.x; ay += c*(double)f.y; az += c*(double)f.z;
+                    }
+                }
+                const double im = 1.0/m;
+                vx += ax*im; vy += ay*im; vz += az*im;
+            }
+            if (a.prescale >= 0 || a.nterms > 0) { v[3*i] = vx; v[3*i+1] = vy; v[3*i+2] = vz; }
+            if (a.drift >= 0) {
+                const double c = globals[a.drift];
+                x[3*i] += c*vx; x[3*i+1] += c*vy; x[3*i+2] += c*vz;
+            }
+            mvv = m*(vx*vx + vy*vy + vz*vz);
+        }
     }
-    double vx = v[3*i] + im*ax, vy = v[3*i+1] + im*ay, vz = v[3*i+2] + im*az;
-    v[3*i] = vx; v[3*i+1] = vy; v[3*i+2] = vz;
-    if (a.drift >= 0) {
-        const double c = globals[a.drift];
-        x[3*i] += c*vx; x[3*i+1] += c*vy; x[3*i+2] += c*vz;
+    if constexpr (MVV) {
+    __shared__ double sh[8];
+    __shared__ bool last;
+    for (int o = 16; o > 0; o >>= 1) mvv += __shfl_xor_sync(FULL, mvv, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mvv;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int k = 0; k < (blockDim.x >> 5); k++) t += sh[k];
+        partial[blockIdx.x] = t;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    __shared__ double red[256];
+    double s = 0;
+    for (int k = threadIdx.x; k < gridDim.x; k += blockDim.x) s += __ldcg(&partial[k]);
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x/2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        globals[a.mvv] = red[0];
+        *ticket = 0;
+        if (a.code_len > 0) run_scalar_program(code, a.code_len, consts, globals, rng_state, energies);
+    }
     }
 }
 
@@ -154,6 +218,173 @@ __global__ void k_scale(int dof_lo, int dof_hi, double* __restrict__ v, const do
     const int d = dof_lo + blockIdx.x*blockDim.x + threadIdx.x;
     if (d >= dof_hi) return;
     v[d] *= globals[gcoef];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused RESPA inner loop (north-star kernel K5): a run of  kick[+drift] / evaluate-bonded-forces
+// ops is ONE launch.  All explicit-list (bonded) terms are intramolecular and molecules are
+// contiguous in the engine's order, so a thread block that owns a chunk of whole molecules can
+// iterate  v += c f/m ; x += c v ; f0 <- bonded(x)  entirely on chip: positions and the inner
+// force live in shared memory, x / v / outer forces are read once and x / v / f0 written once per
+// run instead of once per inner iteration.
+// ---------------------------------------------------------------------------------------------
+#define B2_INNER_MAX_OPS 40
+struct InnerOp {
+    int kind;                        // 0 kick, 1 evaluate the local (bonded) force
+    int nterms;
+    int slot[B2_MAX_KICK_TERMS];
+    int coef[B2_MAX_KICK_TERMS];
+    float sign[B2_MAX_KICK_TERMS];
+    int drift, prescale;
+};
+
+struct InnerArgs {
+    int nops;
+    int local_slot;                  // force slot produced by the local evaluations
+    int write_force;                 // the last local evaluation is valid for the final positions
+    InnerOp op[B2_INNER_MAX_OPS];
+    const float4* f[B2_FSLOTS];
+    int nforces;                     // bonded forces taking part
+    BondArgs a[B2_MAX_BATCH];
+    int arity[B2_MAX_BATCH];
+    int batch_of[B2_INNER_MAX_FORCES];   // bonded-force index -> entry of a[] or -1
+};
+
+__global__ void __launch_bounds__(B2_CHUNK) k_inner(const int* __restrict__ chunk_start,
+                                                    const int* __restrict__ term_ptr,
+                                                    const int2* __restrict__ terms, double* __restrict__ xg,
+                                                    double* __restrict__ vg, const double* __restrict__ mass,
+                                                    const double* __restrict__ globals, float4* __restrict__ fout,
+                                                    const __grid_constant__ InnerArgs A) {
+    __shared__ double xs[3*B2_CHUNK];
+    __shared__ double fs[3*B2_CHUNK];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const int base = chunk_start[c], count = chunk_start[c+1] - base;
+    const int i = base + tid;
+    const bool mine = tid < count;
+    double x[3] = {0, 0, 0}, v[3] = {0, 0, 0}, im = 0;
+    if (mine) {
+        const double m = mass[i];
+        im = m != 0.0 ? 1.0/m : 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { x[k] = xg[3*i+k]; v[k] = vg[3*i+k]; }
+    }
+    const int t0 = term_ptr[c], t1 = term_ptr[c+1];
+    const LocalGeo geo{xs, fs, base};
+    bool have_local = false;
+    for (int q = 0; q < A.nops; q++) {
+        const InnerOp& op = A.op[q];
+        if (op.kind == 0) {
+            if (mine && im != 0.0) {
+                if (op.prescale >= 0) {
+                    const double s = globals[op.prescale];
+                    v[0] *= s; v[1] *= s; v[2] *= s;
+                }
+                double a[3] = {0, 0, 0};
+                for (int k = 0; k < op.nterms; k++) {
+                    const double cf = (double)op.sign[k]*globals[op.coef[k]];
+                    if (have_local && op.slot[k] == A.local_slot) {
+                        a[0] += cf*fs[3*tid]; a[1] += cf*fs[3*tid+1]; a[2] += cf*fs[3*tid+2];
+                    } else {
+                        const float4 f = A.f[op.slot[k]][i];
+                        a[0] += cf*(double)f.x; a[1] += cf*(double)f.y; a[2] += cf*(double)f.z;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++) v[k] += a[k]*im;
+                if (op.drift >= 0) {
+                    const double cd = globals[op.drift];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) x[k] += cd*v[k];
+                }
+            }
+        } else {
+            __syncthreads();           // everybody has consumed the previous local force
+#pragma unroll
+            for (int k = 0; k < 3; k++) { xs[3*tid+k] = x[k]; fs[3*tid+k] = 0.0; }
+            __syncthreads();
+            for (int t = t0 + tid; t < t1; t += B2_CHUNK) {
+                const int2 rec = terms[t];
+                const int b = A.batch_of[rec.x];
+                if (b < 0) continue;
+                double e = 0, w = 0;
+                if (A.arity[b] == 2) term_bond2<true, false>(A.a[b], rec.y, geo, e, w);
+                else if (A.arity[b] == 3) term_angle<true, false>(A.a[b], rec.y, geo, e);
+                else term_torsion<true, false>(A.a[b], rec.y, geo, e);
+            }
+            __syncthreads();
+            have_local = true;
+        }
+    }
+    if (mine) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { xg[3*i+k] = x[k]; vg[3*i+k] = v[k]; }
+        if (A.write_force) fout[i] = make_float4((float)fs[3*tid], (float)fs[3*tid+1], (float)fs[3*tid+2], 0.f);
+    }
+}
+
+// Chunks of whole molecules (<= B2_CHUNK atoms) over the owned range, and for every chunk the
+// bonded terms of its molecules as (bonded-force index, term index) records.
+int inner_prepare(b2_context* ctx) {
+    if (ctx->inner_built) return B2_OK;
+    ctx->inner_built = true;
+    ctx->inner_ok = false;
+    cudaFree(ctx->chunk_start); cudaFree(ctx->chunk_term_ptr); cudaFree(ctx->chunk_terms);
+    ctx->chunk_start = nullptr; ctx->chunk_term_ptr = nullptr; ctx->chunk_terms = nullptr;
+    if ((int)ctx->bonded_forces.size() > B2_INNER_MAX_FORCES || ctx->h_orig.empty()) return B2_OK;
+    const int lo = ctx->a_lo, hi = ctx->a_hi;
+    std::vector<int> start;
+    int s = lo;
+    while (s < hi) {
+        start.push_back(s);
+        int e = s;
+        while (e < hi) {
+            int m_end = e + 1;      // end of the molecule starting at e
+            while (m_end < hi && ctx->h_mol[ctx->h_orig[m_end]] == ctx->h_mol[ctx->h_orig[e]]) m_end++;
+            if (m_end - s > B2_CHUNK) break;
+            e = m_end;
+        }
+        if (e == s) return B2_OK;   // a molecule larger than a chunk: no fused path
+        s = e;
+    }
+    start.push_back(hi);
+    const int nchunks = (int)start.size() - 1;
+    if (nchunks <= 0) return B2_OK;
+    std::vector<int> inv(ctx->n), chunk_of(ctx->n, -1);
+    for (int k = 0; k < ctx->n; k++) inv[ctx->h_orig[k]] = k;
+    for (int c = 0; c < nchunks; c++)
+        for (int k = start[c]; k < start[c+1]; k++) chunk_of[k] = c;
+    std::vector<int> ptr(nchunks + 1, 0);
+    for (size_t f = 0; f < ctx->bonded_forces.size(); f++) {
+        const BondedForce& bf = ctx->bonded_forces[f];
+        for (int t = 0; t < bf.nterms; t++) {
+            const int c = chunk_of[inv[bf.h_atoms[(size_t)bf.arity*t]]];
+            if (c < 0) continue;     // owned by another rank
+            for (int q = 1; q < bf.arity; q++)
+                if (chunk_of[inv[bf.h_atoms[(size_t)bf.arity*t + q]]] != c) return B2_OK;   // not intramolecular
+            ptr[c+1]++;
+        }
+    }
+    for (int c = 0; c < nchunks; c++) ptr[c+1] += ptr[c];
+    std::vector<int2> recs(std::max(1, ptr[nchunks]));
+    std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+    for (size_t f = 0; f < ctx->bonded_forces.size(); f++) {
+        const BondedForce& bf = ctx->bonded_forces[f];
+        for (int t = 0; t < bf.nterms; t++) {
+            const int c = chunk_of[inv[bf.h_atoms[(size_t)bf.arity*t]]];
+            if (c < 0) continue;
+            recs[cur[c]++] = make_int2((int)f, t);
+        }
+    }
+    B2_CUDA(cudaMalloc(&ctx->chunk_start, sizeof(int)*(nchunks + 1)));
+    B2_CUDA(cudaMalloc(&ctx->chunk_term_ptr, sizeof(int)*(nchunks + 1)));
+    B2_CUDA(cudaMalloc(&ctx->chunk_terms, sizeof(int2)*recs.size()));
+    B2_CUDA(cudaMemcpy(ctx->chunk_start, start.data(), sizeof(int)*(nchunks + 1), cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpy(ctx->chunk_term_ptr, ptr.data(), sizeof(int)*(nchunks + 1), cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpy(ctx->chunk_terms, recs.data(), sizeof(int2)*recs.size(), cudaMemcpyHostToDevice));
+    ctx->nchunks = nchunks;
+    ctx->inner_ok = true;
+    return B2_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -191,13 +422,157 @@ int forces_ensure(b2_context* ctx, uint32_t mask, int slot) {
 // ---------------------------------------------------------------------------------------------
 // program execution
 // ---------------------------------------------------------------------------------------------
+static bool bonded_only(const b2_context* ctx, uint32_t mask) {
+    for (const PairForce& pf : ctx->pair_forces)
+        if (mask & (1u << pf.group)) return false;
+    for (const PmeForce& pm : ctx->pme_forces)
+        if (mask & (1u << pm.group)) return false;
+    return true;
+}
+
+static int ensure_partials(b2_context* ctx, int blocks) {
+    if (blocks <= ctx->sum_partial_size) return B2_OK;
+    cudaFree(ctx->sum_partial);
+    ctx->sum_partial = nullptr;
+    B2_CUDA(cudaMalloc(&ctx->sum_partial, sizeof(double)*blocks));
+    ctx->sum_partial_size = blocks;
+    return B2_OK;
+}
+
+static int fill_kick(b2_context* ctx, const b2_op& op, KickArgs& ka) {
+    memset(&ka, 0, sizeof(ka));
+    ka.nterms = op.a;
+    ka.drift = op.c;
+    ka.prescale = op.d;
+    ka.mvv = op.e;
+    ka.code_len = op.g;
+    if (op.a < 0 || op.a > B2_MAX_KICK_TERMS || op.b < 0 || op.b + 3*op.a > (int)ctx->h_code.size())
+        return b2_fail(ctx, B2_ERR_ARG, "malformed kick op");
+    for (int k = 0; k < op.a; k++) {
+        const int slot = ctx->h_code[op.b + 3*k];
+        if (slot < 0 || slot >= B2_FSLOTS || ctx->fbuf[slot] == nullptr)
+            return b2_fail(ctx, B2_ERR_STATE, "kick uses force slot %d before it was evaluated", slot);
+        ka.f[k] = ctx->fbuf[slot];
+        ka.coef[k] = ctx->h_code[op.b + 3*k + 1];
+        ka.sign[k] = (float)ctx->h_code[op.b + 3*k + 2];
+    }
+    return B2_OK;
+}
+
+static int launch_vel(b2_context* ctx, const b2_op& op) {
+    const int T = 256, lo = ctx->a_lo, hi = ctx->a_hi;
+    const int blocks = std::max(1, (hi - lo + T - 1)/T);
+    KickArgs ka;
+    B2_TRY(fill_kick(ctx, op, ka));
+    cudaStream_t s = ctx->stream;
+    // with several ranks the sum must be all-reduced before the scalar program may consume it
+    const bool split = ctx->nranks > 1 && ka.mvv >= 0;
+    if (split) ka.code_len = 0;
+    if (ka.mvv >= 0) {
+        k_vel<true><<<blocks, T, 0, s>>>(lo, hi, ctx->v, ctx->x, ka, ctx->massd, ctx->globals, ctx->sum_partial,
+                                          ctx->ticket, ctx->code + op.f, ctx->consts, ctx->rng_state, ctx->d_energy);
+    } else {
+        k_vel<false><<<blocks, T, 0, s>>>(lo, hi, ctx->v, ctx->x, ka, ctx->massd, ctx->globals, ctx->sum_partial,
+                                           ctx->ticket, ctx->code + op.f, ctx->consts, ctx->rng_state, ctx->d_energy);
+    }
+    B2_LAUNCH_CHECK();
+    if (split) {
+        B2_TRY(dist_allreduce(ctx, ctx->globals + ka.mvv, 1));
+        if (op.g > 0) {
+            k_global<<<1, 64, 0, s>>>(ctx->code + op.f, op.g, ctx->consts, ctx->nconsts, ctx->globals,
+                                       ctx->rng_state, ctx->d_energy);
+            B2_LAUNCH_CHECK();
+        }
+    }
+    if (op.c >= 0) ctx->pos_version++;
+    return B2_OK;
+}
+
+// Try to execute ops[k...] as one fused inner-loop launch.  Returns the number of ops consumed
+// (0: not applicable, run ops[k] the ordinary way).
+static int try_fused_run(b2_context* ctx, size_t k, int* consumed) {
+    *consumed = 0;
+    static const bool allowed = getenv("B2_NO_FUSED_INNER") == nullptr;
+    if (!allowed || !ctx->inner_ok || ctx->profiling) return B2_OK;
+    const std::vector<b2_op>& ops = ctx->ops;
+    if (ops[k].kind != B2_OP_KICK || ops[k].e >= 0) return B2_OK;
+    // the run: KICK (no reduction) and bonded-only EVAL ops, all evaluations into the same slot
+    InnerArgs A;
+    A.nops = 0; A.local_slot = -1; A.write_force = 0;
+    uint32_t local_mask = 0;
+    long long version = ctx->pos_version;
+    long long local_valid = -1;          // position version the local force belongs to
+    int evals = 0;
+    size_t q = k;
+    for (; q < ops.size() && A.nops < B2_INNER_MAX_OPS; q++) {
+        const b2_op& op = ops[q];
+        if (op.kind == B2_OP_KICK) {
+            if (op.e >= 0) break;        // carries a reduction: ordinary velocity kernel
+            KickArgs ka;
+            B2_TRY(fill_kick(ctx, op, ka));
+            InnerOp& io = A.op[A.nops];
+            io.kind = 0; io.nterms = ka.nterms; io.drift = ka.drift; io.prescale = ka.prescale;
+            bool ok = true;
+            for (int t = 0; t < ka.nterms; t++) {
+                io.slot[t] = ctx->h_code[op.b + 3*t]; io.coef[t] = ka.coef[t]; io.sign[t] = ka.sign[t];
+                // every term must be valid at this point: locally (the kernel then reads shared
+                // memory) or in its global buffer
+                const bool local = io.slot[t] == A.local_slot && local_valid == version;
+                if (!local && (io.slot[t] == A.local_slot || ctx->fvalid[io.slot[t]] != version)) ok = false;
+            }
+            if (!ok) break;
+            A.nops++;
+            if (op.c >= 0) version++;
+        } else if (op.kind == B2_OP_EVAL) {
+            const uint32_t mask = (uint32_t)op.a;
+            const bool valid = (op.b == A.local_slot && local_valid == version) ||
+                               (op.b != A.local_slot && ctx->fbuf[op.b] && ctx->fvalid[op.b] == version);
+            if (valid) continue;         // nothing to do; the op stays inside the run
+            if (!bonded_only(ctx, mask)) break;
+            if (A.local_slot >= 0 && (op.b != A.local_slot || mask != local_mask)) break;
+            if (ctx->fbuf[op.b] == nullptr) break;    // first use allocates (ordinary path)
+            A.local_slot = op.b; local_mask = mask;
+            A.op[A.nops].kind = 1;
+            A.nops++;
+            local_valid = version;
+            evals++;
+        } else {
+            break;
+        }
+    }
+    if (evals == 0) return B2_OK;        // a lone kick: the ordinary velocity kernel
+    // bonded forces of the local mask
+    A.nforces = 0;
+    for (int f = 0; f < B2_INNER_MAX_FORCES; f++) A.batch_of[f] = -1;
+    for (size_t f = 0; f < ctx->bonded_forces.size(); f++) {
+        const BondedForce& bf = ctx->bonded_forces[f];
+        if (!(local_mask & (1u << bf.group)) || bf.nterms == 0) continue;
+        if ((bf.family == B2_BOND_CUSTOM || bf.family == B2_ANGLE_CUSTOM) && bf.ncode_de == 0) continue;
+        if (A.nforces == B2_MAX_BATCH) return B2_OK;
+        A.a[A.nforces] = bonded_make_args(ctx, bf);
+        A.arity[A.nforces] = bf.arity;
+        A.batch_of[f] = A.nforces++;
+    }
+    for (int g = 0; g < B2_FSLOTS; g++) A.f[g] = ctx->fbuf[g];
+    A.write_force = local_valid == version ? 1 : 0;
+    k_inner<<<ctx->nchunks, B2_CHUNK, 0, ctx->stream>>>(ctx->chunk_start, ctx->chunk_term_ptr, ctx->chunk_terms,
+                                                        ctx->x, ctx->v, ctx->massd, ctx->globals,
+                                                        ctx->fbuf[A.local_slot], A);
+    B2_LAUNCH_CHECK();
+    ctx->pos_version = version;
+    if (A.write_force) ctx->fvalid[A.local_slot] = version;
+    *consumed = (int)(q - k);
+    return B2_OK;
+}
+
 static int run_one_step(b2_context* ctx) {
     const int T = 256;
     const int lo = ctx->a_lo, hi = ctx->a_hi, n = hi - lo, ndof = 3*n;   // owned range
     cudaStream_t s = ctx->stream;
     k_step_begin<<<1, 1, 0, s>>>(ctx->rng_state);
     B2_LAUNCH_CHECK();
-    for (const b2_op& op : ctx->ops) {
+    for (size_t k = 0; k < ctx->ops.size(); k++) {
+        const b2_op& op = ctx->ops[k];
         switch (op.kind) {
         case B2_OP_EVAL:
             B2_TRY(forces_ensure(ctx, (uint32_t)op.a, op.b));
@@ -231,23 +606,10 @@ static int run_one_step(b2_context* ctx) {
             B2_LAUNCH_CHECK();
             break;
         case B2_OP_KICK: {
-            KickArgs ka;
-            ka.nterms = op.a;
-            ka.drift = op.c;
-            if (op.a < 1 || op.a > B2_MAX_KICK_TERMS || op.b < 0 || op.b + 3*op.a > (int)ctx->h_code.size())
-                return b2_fail(ctx, B2_ERR_ARG, "malformed kick op");
-            for (int k = 0; k < B2_MAX_KICK_TERMS; k++) {
-                const bool live = k < op.a;
-                const int slot = live ? ctx->h_code[op.b + 3*k] : 0;
-                if (live && (slot < 0 || slot >= B2_FSLOTS || ctx->fbuf[slot] == nullptr))
-                    return b2_fail(ctx, B2_ERR_STATE, "kick uses force slot %d before it was evaluated", slot);
-                ka.f[k] = live ? ctx->fbuf[slot] : nullptr;
-                ka.coef[k] = live ? ctx->h_code[op.b + 3*k + 1] : 0;
-                ka.sign[k] = live ? (float)ctx->h_code[op.b + 3*k + 2] : 0.f;
-            }
-            k_kick<<<(n + T - 1)/T, T, 0, s>>>(lo, hi, ctx->v, ctx->x, ka, ctx->invm, ctx->globals);
-            B2_LAUNCH_CHECK();
-            if (op.c >= 0) ctx->pos_version++;
+            int consumed = 0;
+            B2_TRY(try_fused_run(ctx, k, &consumed));
+            if (consumed > 0) { k += consumed - 1; break; }
+            B2_TRY(launch_vel(ctx, op));
             break;
         }
         case B2_OP_DRIFT:
@@ -292,6 +654,8 @@ int program_run(b2_context* ctx, int nsteps) {
     // slot it assumed valid at entry is valid now; otherwise one step runs eagerly, which
     // restores the steady-state pattern.  The first step always runs eagerly (it also performs
     // all lazy allocations, which are illegal during capture).
+    B2_TRY(inner_prepare(ctx));
+    B2_TRY(ensure_partials(ctx, (ctx->a_hi - ctx->a_lo + 255)/256 + 1));
     static const bool graph_allowed = getenv("B2_NO_GRAPH") == nullptr;
     const bool use_graph = graph_allowed && !ctx->profiling;
     for (int done = 0; done < nsteps; done++) {

@@ -585,6 +585,8 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
             P.bc.emit('STOREG', slot)
         P.ops.insert(0, [OP_GLOBAL, 0, start, (len(P.bc.code) - start)//2, 0, 0, 0, 0])
     _fuse_kicks(P)
+    if fast:
+        _fuse_velocity_ops(P)
     return P
 
 
@@ -607,7 +609,7 @@ def _fuse_kicks(P):
                 P.bc.code += [slot, coef, sign]
             if len(P.bc.code) % 2:
                 P.bc.code.append(0)
-            out.append([OP_KICK, len(terms), offset, drift, 0, 0, 0, 0])
+            out.append([OP_KICK, len(terms), offset, drift, -1, -1, 0, 0])
             pending = None
 
     for op in P.ops:
@@ -631,6 +633,75 @@ def _fuse_kicks(P):
             flush()
             out.append(op)
     flush()
+    P.ops = out
+
+
+def _fuse_velocity_ops(P):
+    """Second peephole: everything that only rescales / kicks velocities and reduces ``m*v*v``
+    becomes part of ONE velocity kernel (OP_KICK with optional pre-scale, kick terms, drift,
+    mvv reduction and the scalar program that consumes the sum):
+
+        SCALE s ; [EVAL|UPDATE]* ; KICK        ->  KICK(prescale=s)    (evaluations touch neither v nor globals)
+        SCALE s ; SUM mvv                      ->  KICK(0 terms, prescale=s, mvv)
+        KICK ; SUM mvv                         ->  KICK(mvv)
+        KICK(mvv) ; GLOBAL                     ->  KICK(mvv, scalar program)
+
+    A Nose-Hoover block (sum, scalar update, scale) thereby costs one launch instead of four."""
+    out = []
+    held = None          # a SCALE waiting for the next velocity op
+    passed = []          # EVAL / UPDATE ops that overtook the held scale
+
+    def bare(prescale=-1):
+        return [OP_KICK, 0, 0, -1, prescale, -1, 0, 0]
+
+    def release():
+        nonlocal held, passed
+        if held is not None:
+            out.append(bare(held))
+            held = None
+        out.extend(passed)
+        passed = []
+
+    for op in P.ops:
+        kind = op[0]
+        if kind == OP_SCALE:
+            release()
+            held = op[1]
+        elif kind in (OP_EVAL, OP_UPDATE_STATE):
+            if held is not None:
+                passed.append(op)
+            else:
+                out.append(op)
+        elif kind == OP_KICK:
+            if held is not None:
+                out.extend(passed)
+                passed = []
+                op = list(op)
+                op[4] = held
+                held = None
+            out.append(list(op))
+        elif kind == OP_SUM and op[4] == 1:
+            if held is not None and not passed:
+                out.append(bare(held))
+                held = None
+            else:
+                release()
+            if out and out[-1][0] == OP_KICK and out[-1][5] < 0:
+                out[-1][5] = op[1]
+            else:
+                k = bare()
+                k[5] = op[1]
+                out.append(k)
+        elif kind == OP_GLOBAL:
+            release()
+            if out and out[-1][0] == OP_KICK and out[-1][5] >= 0 and out[-1][7] == 0:
+                out[-1][6], out[-1][7] = op[2], op[3]
+            else:
+                out.append(op)
+        else:
+            release()
+            out.append(op)
+    release()
     P.ops = out
 
 

@@ -53,12 +53,34 @@ def test_respa_program_lowering():
     assert kinds.count(lowering.OP_GLOBAL) == 1          # only the per-step coefficient prologue
 
 
+def test_nose_hoover_block_is_one_velocity_kernel():
+    dof = 4605
+    nh = atomsmm.NoseHooverPropagator(300*K, dof, 100*fs)
+    integrator = atomsmm.TrotterSuzukiPropagator(atomsmm.RespaPropagator([4, 2, 1]),
+                                                 atomsmm.SuzukiYoshidaPropagator(nh, 3)).integrator(4*fs)
+    program = lowering.lower_program(integrator, 0b111)
+    kinds = [op[0] for op in program.ops]
+    # sum(m v v) + scalar update + rescaling fold into the velocity kernels: no SUM / SCALE ops left,
+    # and the only stand-alone scalar program is the coefficient prologue
+    assert kinds.count(lowering.OP_SUM) == 0 and kinds.count(lowering.OP_SCALE) == 0
+    assert kinds.count(lowering.OP_GLOBAL) == 1
+    reductions = [op for op in program.ops if op[0] == lowering.OP_KICK and op[5] >= 0]
+    assert len(reductions) == 6 and all(op[7] > 0 for op in reductions)
+    assert kinds.count(lowering.OP_KICK) == 9 + 6      # 9 RESPA kicks (one carries a reduction) + 5 bare + final scale
+
+
 def test_bussi_program_keeps_rejection_loop_on_device():
     thermostat = atomsmm.VelocityRescalingPropagator(300*K, 4605, 0.1*ps)
     integrator = atomsmm.TrotterSuzukiPropagator(atomsmm.RespaPropagator([2, 1]), thermostat).integrator(1*fs)
     program = lowering.lower_program(integrator, 0b11)
     ops = [op[0] for op in program.ops]
-    assert lowering.OP_PERDOF not in ops and ops.count(lowering.OP_SCALE) == 2
+    # the two velocity rescalings ride on velocity kernels (pre-scale of a kick / bare scale op)
+    assert lowering.OP_PERDOF not in ops and ops.count(lowering.OP_SCALE) == 0
+    assert sum(1 for op in program.ops if op[0] == lowering.OP_KICK and op[4] >= 0) == 2
+    unfused = lowering.lower_program(atomsmm.TrotterSuzukiPropagator(
+        atomsmm.RespaPropagator([2, 1]), atomsmm.VelocityRescalingPropagator(300*K, 4605, 0.1*ps)).integrator(1*fs),
+        0b11, fast=False)
+    assert lowering.OP_KICK not in [op[0] for op in unfused.ops]
     assert 33 in program.bc.code[::2]                    # VM_JMPZ: while/if compiled into the scalar VM
 
 
