@@ -127,15 +127,15 @@ extern "C" int b2_destroy(b2_context* ctx) {
     cudaStreamSynchronize(ctx->stream);
     program_release(ctx);
     dist_release(ctx);
-    cudaFree(ctx->x); cudaFree(ctx->v); cudaFree(ctx->xref); cudaFree(ctx->xsort); cudaFree(ctx->pos4);
+    cudaFree(ctx->x); cudaFree(ctx->v); cudaFree(ctx->xref); cudaFree(ctx->xsort);
     for (int s = 0; s < B2_MAX_SETS; s++) { cudaFree(ctx->par[s]); cudaFree(ctx->pard[s]); }
     cudaFree(ctx->massd); cudaFree(ctx->invm); cudaFree(ctx->orig); cudaFree(ctx->inv); cudaFree(ctx->exmask);
     cudaFree(ctx->excl_ptr); cudaFree(ctx->excl_idx); cudaFree(ctx->scratch3);
     for (int g = 0; g < B2_FSLOTS; g++) cudaFree(ctx->fbuf[g]);
     for (double* p : ctx->perdof) cudaFree(p);
     for (int k = 0; k < B2_MAX_LISTS; k++) { cudaFree(ctx->lists[k].entries); cudaFree(ctx->lists[k].counts); cudaFree(ctx->lists[k].gflags); }
-    cudaFree(ctx->cell_count); cudaFree(ctx->cell_start); cudaFree(ctx->cell_atoms); cudaFree(ctx->cell_of);
-    cudaFree(ctx->cpos); cudaFree(ctx->corig);
+    cudaFree(ctx->cell_count); cudaFree(ctx->cell_start); cudaFree(ctx->cell_groups); cudaFree(ctx->gcell);
+    cudaFree(ctx->gcen); cudaFree(ctx->ghalf); cudaFree(ctx->cgc); cudaFree(ctx->cgh); cudaFree(ctx->prel); cudaFree(ctx->fat_list);
     cudaFree(ctx->nl_flags); cudaFree(ctx->d_energy); cudaFree(ctx->code); cudaFree(ctx->consts);
     cudaFree(ctx->globals); cudaFree(ctx->sum_partial); cudaFree(ctx->rng_state);
     cudaFree(ctx->band_pairs); cudaFree(ctx->band_count); cudaFree(ctx->ticket);
@@ -200,7 +200,6 @@ extern "C" int b2_set_particles(b2_context* ctx, int n, const double* mass, cons
     B2_CUDA(cudaMalloc(&ctx->xref, sizeof(double)*3*n));
     B2_CUDA(cudaMalloc(&ctx->xsort, sizeof(double)*3*n));
     B2_CUDA(cudaMalloc(&ctx->scratch3, sizeof(double)*3*n));
-    B2_CUDA(cudaMalloc(&ctx->pos4, sizeof(float4)*n));
     B2_CUDA(cudaMalloc(&ctx->massd, sizeof(double)*n));
     B2_CUDA(cudaMalloc(&ctx->invm, sizeof(float)*n));
     B2_CUDA(cudaMalloc(&ctx->orig, sizeof(int)*n));
@@ -392,14 +391,28 @@ extern "C" int b2_set_skin(b2_context* ctx, double skin) {
 // spatial ordering (host side; runs when positions are set for the first time or have moved far
 // from the configuration the current order was computed for)
 // ---------------------------------------------------------------------------------------------
-static inline uint64_t spread21(uint64_t v) {
-    v &= 0x1fffff;
-    v = (v | v << 32) & 0x1f00000000ffffull;
-    v = (v | v << 16) & 0x1f0000ff0000ffull;
-    v = (v | v << 8) & 0x100f00f00f00f00full;
-    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
-    v = (v | v << 2) & 0x1249249249249249ull;
-    return v;
+// Hilbert-curve index of a cell (Skilling's transpose algorithm).  Unlike the Morton (Z) curve
+// the Hilbert curve has no jumps: consecutive keys are always face-adjacent cells, so every run of
+// consecutive molecules -- in particular every 8-atom i-group -- is spatially compact.
+static uint64_t hilbert_key(const uint32_t cell[3], int bits) {
+    uint32_t X[3] = {cell[0], cell[1], cell[2]};
+    const uint32_t M = 1u << (bits - 1);
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+        for (int i = 0; i < 3; i++) {
+            if (X[i] & Q) X[0] ^= P;
+            else { const uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    for (int i = 1; i < 3; i++) X[i] ^= X[i-1];
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1;
+    for (int i = 0; i < 3; i++) X[i] ^= t;
+    uint64_t key = 0;
+    for (int q = bits - 1; q >= 0; q--)
+        for (int i = 0; i < 3; i++) key = (key << 1) | ((X[i] >> q) & 1u);
+    return key;
 }
 
 static int compute_order(b2_context* ctx, const std::vector<double>& hx) {
@@ -414,18 +427,21 @@ static int compute_order(b2_context* ctx, const std::vector<double>& hx) {
     }
     std::vector<std::pair<uint64_t, int>> keys;
     keys.reserve(nmol);
+    // curve resolution: cells of 0.28-0.57 nm along the longest box edge
+    const double longest = std::max(ctx->box[0], std::max(ctx->box[1], ctx->box[2]));
+    int bits = 1;
+    while (bits < 20 && longest/(double)(1u << bits) > 0.57) bits++;
     for (int m = 0; m < nmol; m++) {
         if (mols[m].empty()) continue;
-        uint64_t c[3];
+        uint32_t c[3];
         const int a = mols[m][0];
         for (int d = 0; d < 3; d++) {
             const double L = ctx->box[d];
-            double w = hx[3*a+d] - L*floor(hx[3*a+d]/L);
-            const int nc = std::max(1, std::min(1 << 20, (int)floor(L/0.4)));
-            int k = (int)(w/L*nc);
-            c[d] = (uint64_t)std::min(std::max(k, 0), nc - 1);
+            const double w = hx[3*a+d] - L*floor(hx[3*a+d]/L);
+            const int k = (int)(w/L*(double)(1u << bits));      // the box maps onto the full 2^bits cube
+            c[d] = (uint32_t)std::min(std::max(k, 0), (1 << bits) - 1);
         }
-        keys.emplace_back(spread21(c[0]) | (spread21(c[1]) << 1) | (spread21(c[2]) << 2), m);
+        keys.emplace_back(hilbert_key(c, bits), m);
     }
     std::stable_sort(keys.begin(), keys.end());
     ctx->h_orig.clear();

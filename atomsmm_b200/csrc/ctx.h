@@ -6,7 +6,7 @@
 //
 //   x, v        double [n][3]   master state, never wrapped (molecules stay whole)
 //   xref        double [n][3]   positions at the last neighbour-list build (skin test)
-//   pos4        float4 [n]      periodic image of x in [0,L) rounded to fp32 (w unused)
+//   prel        float4 [n]      position relative to the centre of the atom's 8-atom group (list build)
 //   par[s]      float4 [n]      per parameter set: {charge, sigma/2, sqrt(epsilon), 0}
 //   massd       double [n]      mass;  invm: float [n] 1/mass (0 for massless)
 //   fbuf[g]     float4 [n]      force of group g (slot 32 = all groups, "f")
@@ -99,7 +99,6 @@ struct b2_context {
     bool have_order = false, have_positions = false;
     std::vector<int> h_orig;                      // sorted -> caller index
     double *x = nullptr, *v = nullptr, *xref = nullptr, *xsort = nullptr;
-    float4* pos4 = nullptr;
     float4* par[B2_MAX_SETS] = {nullptr};
     double* pard[B2_MAX_SETS] = {nullptr};        // double [n][3]: charge, sigma, epsilon
     double* massd = nullptr;
@@ -118,9 +117,12 @@ struct b2_context {
     NList lists[B2_MAX_LISTS];
     int ncell[3] = {0, 0, 0}, ncells = 0;
     double cellsize[3] = {0, 0, 0};
-    int *cell_count = nullptr, *cell_start = nullptr, *cell_atoms = nullptr, *cell_of = nullptr;
-    float4* cpos = nullptr;      // positions in cell order (w = atom index), for the list build
-    int* corig = nullptr;        // caller index in cell order
+    int *cell_count = nullptr, *cell_start = nullptr;   // cells of GROUP centres
+    int *cell_groups = nullptr, *gcell = nullptr;      // group ids in cell order; cell of every group (-1: fat)
+    int* fat_list = nullptr;                           // groups too extended for the cells, in index order
+    float4 *gcen = nullptr, *ghalf = nullptr;          // per group: box centre (wrapped), half extents
+    float4 *cgc = nullptr, *cgh = nullptr;             // the same in cell order (w of cgc = group id)
+    float4* prel = nullptr;                            // per atom: position relative to its group's centre
     int* nl_flags = nullptr;     // [0] rebuild needed, [1] overflow, [2] rebuild counter, [3] max count
     bool lists_built = false;
 

@@ -43,42 +43,99 @@ __device__ __forceinline__ double wrap1(double x, double L, double invL) {
     return w >= L ? w - L : w;
 }
 
-// K8: skin test + fp32 wrapped copy used by the list build (the pair kernels read the float64
-// master positions directly), one pass over x.
-__global__ void k_wrap_check(int n, const double* __restrict__ x, const double* __restrict__ xref,
-                             float4* __restrict__ pos4, Grid g, double limit2, int* flags, int have_ref) {
+__device__ __forceinline__ bool is_excluded(int oi, int oj, unsigned long long mask, const int* excl_ptr,
+                                            const int* excl_idx) {
+    int d = oj - oi;
+    if (d >= -32 && d < 32) return (mask >> (d + 32)) & 1ull;
+    if (excl_ptr) {
+        for (int k = excl_ptr[oi]; k < excl_ptr[oi+1]; k++)
+            if (excl_idx[k] == oj) return true;
+    }
+    return false;
+}
+
+// K8: skin test, one pass over x and xref (48 B/atom), before every pair-force evaluation.
+__global__ void k_skin_check(int n, const double* __restrict__ x, const double* __restrict__ xref, double limit2,
+                             int* flags, int have_ref) {
     int i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double px = x[3*i], py = x[3*i+1], pz = x[3*i+2];
-    pos4[i] = make_float4((float)wrap1(px, g.box[0], g.inv[0]), (float)wrap1(py, g.box[1], g.inv[1]),
-                          (float)wrap1(pz, g.box[2], g.inv[2]), 0.f);
     if (have_ref) {
-        double dx = px - xref[3*i], dy = py - xref[3*i+1], dz = pz - xref[3*i+2];
+        double dx = x[3*i] - xref[3*i], dy = x[3*i+1] - xref[3*i+1], dz = x[3*i+2] - xref[3*i+2];
         if (dx*dx + dy*dy + dz*dz > limit2) flags[0] = 1;
     } else {
         flags[0] = 1;
     }
 }
 
-__global__ void k_cell_count(int n, const double* __restrict__ x, Grid g, int* cell_of, int* cell_count,
-                             const int* flags) {
+// Geometry of every 8-atom group (8 lanes per group): bounding box of the group's atoms unwrapped
+// around its first atom -> centre (wrapped into the box, fp32), half extents, atom positions
+// RELATIVE to the centre (fp32 of a < 1 nm vector: 6e-8 nm regardless of the box size), and the
+// cell of the centre.  Groups, not atoms, are binned: 8x less sorting work.
+__global__ void k_group_geom(int n, int ngroups, const double* __restrict__ x, Grid g, float4* __restrict__ prel,
+                             float4* __restrict__ gcen, float4* __restrict__ ghalf, int* __restrict__ gcell,
+                             int* cell_count, int* hmax_bits, float fat_limit, const int* flags) {
     if (!flags[0]) return;
-    int i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int c[3];
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    const int grp = t >> 3, a = t & 7;
+    const bool live = grp < ngroups;
+    const int i = min(min(grp, ngroups - 1)*B2_GROUP + a, n - 1);    // padding duplicates the last atom
+    const int lane = threadIdx.x & 31, seg = lane & ~7;
+    double u[3];
+    float lo[3], hi[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) {
-        double w = wrap1(x[3*i+d], g.box[d], g.inv[d]);
-        int k = (int)(w*g.cs_inv[d]);
-        c[d] = min(max(k, 0), g.nc[d]-1);
+        const double p = x[3*i+d];
+        const double r0 = __shfl_sync(FULL, p, seg);
+        double dd = p - r0;
+        dd -= g.box[d]*rint(dd*g.inv[d]);
+        u[d] = dd;
+        float l = (float)dd, h = (float)dd;
+        // round outwards so that the fp32 box contains the fp64 point
+        l = l > dd ? nextafterf(l, -1e30f) : l;
+        h = h < dd ? nextafterf(h, 1e30f) : h;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            l = fminf(l, __shfl_xor_sync(FULL, l, o));
+            h = fmaxf(h, __shfl_xor_sync(FULL, h, o));
+        }
+        lo[d] = l; hi[d] = h;
     }
-    int cell = (c[2]*g.nc[1] + c[1])*g.nc[0] + c[0];
-    cell_of[i] = cell;
-    atomicAdd(&cell_count[cell], 1);
+    double r0[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) r0[d] = __shfl_sync(FULL, x[3*i+d], seg);
+    float c[3], h[3];
+    int cell[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const double cu = 0.5*((double)lo[d] + (double)hi[d]);
+        h[d] = 0.5f*(hi[d] - lo[d]) + 2e-6f;
+        u[d] -= cu;
+        const double cw = wrap1(r0[d] + cu, g.box[d], g.inv[d]);
+        c[d] = (float)cw;
+        cell[d] = min(max((int)(cw*g.cs_inv[d]), 0), g.nc[d] - 1);
+    }
+    if (!live) return;
+    prel[grp*B2_GROUP + a] = make_float4((float)u[0], (float)u[1], (float)u[2], 0.f);
+    if (a == 0) {
+        gcen[grp] = make_float4(c[0], c[1], c[2], 0.f);
+        ghalf[grp] = make_float4(h[0], h[1], h[2], 0.f);
+        // "fat" groups (atoms of molecules that have drifted apart, or a large molecule) stay out of
+        // the cells: every i-group tests them directly, so they do not inflate everybody's search region
+        if (fmaxf(h[0], fmaxf(h[1], h[2])) > fat_limit) {
+            gcell[grp] = -1;
+        } else {
+            const int cidx = (cell[2]*g.nc[1] + cell[1])*g.nc[0] + cell[0];
+            gcell[grp] = cidx;
+            atomicAdd(&cell_count[cidx], 1);
+#pragma unroll
+            for (int d = 0; d < 3; d++) atomicMax(&hmax_bits[d], __float_as_int(h[d]));   // h > 0: int order = float order
+        }
+    }
 }
 
 // single-block exclusive scan (ncells <= a few 1e5); also resets the fill cursors
-__global__ void k_cell_scan(int ncells, int* cell_count, int* cell_start, const int* flags) {
+__global__ void k_cell_scan(int ncells, int* cell_count, int* cell_start, int ngroups, const int* __restrict__ gcell,
+                            int* __restrict__ fat_list, int* flags) {
     if (!flags[0]) return;
     __shared__ int part[1024];
     int t = threadIdx.x;
@@ -102,98 +159,113 @@ __global__ void k_cell_scan(int ncells, int* cell_count, int* cell_start, const 
         run += c;
     }
     if (t == blockDim.x - 1) cell_start[ncells] = part[t];
+    // the fat groups, compacted in index order (deterministic)
+    __shared__ int wsum[32];
+    __shared__ int base;
+    if (t == 0) base = 0;
+    __syncthreads();
+    for (int g0 = 0; g0 < ngroups; g0 += blockDim.x) {
+        const int grp = g0 + t;
+        const bool fat = grp < ngroups && gcell[grp] < 0;
+        const unsigned ballot = __ballot_sync(FULL, fat);
+        const int lane = t & 31, w = t >> 5;
+        if (lane == 0) wsum[w] = __popc(ballot);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) {
+            if (k < w) before += wsum[k];
+            total += wsum[k];
+        }
+        if (fat) fat_list[base + before + __popc(ballot & ((1u << lane) - 1u))] = grp;
+        __syncthreads();
+        if (t == 0) base += total;
+        __syncthreads();
+    }
+    if (t == 0) flags[8] = base;
 }
 
-__global__ void k_cell_fill(int n, const int* cell_of, const int* cell_start, int* cell_count, int* cell_atoms,
+__global__ void k_cell_fill(int ngroups, const int* gcell, const int* cell_start, int* cell_count, int* cell_groups,
                             const int* flags) {
     if (!flags[0]) return;
-    int i = blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int c = cell_of[i];
+    int grp = blockIdx.x*blockDim.x + threadIdx.x;
+    if (grp >= ngroups) return;
+    int c = gcell[grp];
+    if (c < 0) return;
     int slot = atomicAdd(&cell_count[c], 1);
-    cell_atoms[cell_start[c] + slot] = i;
+    cell_groups[cell_start[c] + slot] = grp;
 }
 
-// deterministic order inside each cell (atomics above fill in arbitrary order)
-__global__ void k_cell_sort(int ncells, const int* cell_start, int* cell_atoms, const int* flags) {
+// deterministic order inside each cell (the atomics above fill in arbitrary order), then the
+// cell-ordered copies of the group geometry that the list build streams; resets the counters
+__global__ void k_cell_sort_pack(int ncells, const int* __restrict__ cell_start, int* cell_groups, int* cell_count,
+                                 const float4* __restrict__ gcen, const float4* __restrict__ ghalf,
+                                 float4* __restrict__ cgc, float4* __restrict__ cgh, const int* flags) {
     if (!flags[0]) return;
     int c = blockIdx.x*blockDim.x + threadIdx.x;
     if (c >= ncells) return;
+    cell_count[c] = 0;          // ready for the next rebuild
     int lo = cell_start[c], hi = cell_start[c+1];
     for (int a = lo + 1; a < hi; a++) {
-        int key = cell_atoms[a];
+        int key = cell_groups[a];
         int b = a - 1;
-        while (b >= lo && cell_atoms[b] > key) { cell_atoms[b+1] = cell_atoms[b]; b--; }
-        cell_atoms[b+1] = key;
+        while (b >= lo && cell_groups[b] > key) { cell_groups[b+1] = cell_groups[b]; b--; }
+        cell_groups[b+1] = key;
+    }
+    for (int a = lo; a < hi; a++) {
+        const int grp = cell_groups[a];
+        float4 cc = gcen[grp];
+        cc.w = __int_as_float(grp);
+        cgc[a] = cc;
+        cgh[a] = ghalf[grp];
     }
 }
 
-// cell-ordered copies so that the list build streams candidates with coalesced loads
-__global__ void k_cell_pack(int n, const int* __restrict__ cell_atoms, const float4* __restrict__ pos4,
-                            const int* __restrict__ orig, float4* __restrict__ cpos, int* __restrict__ corig,
-                            const int* flags) {
-    if (!flags[0]) return;
-    int k = blockIdx.x*blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const int j = cell_atoms[k];
-    float4 p = pos4[j];
-    p.w = __int_as_float(j);
-    cpos[k] = p;
-    corig[k] = orig[j];
-}
-
-__device__ __forceinline__ bool is_excluded(int oi, int oj, unsigned long long mask, const int* excl_ptr,
-                                            const int* excl_idx) {
-    int d = oj - oi;
-    if (d >= -32 && d < 32) return (mask >> (d + 32)) & 1ull;
-    if (excl_ptr) {
-        for (int k = excl_ptr[oi]; k < excl_ptr[oi+1]; k++)
-            if (excl_idx[k] == oj) return true;
-    }
-    return false;
-}
-
-// K2: one warp per i-group.  Membership is tested in fp32 on wrapped coordinates with a safety
-// margin (the list only has to be a superset of the pairs within cutoff+skin; the interacting set is
-// decided exactly by the pair kernels).  Cells farther than the list radius from the group's
-// bounding box are culled before their atoms are touched.
+// K2: one warp per i-group, two levels.
+//  (1) group level: walk the cells whose group centres can matter (the i-group's box grown by the list
+//      radius and the largest half extent of any group), one candidate j-GROUP per lane, box-box
+//      distance test -> survivors go to a small per-warp queue;
+//  (2) atom level: four queued j-groups (32 atoms) per sweep, each lane tests its j-atom against the 8
+//      i-atoms in fp32 on centre-relative coordinates with a safety margin (the list only has to be
+//      a superset of the pairs within cutoff+skin; the interacting set is decided exactly by the pair
+//      kernels), resolves the exclusion mask and appends to each list by ballot.
 #define NL_MARGIN 3e-4f
-__global__ void __launch_bounds__(128) k_build_lists(int n, int g_lo, int ngroups, const float4* __restrict__ pos4, Grid g,
-                                                    const int* __restrict__ cell_start,
-                                                    const float4* __restrict__ cpos,
-                                                    const int* __restrict__ corig,
-                                                    const int* __restrict__ orig,
-                                                    const unsigned long long* __restrict__ exmask,
-                                                    const int* __restrict__ excl_ptr,
-                                                    const int* __restrict__ excl_idx, BuildArgs a, int* flags) {
+#define NL_WARPS 4
+#define NL_QUEUE 40
+__global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, int ngroups, Grid g,
+                                                             const int* __restrict__ cell_start,
+                                                             const float4* __restrict__ cgc,
+                                                             const float4* __restrict__ cgh,
+                                                             const float4* __restrict__ gcen,
+                                                             const float4* __restrict__ ghalf,
+                                                             const float4* __restrict__ prel,
+                                                             const int* __restrict__ hmax_bits,
+                                                             const int* __restrict__ fat_list,
+                                                             const int* __restrict__ orig,
+                                                             const unsigned long long* __restrict__ exmask,
+                                                             const int* __restrict__ excl_ptr,
+                                                             const int* __restrict__ excl_idx, BuildArgs a, int* flags) {
     if (!flags[0]) return;
     const int warp = g_lo + ((blockIdx.x*blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     if (warp >= ngroups) return;
-    __shared__ float sxi[4][B2_GROUP][3];
-    __shared__ int soi[4][B2_GROUP];
-    __shared__ unsigned long long smask[4][B2_GROUP];
+    __shared__ float sxi[NL_WARPS][B2_GROUP][3];
+    __shared__ int soi[NL_WARPS][B2_GROUP];
+    __shared__ unsigned long long smask[NL_WARPS][B2_GROUP];
+    __shared__ float4 queue[NL_WARPS][NL_QUEUE];
     const int i0 = warp*B2_GROUP;
-    const float bx = (float)g.box[0], by = (float)g.box[1], bz = (float)g.box[2];
-    const float ibx = (float)g.inv[0], iby = (float)g.inv[1], ibz = (float)g.inv[2];
-    const float4 r0 = pos4[i0];
+    const float box[3] = {(float)g.box[0], (float)g.box[1], (float)g.box[2]};
+    const float ibox[3] = {(float)g.inv[0], (float)g.inv[1], (float)g.inv[2]};
     if (lane < B2_GROUP) {
-        const int i = min(i0 + lane, n - 1);
-        const float4 p = pos4[i];
-        float dx = p.x - r0.x, dy = p.y - r0.y, dz = p.z - r0.z;      // unwrap relative to atom 0
-        dx -= bx*rintf(dx*ibx); dy -= by*rintf(dy*iby); dz -= bz*rintf(dz*ibz);
-        sxi[wib][lane][0] = r0.x + dx; sxi[wib][lane][1] = r0.y + dy; sxi[wib][lane][2] = r0.z + dz;
-        soi[wib][lane] = (i0 + lane < n) ? orig[i] : -1;
-        smask[wib][lane] = exmask[i];
+        const float4 p = prel[i0 + lane];
+        sxi[wib][lane][0] = p.x; sxi[wib][lane][1] = p.y; sxi[wib][lane][2] = p.z;
+        const int i = i0 + lane;
+        soi[wib][lane] = i < n ? orig[i] : -1;
+        smask[wib][lane] = i < n ? exmask[i] : 0ull;
     }
     __syncwarp();
-    float lo[3], hi[3];
-    for (int d = 0; d < 3; d++) {
-        lo[d] = 1e30f; hi[d] = -1e30f;
-        for (int k = 0; k < B2_GROUP; k++)
-            if (soi[wib][k] >= 0) { lo[d] = fminf(lo[d], sxi[wib][k][d]); hi[d] = fmaxf(hi[d], sxi[wib][k][d]); }
-    }
+    const float4 ci4 = gcen[warp], hi4 = ghalf[warp];
+    const float ci[3] = {ci4.x, ci4.y, ci4.z}, hi[3] = {hi4.x, hi4.y, hi4.z};
     unsigned padmask = 0;
     int omin = 0x7fffffff, omax = -1;
     for (int k = 0; k < B2_GROUP; k++) {
@@ -203,12 +275,17 @@ __global__ void __launch_bounds__(128) k_build_lists(int n, int g_lo, int ngroup
     }
     const float rmax = (float)g.rmax + NL_MARGIN;
     const float cs[3] = {(float)(g.box[0]/g.nc[0]), (float)(g.box[1]/g.nc[1]), (float)(g.box[2]/g.nc[2])};
-    const float box[3] = {bx, by, bz};
+    // the i-box grown by the largest half extent any j-group can have: a j-group can only matter if
+    // its CENTRE is within rmax of this grown box
+    float lo[3], up[3];
     int c_lo[3], c_n[3];
     bool all[3];
     for (int d = 0; d < 3; d++) {
+        const float grow = __int_as_float(hmax_bits[d]) + 1e-5f;
+        lo[d] = ci[d] - hi[d] - grow;
+        up[d] = ci[d] + hi[d] + grow;
         const int a0 = (int)floorf((lo[d] - rmax)/cs[d]);
-        const int a1 = (int)floorf((hi[d] + rmax)/cs[d]);
+        const int a1 = (int)floorf((up[d] + rmax)/cs[d]);
         const int cover = a1 - a0 + 1;
         all[d] = cover >= g.nc[d];
         if (all[d]) { c_lo[d] = 0; c_n[d] = g.nc[d]; }
@@ -218,7 +295,7 @@ __global__ void __launch_bounds__(128) k_build_lists(int n, int g_lo, int ngroup
         for (int k = 0; k < a.nlists; k++) {
             unsigned char f = 0;
             for (int d = 0; d < 3; d++)
-                if ((double)(hi[d] - lo[d]) + a.rlist[k] > 0.5*g.box[d] - 1e-4) f = 1;
+                if ((double)(2.f*hi[d]) + a.rlist[k] > 0.5*g.box[d] - 1e-4) f = 1;
             a.gflags[k][warp] = f;
         }
     }
@@ -227,16 +304,70 @@ __global__ void __launch_bounds__(128) k_build_lists(int n, int g_lo, int ngroup
     const float rmax2 = rmax*rmax;
     int count[B2_MAX_LISTS] = {0, 0, 0, 0};
     const unsigned lt = (1u << lane) - 1u;
+    int qn = 0;
+
+    // atom-level sweep over queue[0 .. nq): four j-groups per pass
+    bool wide = false;       // queue entries are minimum-image centre differences of fat groups
+    auto sweep = [&](int nq) {
+        for (int q0 = 0; q0 < nq; q0 += 4) {
+            const int q = q0 + (lane >> 3);
+            const bool valid = q < nq;
+            const float4 e = queue[wib][valid ? q : 0];
+            const int j = __float_as_int(e.w)*B2_GROUP + (lane & 7);
+            const bool have = valid && j < n;
+            float d2min = 1e30f;
+            unsigned m = 0;
+            if (have) {
+                const float4 pj = prel[j];
+                const float xj = e.x + pj.x, yj = e.y + pj.y, zj = e.z + pj.z;
+#pragma unroll
+                for (int k = 0; k < B2_GROUP; k++) {
+                    float dx = xj - sxi[wib][k][0], dy = yj - sxi[wib][k][1], dz = zj - sxi[wib][k][2];
+                    if (all[0] || wide) dx -= box[0]*rintf(dx*ibox[0]);
+                    if (all[1] || wide) dy -= box[1]*rintf(dy*ibox[1]);
+                    if (all[2] || wide) dz -= box[2]*rintf(dz*ibox[2]);
+                    d2min = fminf(d2min, dx*dx + dy*dy + dz*dz);
+                }
+                // exclusion mask: only candidates whose caller index is close to the group's own index
+                // range (same molecule) can be excluded or be the atom itself
+                m = padmask;
+                const int oj = orig[j];
+                if (excl_ptr != nullptr || (oj >= omin - 32 && oj <= omax + 32)) {
+                    for (int k = 0; k < B2_GROUP; k++) {
+                        const int oi = soi[wib][k];
+                        if (oi < 0) continue;
+                        const int dd = oj - oi;
+                        bool ex = dd == 0;
+                        if (dd >= -32 && dd < 32) ex = ex || ((smask[wib][k] >> (dd + 32)) & 1ull);
+                        else if (excl_ptr) ex = is_excluded(oi, oj, 0ull, excl_ptr, excl_idx);
+                        if (ex) m |= 1u << k;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < B2_MAX_LISTS; k++) {
+                if (k >= a.nlists) break;
+                const bool in = have && d2min < rl2[k];
+                const unsigned ballot = __ballot_sync(FULL, in);
+                if (in) {
+                    const int pos = count[k] + __popc(ballot & lt);
+                    if (pos < a.cap[k]) a.entries[k][(size_t)warp*a.cap[k] + pos] = (int)((m << 24) | (unsigned)j);
+                }
+                count[k] += __popc(ballot);
+            }
+        }
+    };
+
     for (int cz = 0; cz < c_n[2]; cz++) {
         const int uz = c_lo[2] + cz;
         int iz = uz % g.nc[2]; if (iz < 0) iz += g.nc[2];
         const float sz = all[2] ? 0.f : (float)((uz - iz)/g.nc[2])*box[2];      // periodic shift of this cell layer
-        const float gz = all[2] ? 0.f : fmaxf(0.f, fmaxf(lo[2] - (uz + 1)*cs[2], uz*cs[2] - hi[2]));
+        const float gz = all[2] ? 0.f : fmaxf(0.f, fmaxf(lo[2] - (uz + 1)*cs[2], uz*cs[2] - up[2]));
         for (int cy = 0; cy < c_n[1]; cy++) {
             const int uy = c_lo[1] + cy;
             int iy = uy % g.nc[1]; if (iy < 0) iy += g.nc[1];
             const float sy = all[1] ? 0.f : (float)((uy - iy)/g.nc[1])*box[1];
-            const float gy = all[1] ? 0.f : fmaxf(0.f, fmaxf(lo[1] - (uy + 1)*cs[1], uy*cs[1] - hi[1]));
+            const float gy = all[1] ? 0.f : fmaxf(0.f, fmaxf(lo[1] - (uy + 1)*cs[1], uy*cs[1] - up[1]));
             const float rem2 = rmax2 - gz*gz - gy*gy;
             if (rem2 < 0.f) continue;
             // trim the x-range of this row of cells to the sphere cross-section, then walk it in runs
@@ -246,7 +377,7 @@ __global__ void __launch_bounds__(128) k_build_lists(int n, int g_lo, int ngroup
             if (!all[0]) {
                 const float reach = sqrtf(rem2);
                 u_first = max(u_first, (int)floorf((lo[0] - reach)/cs[0]));
-                u_last = min(u_last, (int)floorf((hi[0] + reach)/cs[0]));
+                u_last = min(u_last, (int)floorf((up[0] + reach)/cs[0]));
             }
             const int row = (iz*g.nc[1] + iy)*g.nc[0];
             int u = u_first;
@@ -259,54 +390,81 @@ __global__ void __launch_bounds__(128) k_build_lists(int n, int g_lo, int ngroup
                 const int cb = cell_start[row + ix0], ce = cell_start[row + ix1 + 1];
                 for (int base = cb; base < ce; base += 32) {
                     const int idx = base + lane;
-                    const bool have = idx < ce;
-                    float d2min = 1e30f;
-                    unsigned m = 0;
-                    int j = 0;
-                    if (have) {
-                        const float4 pj = cpos[idx];
-                        j = __float_as_int(pj.w);
-                        const float xj = pj.x + sx, yj = pj.y + sy, zj = pj.z + sz;
-                        const int oj = corig[idx];
-                        // distance to the nearest of the 8 i-atoms (padding slots duplicate a real atom)
-#pragma unroll
-                        for (int k = 0; k < B2_GROUP; k++) {
-                            float dx = xj - sxi[wib][k][0], dy = yj - sxi[wib][k][1], dz = zj - sxi[wib][k][2];
-                            if (all[0]) dx -= bx*rintf(dx*ibx);
-                            if (all[1]) dy -= by*rintf(dy*iby);
-                            if (all[2]) dz -= bz*rintf(dz*ibz);
-                            d2min = fminf(d2min, dx*dx + dy*dy + dz*dz);
-                        }
-                        // exclusion mask: only candidates whose caller index is close to the group's
-                        // own index range (same molecule) can be excluded or be the atom itself
-                        m = padmask;
-                        if (excl_ptr != nullptr || (oj >= omin - 32 && oj <= omax + 32)) {
-                            for (int k = 0; k < B2_GROUP; k++) {
-                                const int oi = soi[wib][k];
-                                if (oi < 0) continue;
-                                const int dd = oj - oi;
-                                bool ex = dd == 0;
-                                if (dd >= -32 && dd < 32) ex = ex || ((smask[wib][k] >> (dd + 32)) & 1ull);
-                                else if (excl_ptr) ex = is_excluded(oi, oj, 0ull, excl_ptr, excl_idx);
-                                if (ex) m |= 1u << k;
-                            }
-                        }
+                    bool pass = false;
+                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (idx < ce) {
+                        const float4 cj = cgc[idx], hj = cgh[idx];
+                        float dx = cj.x + sx - ci[0], dy = cj.y + sy - ci[1], dz = cj.z + sz - ci[2];
+                        if (all[0]) dx -= box[0]*rintf(dx*ibox[0]);
+                        if (all[1]) dy -= box[1]*rintf(dy*ibox[1]);
+                        if (all[2]) dz -= box[2]*rintf(dz*ibox[2]);
+                        const float gx = fmaxf(fabsf(dx) - (hi[0] + hj.x), 0.f);
+                        const float gyy = fmaxf(fabsf(dy) - (hi[1] + hj.y), 0.f);
+                        const float gzz = fmaxf(fabsf(dz) - (hi[2] + hj.z), 0.f);
+                        pass = gx*gx + gyy*gyy + gzz*gzz < rmax2;
+                        e = make_float4(dx, dy, dz, cj.w);
                     }
-#pragma unroll
-                    for (int k = 0; k < B2_MAX_LISTS; k++) {
-                        if (k >= a.nlists) break;
-                        const bool in = have && d2min < rl2[k];
-                        const unsigned ballot = __ballot_sync(FULL, in);
-                        if (in) {
-                            const int pos = count[k] + __popc(ballot & lt);
-                            if (pos < a.cap[k]) a.entries[k][(size_t)warp*a.cap[k] + pos] = (int)((m << 24) | (unsigned)j);
-                        }
-                        count[k] += __popc(ballot);
+                    const unsigned ballot = __ballot_sync(FULL, pass);
+                    if (pass) queue[wib][qn + __popc(ballot & lt)] = e;
+                    qn += __popc(ballot);
+                    __syncwarp();
+                    if (qn >= 4) {
+                        const int full = qn & ~3;
+                        sweep(full);
+                        // move the (< 4) left-over entries to the head of the queue
+                        const int rest = qn - full;
+                        float4 keep = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (lane < rest) keep = queue[wib][full + lane];
+                        __syncwarp();
+                        if (lane < rest) queue[wib][lane] = keep;
+                        qn = rest;
+                        __syncwarp();
                     }
                 }
                 u = run_end + 1;
             }
         }
+    }
+    if (qn > 0) sweep(qn);
+    // fat groups: tested directly, minimum image per atom (valid because list radius < L/2)
+    const int nfat = flags[8];
+    if (nfat > 0) {
+        wide = true;
+        qn = 0;
+        for (int base = 0; base < nfat; base += 32) {
+            const int idx = base + lane;
+            bool pass = false;
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < nfat) {
+                const int jg = fat_list[idx];
+                const float4 cj = gcen[jg], hj = ghalf[jg];
+                float dx = cj.x - ci[0], dy = cj.y - ci[1], dz = cj.z - ci[2];
+                dx -= box[0]*rintf(dx*ibox[0]);
+                dy -= box[1]*rintf(dy*ibox[1]);
+                dz -= box[2]*rintf(dz*ibox[2]);
+                const float gx = fmaxf(fabsf(dx) - (hi[0] + hj.x), 0.f);
+                const float gyy = fmaxf(fabsf(dy) - (hi[1] + hj.y), 0.f);
+                const float gzz = fmaxf(fabsf(dz) - (hi[2] + hj.z), 0.f);
+                pass = gx*gx + gyy*gyy + gzz*gzz < rmax2;
+                e = make_float4(dx, dy, dz, __int_as_float(jg));
+            }
+            const unsigned ballot = __ballot_sync(FULL, pass);
+            if (pass) queue[wib][qn + __popc(ballot & lt)] = e;
+            qn += __popc(ballot);
+            __syncwarp();
+            if (qn >= 4) {
+                const int full = qn & ~3;
+                sweep(full);
+                const int rest = qn - full;
+                float4 keep = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lane < rest) keep = queue[wib][full + lane];
+                __syncwarp();
+                if (lane < rest) queue[wib][lane] = keep;
+                qn = rest;
+                __syncwarp();
+            }
+        }
+        if (qn > 0) sweep(qn);
     }
     if (lane == 0) {
         for (int k = 0; k < a.nlists; k++) {
@@ -317,14 +475,25 @@ __global__ void __launch_bounds__(128) k_build_lists(int n, int g_lo, int ngroup
     }
 }
 
-__global__ void k_save_ref(int n3, const double* __restrict__ x, double* __restrict__ xref, int* flags) {
+// reference positions for the next skin test; the last block to finish closes the rebuild
+__global__ void k_save_ref(int n3, const double* __restrict__ x, double* __restrict__ xref, int* flags, int* hmax_bits) {
     if (!flags[0]) return;
     int i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i < n3) xref[i] = x[i];
-}
-
-__global__ void k_finish_rebuild(int* flags) {
-    if (flags[0]) { flags[0] = 0; flags[2] += 1; }
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(&flags[4], 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        flags[4] = 0;
+        flags[2] += 1;
+        hmax_bits[0] = hmax_bits[1] = hmax_bits[2] = 0;
+        __threadfence();
+        flags[0] = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -363,16 +532,24 @@ int nl_setup(b2_context* ctx) {
         ctx->ncells = ncells;
         B2_CUDA(cudaMalloc(&ctx->cell_count, sizeof(int)*(ncells + 1)));
         B2_CUDA(cudaMalloc(&ctx->cell_start, sizeof(int)*(ncells + 1)));
+        B2_CUDA(cudaMemsetAsync(ctx->cell_count, 0, sizeof(int)*(ncells + 1), ctx->stream));
     }
-    if (ctx->cell_atoms == nullptr) {
-        B2_CUDA(cudaMalloc(&ctx->cell_atoms, sizeof(int)*ctx->n));
-        B2_CUDA(cudaMalloc(&ctx->cell_of, sizeof(int)*ctx->n));
-        B2_CUDA(cudaMalloc(&ctx->cpos, sizeof(float4)*ctx->n));
-        B2_CUDA(cudaMalloc(&ctx->corig, sizeof(int)*ctx->n));
+    if (ctx->cell_groups == nullptr) {
+        const int ng = ctx->ngroups;
+        B2_CUDA(cudaMalloc(&ctx->cell_groups, sizeof(int)*ng));
+        B2_CUDA(cudaMalloc(&ctx->gcell, sizeof(int)*ng));
+        B2_CUDA(cudaMalloc(&ctx->fat_list, sizeof(int)*ng));
+        B2_CUDA(cudaMalloc(&ctx->gcen, sizeof(float4)*ng));
+        B2_CUDA(cudaMalloc(&ctx->ghalf, sizeof(float4)*ng));
+        B2_CUDA(cudaMalloc(&ctx->cgc, sizeof(float4)*ng));
+        B2_CUDA(cudaMalloc(&ctx->cgh, sizeof(float4)*ng));
+        B2_CUDA(cudaMalloc(&ctx->prel, sizeof(float4)*(size_t)ng*B2_GROUP));
     }
     if (ctx->nl_flags == nullptr) {
-        B2_CUDA(cudaMalloc(&ctx->nl_flags, sizeof(int)*8));
-        B2_CUDA(cudaMemsetAsync(ctx->nl_flags, 0, sizeof(int)*8, ctx->stream));
+        // [0] rebuild needed [1] overflow [2] rebuild counter [3] max count [4] ticket [5..7] max half extent
+        // [8] number of fat groups
+        B2_CUDA(cudaMalloc(&ctx->nl_flags, sizeof(int)*16));
+        B2_CUDA(cudaMemsetAsync(ctx->nl_flags, 0, sizeof(int)*16, ctx->stream));
     }
     return B2_OK;
 }
@@ -390,29 +567,32 @@ static int alloc_lists(b2_context* ctx, int k, int cap) {
     return B2_OK;
 }
 
-// enqueue: wrap + skin test, then the (device-conditional) rebuild pipeline
+// enqueue: skin test, then the (device-conditional) rebuild pipeline
 int nl_prepare(b2_context* ctx, bool force) {
     if (ctx->nlists == 0) {
         return B2_OK;
     }
-    const int n = ctx->n, T = 256;
+    const int n = ctx->n, ng = ctx->ngroups, T = 256;
     Grid g = make_grid(ctx);
     cudaStream_t s = ctx->stream;
     double limit = 0.5*ctx->skin;
-    k_wrap_check<<<(n + T - 1)/T, T, 0, s>>>(n, ctx->x, ctx->xref, ctx->pos4, g, limit*limit, ctx->nl_flags,
+    int* hmax = ctx->nl_flags + 5;
+    k_skin_check<<<(n + T - 1)/T, T, 0, s>>>(n, ctx->x, ctx->xref, limit*limit, ctx->nl_flags,
                                                (ctx->lists_built && !force) ? 1 : 0);
     B2_LAUNCH_CHECK();
-    B2_CUDA(cudaMemsetAsync(ctx->cell_count, 0, sizeof(int)*(ctx->ncells + 1), s));
-    k_cell_count<<<(n + T - 1)/T, T, 0, s>>>(n, ctx->x, g, ctx->cell_of, ctx->cell_count, ctx->nl_flags);
+    k_group_geom<<<(8*ng + T - 1)/T, T, 0, s>>>(n, ng, ctx->x, g, ctx->prel, ctx->gcen, ctx->ghalf, ctx->gcell,
+                                                 ctx->cell_count, hmax, (float)(0.75*std::min(ctx->cellsize[0], std::min(ctx->cellsize[1], ctx->cellsize[2]))),
+                                                 ctx->nl_flags);
     B2_LAUNCH_CHECK();
-    k_cell_scan<<<1, 1024, 0, s>>>(ctx->ncells, ctx->cell_count, ctx->cell_start, ctx->nl_flags);
+    k_cell_scan<<<1, 1024, 0, s>>>(ctx->ncells, ctx->cell_count, ctx->cell_start, ng, ctx->gcell, ctx->fat_list,
+                                   ctx->nl_flags);
     B2_LAUNCH_CHECK();
-    k_cell_fill<<<(n + T - 1)/T, T, 0, s>>>(n, ctx->cell_of, ctx->cell_start, ctx->cell_count, ctx->cell_atoms,
-                                              ctx->nl_flags);
+    k_cell_fill<<<(ng + T - 1)/T, T, 0, s>>>(ng, ctx->gcell, ctx->cell_start, ctx->cell_count, ctx->cell_groups,
+                                               ctx->nl_flags);
     B2_LAUNCH_CHECK();
-    k_cell_sort<<<(ctx->ncells + T - 1)/T, T, 0, s>>>(ctx->ncells, ctx->cell_start, ctx->cell_atoms, ctx->nl_flags);
-    B2_LAUNCH_CHECK();
-    k_cell_pack<<<(n + T - 1)/T, T, 0, s>>>(n, ctx->cell_atoms, ctx->pos4, ctx->orig, ctx->cpos, ctx->corig, ctx->nl_flags);
+    k_cell_sort_pack<<<(ctx->ncells + T - 1)/T, T, 0, s>>>(ctx->ncells, ctx->cell_start, ctx->cell_groups,
+                                                            ctx->cell_count, ctx->gcen, ctx->ghalf, ctx->cgc, ctx->cgh,
+                                                            ctx->nl_flags);
     B2_LAUNCH_CHECK();
     BuildArgs a;
     a.nlists = ctx->nlists;
@@ -422,14 +602,11 @@ int nl_prepare(b2_context* ctx, bool force) {
         a.rlist[k] = r; a.rlist2[k] = r*r;
         a.entries[k] = L.entries; a.counts[k] = L.counts; a.gflags[k] = L.gflags; a.cap[k] = L.cap;
     }
-    const int warps_per_block = 4;
-    k_build_lists<<<std::max(1, (ctx->g_hi - ctx->g_lo + warps_per_block - 1)/warps_per_block), 32*warps_per_block, 0, s>>>(
-        n, ctx->g_lo, ctx->g_hi, ctx->pos4, g, ctx->cell_start, ctx->cpos, ctx->corig, ctx->orig, ctx->exmask,
-        ctx->excl_far ? ctx->excl_ptr : nullptr, ctx->excl_idx, a, ctx->nl_flags);
+    k_build_lists<<<std::max(1, (ctx->g_hi - ctx->g_lo + NL_WARPS - 1)/NL_WARPS), 32*NL_WARPS, 0, s>>>(
+        n, ctx->g_lo, ctx->g_hi, g, ctx->cell_start, ctx->cgc, ctx->cgh, ctx->gcen, ctx->ghalf, ctx->prel, hmax,
+        ctx->fat_list, ctx->orig, ctx->exmask, ctx->excl_far ? ctx->excl_ptr : nullptr, ctx->excl_idx, a, ctx->nl_flags);
     B2_LAUNCH_CHECK();
-    k_save_ref<<<(3*n + T - 1)/T, T, 0, s>>>(3*n, ctx->x, ctx->xref, ctx->nl_flags);
-    B2_LAUNCH_CHECK();
-    k_finish_rebuild<<<1, 1, 0, s>>>(ctx->nl_flags);
+    k_save_ref<<<(3*n + T - 1)/T, T, 0, s>>>(3*n, ctx->x, ctx->xref, ctx->nl_flags, hmax);
     B2_LAUNCH_CHECK();
     ctx->lists_built = true;
     return B2_OK;
