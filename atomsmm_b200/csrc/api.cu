@@ -478,8 +478,10 @@ static int upload_static(b2_context* ctx) {
         B2_CUDA(cudaMemcpy(ctx->pard[k], pd.data(), sizeof(double)*3*n, cudaMemcpyHostToDevice));
     }
     std::vector<unsigned long long> mask(n, 0ull);   // indexed by caller index first
+    ctx->excl_span = 0;
     for (size_t k = 0; k + 1 < ctx->h_excl.size(); k += 2) {
         const int i = ctx->h_excl[k], j = ctx->h_excl[k+1];
+        ctx->excl_span = std::max(ctx->excl_span, abs(inv[i] - inv[j]));
         const int d = j - i;
         if (d >= -32 && d < 32) mask[i] |= 1ull << (d + 32);
         if (-d >= -32 && -d < 32) mask[j] |= 1ull << (-d + 32);

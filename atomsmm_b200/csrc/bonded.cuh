@@ -35,15 +35,21 @@ struct GlobalGeo {
     }
 };
 
+// Forces are accumulated in 64-bit fixed point (2^-32 kJ/mol/nm resolution): integer addition is
+// associative, so the sum does not depend on the order in which threads arrive -- bit-reproducible.
+#define B2_FIXED_SCALE 4294967296.0
 struct LocalGeo {
-    const double* xs;     // [chunk][3] shared memory
-    double* fs;           // [chunk][3] shared memory
-    int base;             // sorted index of the chunk's first atom
+    const double* xs;            // [chunk][3] shared memory
+    unsigned long long* fs;      // [chunk][3] shared memory, fixed point
+    int base;                    // sorted index of the chunk's first atom
     __device__ __forceinline__ double pos(int i, int k) const { return xs[3*(i - base)+k]; }
     __device__ __forceinline__ void add(int i, double fx, double fy, double fz) const {
-        atomicAdd(&fs[3*(i - base)], fx);
-        atomicAdd(&fs[3*(i - base)+1], fy);
-        atomicAdd(&fs[3*(i - base)+2], fz);
+        atomicAdd(&fs[3*(i - base)], (unsigned long long)__double2ll_rn(fx*B2_FIXED_SCALE));
+        atomicAdd(&fs[3*(i - base)+1], (unsigned long long)__double2ll_rn(fy*B2_FIXED_SCALE));
+        atomicAdd(&fs[3*(i - base)+2], (unsigned long long)__double2ll_rn(fz*B2_FIXED_SCALE));
+    }
+    __device__ __forceinline__ double force(int local, int k) const {
+        return (double)(long long)fs[3*local+k]*(1.0/B2_FIXED_SCALE);
     }
 };
 

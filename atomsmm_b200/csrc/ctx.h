@@ -94,6 +94,7 @@ struct b2_context {
     std::vector<BondedForce> bonded_forces;
     std::vector<PmeForce> pme_forces;
     bool excl_far = false;                        // some exclusion spans > 31 in index
+    int excl_span = 0;                            // largest distance in the engine's order between excluded atoms
 
     // ---- device state ----------------------------------------------------------------------
     bool have_order = false, have_positions = false;

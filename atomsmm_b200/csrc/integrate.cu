@@ -91,27 +91,6 @@ __global__ void k_sum_final(int nblocks, const double* __restrict__ partial, dou
     if (threadIdx.x == 0) globals[target] = sh[0];
 }
 
-// scalar program: one warp stages bytecode + constants in shared memory, lane 0 interprets
-#define B2_GLOBAL_SMEM_INTS 2048
-#define B2_GLOBAL_SMEM_CONSTS 256
-__global__ void k_global(const int* __restrict__ code, int len, const double* __restrict__ consts, int nconsts,
-                         double* globals, unsigned long long* rng_state, const double* energies) {
-    __shared__ int scode[B2_GLOBAL_SMEM_INTS];
-    __shared__ double sconsts[B2_GLOBAL_SMEM_CONSTS];
-    const bool staged = 2*len <= B2_GLOBAL_SMEM_INTS && nconsts <= B2_GLOBAL_SMEM_CONSTS;
-    if (staged) {
-        for (int k = threadIdx.x; k < 2*len; k += blockDim.x) scode[k] = code[k];
-        for (int k = threadIdx.x; k < nconsts; k += blockDim.x) sconsts[k] = consts[k];
-    }
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    RngStream rng;
-    rng.seed = rng_state[0] ^ 0x5851f42d4c957f2dull;
-    rng.c0 = 0xffffffffu; rng.c1 = (uint32_t)rng_state[1]; rng.c2 = (uint32_t)(rng_state[1] >> 32); rng.draw = 0;
-    vm_run<1>(staged ? scode : code, len, staged ? sconsts : consts, globals, nullptr, 0, nullptr, &rng, energies);
-    rng_state[1] += 1ull;
-}
-
 struct KickArgs {
     int nterms;
     const float4* f[B2_MAX_KICK_TERMS];
@@ -123,13 +102,46 @@ struct KickArgs {
     int code_len;                    // scalar program run once after the sum (0: none)
 };
 
-__device__ void run_scalar_program(const int* __restrict__ code, int len, const double* __restrict__ consts,
-                                   double* globals, unsigned long long* rng_state, const double* energies) {
-    RngStream rng;
-    rng.seed = rng_state[0] ^ 0x5851f42d4c957f2dull;
-    rng.c0 = 0xffffffffu; rng.c1 = (uint32_t)rng_state[1]; rng.c2 = (uint32_t)(rng_state[1] >> 32); rng.draw = 0;
-    vm_run<1>(code, len, consts, globals, nullptr, 0, nullptr, &rng, energies);
-    rng_state[1] += 1ull;
+// Scalar program executed by one thread, with bytecode, constants AND the global variables staged in
+// shared memory by the whole block (every VM instruction is a dependent load: from HBM/L2 that is
+// ~0.3 us per instruction, from shared memory ~30 ns).  Falls back to global memory when it does not fit.
+#define B2_STAGE_INTS 1024
+#define B2_STAGE_CONSTS 256
+#define B2_STAGE_GLOBALS 256
+struct ScalarStage {
+    int code[B2_STAGE_INTS];
+    double consts[B2_STAGE_CONSTS];
+    double globals[B2_STAGE_GLOBALS];
+};
+
+__device__ void run_scalar_program_staged(ScalarStage& st, const int* __restrict__ code, int len,
+                                          const double* __restrict__ consts, int nconsts, double* globals,
+                                          int nglobals, unsigned long long* rng_state, const double* energies) {
+    const bool staged = 2*len <= B2_STAGE_INTS && nconsts <= B2_STAGE_CONSTS && nglobals <= B2_STAGE_GLOBALS;
+    if (staged) {
+        for (int k = threadIdx.x; k < 2*len; k += blockDim.x) st.code[k] = code[k];
+        for (int k = threadIdx.x; k < nconsts; k += blockDim.x) st.consts[k] = consts[k];
+        for (int k = threadIdx.x; k < nglobals; k += blockDim.x) st.globals[k] = __ldcg(&globals[k]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        RngStream rng;
+        rng.seed = rng_state[0] ^ 0x5851f42d4c957f2dull;
+        rng.c0 = 0xffffffffu; rng.c1 = (uint32_t)rng_state[1]; rng.c2 = (uint32_t)(rng_state[1] >> 32); rng.draw = 0;
+        if (staged) vm_run<1>(st.code, len, st.consts, st.globals, nullptr, 0, nullptr, &rng, energies);
+        else vm_run<1>(code, len, consts, globals, nullptr, 0, nullptr, &rng, energies);
+        rng_state[1] += 1ull;
+    }
+    __syncthreads();
+    if (staged)
+        for (int k = threadIdx.x; k < nglobals; k += blockDim.x) globals[k] = st.globals[k];
+}
+
+// stand-alone scalar program (prologue of a step, Bussi's rejection loop, AFED wall reflection ...)
+__global__ void k_global(const int* __restrict__ code, int len, const double* __restrict__ consts, int nconsts,
+                         double* globals, int nglobals, unsigned long long* rng_state, const double* energies) {
+    __shared__ ScalarStage stage;
+    run_scalar_program_staged(stage, code, len, consts, nconsts, globals, nglobals, rng_state, energies);
 }
 
 // The velocity kernel: v <- s*v + sum_k s_k c_k f_k/m ; [x += c_d v] ; [mvv <- sum(m v.v) ; scalar
@@ -141,6 +153,7 @@ __global__ void __launch_bounds__(256) k_vel(int lo, int hi, double* __restrict_
                                              const double* __restrict__ mass, double* globals,
                                              double* __restrict__ partial, unsigned* __restrict__ ticket,
                                              const int* __restrict__ code, const double* __restrict__ consts,
+                                             int nconsts, int nglobals,
                                              unsigned long long* rng_state, const double* energies) {
     const int i = lo + blockIdx.x*blockDim.x + threadIdx.x;
     double mvv = 0;
@@ -201,7 +214,12 @@ __global__ void __launch_bounds__(256) k_vel(int lo, int hi, double* __restrict_
     if (threadIdx.x == 0) {
         globals[a.mvv] = red[0];
         *ticket = 0;
-        if (a.code_len > 0) run_scalar_program(code, a.code_len, consts, globals, rng_state, energies);
+        __threadfence();
+    }
+    __syncthreads();
+    if (a.code_len > 0) {
+        __shared__ ScalarStage stage;
+        run_scalar_program_staged(stage, code, a.code_len, consts, nconsts, globals, nglobals, rng_state, energies);
     }
     }
 }
@@ -257,7 +275,7 @@ __global__ void __launch_bounds__(B2_CHUNK) k_inner(const int* __restrict__ chun
                                                     const double* __restrict__ globals, float4* __restrict__ fout,
                                                     const __grid_constant__ InnerArgs A) {
     __shared__ double xs[3*B2_CHUNK];
-    __shared__ double fs[3*B2_CHUNK];
+    __shared__ unsigned long long fs[3*B2_CHUNK];
     const int c = blockIdx.x, tid = threadIdx.x;
     const int base = chunk_start[c], count = chunk_start[c+1] - base;
     const int i = base + tid;
@@ -284,7 +302,7 @@ __global__ void __launch_bounds__(B2_CHUNK) k_inner(const int* __restrict__ chun
                 for (int k = 0; k < op.nterms; k++) {
                     const double cf = (double)op.sign[k]*globals[op.coef[k]];
                     if (have_local && op.slot[k] == A.local_slot) {
-                        a[0] += cf*fs[3*tid]; a[1] += cf*fs[3*tid+1]; a[2] += cf*fs[3*tid+2];
+                        a[0] += cf*geo.force(tid, 0); a[1] += cf*geo.force(tid, 1); a[2] += cf*geo.force(tid, 2);
                     } else {
                         const float4 f = A.f[op.slot[k]][i];
                         a[0] += cf*(double)f.x; a[1] += cf*(double)f.y; a[2] += cf*(double)f.z;
@@ -301,7 +319,7 @@ __global__ void __launch_bounds__(B2_CHUNK) k_inner(const int* __restrict__ chun
         } else {
             __syncthreads();           // everybody has consumed the previous local force
 #pragma unroll
-            for (int k = 0; k < 3; k++) { xs[3*tid+k] = x[k]; fs[3*tid+k] = 0.0; }
+            for (int k = 0; k < 3; k++) { xs[3*tid+k] = x[k]; fs[3*tid+k] = 0ull; }
             __syncthreads();
             for (int t = t0 + tid; t < t1; t += B2_CHUNK) {
                 const int2 rec = terms[t];
@@ -319,7 +337,7 @@ __global__ void __launch_bounds__(B2_CHUNK) k_inner(const int* __restrict__ chun
     if (mine) {
 #pragma unroll
         for (int k = 0; k < 3; k++) { xg[3*i+k] = x[k]; vg[3*i+k] = v[k]; }
-        if (A.write_force) fout[i] = make_float4((float)fs[3*tid], (float)fs[3*tid+1], (float)fs[3*tid+2], 0.f);
+        if (A.write_force) fout[i] = make_float4((float)geo.force(tid, 0), (float)geo.force(tid, 1), (float)geo.force(tid, 2), 0.f);
     }
 }
 
@@ -470,17 +488,19 @@ static int launch_vel(b2_context* ctx, const b2_op& op) {
     if (split) ka.code_len = 0;
     if (ka.mvv >= 0) {
         k_vel<true><<<blocks, T, 0, s>>>(lo, hi, ctx->v, ctx->x, ka, ctx->massd, ctx->globals, ctx->sum_partial,
-                                          ctx->ticket, ctx->code + op.f, ctx->consts, ctx->rng_state, ctx->d_energy);
+                                          ctx->ticket, ctx->code + op.f, ctx->consts, ctx->nconsts, ctx->nglobals,
+                                          ctx->rng_state, ctx->d_energy);
     } else {
         k_vel<false><<<blocks, T, 0, s>>>(lo, hi, ctx->v, ctx->x, ka, ctx->massd, ctx->globals, ctx->sum_partial,
-                                           ctx->ticket, ctx->code + op.f, ctx->consts, ctx->rng_state, ctx->d_energy);
+                                           ctx->ticket, ctx->code + op.f, ctx->consts, ctx->nconsts, ctx->nglobals,
+                                          ctx->rng_state, ctx->d_energy);
     }
     B2_LAUNCH_CHECK();
     if (split) {
         B2_TRY(dist_allreduce(ctx, ctx->globals + ka.mvv, 1));
         if (op.g > 0) {
             k_global<<<1, 64, 0, s>>>(ctx->code + op.f, op.g, ctx->consts, ctx->nconsts, ctx->globals,
-                                       ctx->rng_state, ctx->d_energy);
+                                       ctx->nglobals, ctx->rng_state, ctx->d_energy);
             B2_LAUNCH_CHECK();
         }
     }
@@ -602,7 +622,7 @@ static int run_one_step(b2_context* ctx) {
         }
         case B2_OP_GLOBAL:
             k_global<<<1, 64, 0, s>>>(ctx->code + op.b, op.c, ctx->consts, ctx->nconsts, ctx->globals,
-                                       ctx->rng_state, ctx->d_energy);
+                                       ctx->nglobals, ctx->rng_state, ctx->d_energy);
             B2_LAUNCH_CHECK();
             break;
         case B2_OP_KICK: {

@@ -17,6 +17,7 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "ctx.h"
 
@@ -243,7 +244,8 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
                                                              const int* __restrict__ orig,
                                                              const unsigned long long* __restrict__ exmask,
                                                              const int* __restrict__ excl_ptr,
-                                                             const int* __restrict__ excl_idx, BuildArgs a, int* flags) {
+                                                             const int* __restrict__ excl_idx, int excl_span,
+                                                             BuildArgs a, int* flags) {
     if (!flags[0]) return;
     const int warp = g_lo + ((blockIdx.x*blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -267,12 +269,12 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
     const float4 ci4 = gcen[warp], hi4 = ghalf[warp];
     const float ci[3] = {ci4.x, ci4.y, ci4.z}, hi[3] = {hi4.x, hi4.y, hi4.z};
     unsigned padmask = 0;
-    int omin = 0x7fffffff, omax = -1;
-    for (int k = 0; k < B2_GROUP; k++) {
-        const int oi = soi[wib][k];
-        if (oi < 0) padmask |= 1u << k;
-        else { omin = min(omin, oi); omax = max(omax, oi); }
-    }
+    for (int k = 0; k < B2_GROUP; k++)
+        if (soi[wib][k] < 0) padmask |= 1u << k;
+    // only atoms within excl_span positions (engine order) of the group can be excluded partners
+    // or the atoms themselves: excl_span is the largest distance, in the engine's order, between
+    // the two atoms of any exclusion
+    const int j_first = i0 - excl_span, j_last = i0 + B2_GROUP - 1 + excl_span;
     const float rmax = (float)g.rmax + NL_MARGIN;
     const float cs[3] = {(float)(g.box[0]/g.nc[0]), (float)(g.box[1]/g.nc[1]), (float)(g.box[2]/g.nc[2])};
     // the i-box grown by the largest half extent any j-group can have: a j-group can only matter if
@@ -308,7 +310,9 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
 
     // atom-level sweep over queue[0 .. nq): four j-groups per pass
     bool wide = false;       // queue entries are minimum-image centre differences of fat groups
-    auto sweep = [&](int nq) {
+    // MI: apply the minimum image per atom pair (small boxes, fat groups)
+    auto sweep_t = [&](int nq, auto mi_tag) {
+        constexpr bool MI = decltype(mi_tag)::value;
         for (int q0 = 0; q0 < nq; q0 += 4) {
             const int q = q0 + (lane >> 3);
             const bool valid = q < nq;
@@ -316,23 +320,22 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
             const int j = __float_as_int(e.w)*B2_GROUP + (lane & 7);
             const bool have = valid && j < n;
             float d2min = 1e30f;
-            unsigned m = 0;
+            unsigned m = padmask;
             if (have) {
                 const float4 pj = prel[j];
                 const float xj = e.x + pj.x, yj = e.y + pj.y, zj = e.z + pj.z;
 #pragma unroll
                 for (int k = 0; k < B2_GROUP; k++) {
                     float dx = xj - sxi[wib][k][0], dy = yj - sxi[wib][k][1], dz = zj - sxi[wib][k][2];
-                    if (all[0] || wide) dx -= box[0]*rintf(dx*ibox[0]);
-                    if (all[1] || wide) dy -= box[1]*rintf(dy*ibox[1]);
-                    if (all[2] || wide) dz -= box[2]*rintf(dz*ibox[2]);
+                    if (MI) {
+                        if (all[0] || wide) dx -= box[0]*rintf(dx*ibox[0]);
+                        if (all[1] || wide) dy -= box[1]*rintf(dy*ibox[1]);
+                        if (all[2] || wide) dz -= box[2]*rintf(dz*ibox[2]);
+                    }
                     d2min = fminf(d2min, dx*dx + dy*dy + dz*dz);
                 }
-                // exclusion mask: only candidates whose caller index is close to the group's own index
-                // range (same molecule) can be excluded or be the atom itself
-                m = padmask;
-                const int oj = orig[j];
-                if (excl_ptr != nullptr || (oj >= omin - 32 && oj <= omax + 32)) {
+                if (j >= j_first && j <= j_last) {
+                    const int oj = orig[j];
                     for (int k = 0; k < B2_GROUP; k++) {
                         const int oi = soi[wib][k];
                         if (oi < 0) continue;
@@ -356,6 +359,11 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
                 count[k] += __popc(ballot);
             }
         }
+    };
+    const bool any_all = all[0] || all[1] || all[2];
+    auto sweep = [&](int nq) {
+        if (any_all || wide) sweep_t(nq, std::true_type());
+        else sweep_t(nq, std::false_type());
     };
 
     for (int cz = 0; cz < c_n[2]; cz++) {
@@ -520,7 +528,10 @@ int nl_setup(b2_context* ctx) {
         if (ctx->lists[0].cutoff > 0.5*ctx->box[d] + 1e-9)
             return b2_fail(ctx, B2_ERR_ARG, "cutoff %g nm exceeds half the box length %g nm", rmax - ctx->skin,
                            ctx->box[d]);
-        double target = std::max(0.5*rmax, 0.35);
+        // cells are short along x (the contiguous direction of the cell-ordered arrays: the list build
+        // walks rows of cells along x) and as long as the list radius along y and z, so that a row is
+        // one long contiguous run of candidates instead of many short ones
+        double target = d == 0 ? std::max(0.5*rmax, 0.35) : std::max(rmax, 0.7);
         int nc = std::max(1, (int)floor(ctx->box[d]/target));
         nc = std::min(nc, 160);
         ctx->ncell[d] = nc;
@@ -581,7 +592,7 @@ int nl_prepare(b2_context* ctx, bool force) {
                                                (ctx->lists_built && !force) ? 1 : 0);
     B2_LAUNCH_CHECK();
     k_group_geom<<<(8*ng + T - 1)/T, T, 0, s>>>(n, ng, ctx->x, g, ctx->prel, ctx->gcen, ctx->ghalf, ctx->gcell,
-                                                 ctx->cell_count, hmax, (float)(0.75*std::min(ctx->cellsize[0], std::min(ctx->cellsize[1], ctx->cellsize[2]))),
+                                                 ctx->cell_count, hmax, (float)(0.75*ctx->cellsize[0]),
                                                  ctx->nl_flags);
     B2_LAUNCH_CHECK();
     k_cell_scan<<<1, 1024, 0, s>>>(ctx->ncells, ctx->cell_count, ctx->cell_start, ng, ctx->gcell, ctx->fat_list,
@@ -604,7 +615,7 @@ int nl_prepare(b2_context* ctx, bool force) {
     }
     k_build_lists<<<std::max(1, (ctx->g_hi - ctx->g_lo + NL_WARPS - 1)/NL_WARPS), 32*NL_WARPS, 0, s>>>(
         n, ctx->g_lo, ctx->g_hi, g, ctx->cell_start, ctx->cgc, ctx->cgh, ctx->gcen, ctx->ghalf, ctx->prel, hmax,
-        ctx->fat_list, ctx->orig, ctx->exmask, ctx->excl_far ? ctx->excl_ptr : nullptr, ctx->excl_idx, a, ctx->nl_flags);
+        ctx->fat_list, ctx->orig, ctx->exmask, ctx->excl_far ? ctx->excl_ptr : nullptr, ctx->excl_idx, ctx->excl_span, a, ctx->nl_flags);
     B2_LAUNCH_CHECK();
     k_save_ref<<<(3*n + T - 1)/T, T, 0, s>>>(3*n, ctx->x, ctx->xref, ctx->nl_flags, hmax);
     B2_LAUNCH_CHECK();
@@ -625,7 +636,7 @@ int nl_initial_build(b2_context* ctx) {
         guess = ((guess + 31)/32)*32;
         if (ctx->lists[k].entries == nullptr || ctx->lists[k].cap < guess) B2_TRY(alloc_lists(ctx, k, guess));
     }
-    for (int attempt = 0; attempt < 4; attempt++) {
+    for (int attempt = 0; attempt < 6; attempt++) {
         int zero[8] = {0};
         int flags[8];
         B2_CUDA(cudaMemcpyAsync(flags, ctx->nl_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
@@ -636,14 +647,23 @@ int nl_initial_build(b2_context* ctx) {
         B2_CUDA(cudaMemcpyAsync(flags, ctx->nl_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
         B2_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->counters[4] = flags[3];
-        if (!flags[1]) {
+        // capacity = 1.3 x the largest list seen now (density fluctuations during a run), scaled per list
+        // by the ratio of list volumes
+        double rbig = 0;
+        for (int k = 0; k < ctx->nlists; k++) rbig = std::max(rbig, ctx->lists[k].cutoff + ctx->skin);
+        bool grown = false;
+        for (int k = 0; k < ctx->nlists; k++) {
+            const double ratio = pow((ctx->lists[k].cutoff + ctx->skin)/rbig, 3.0);
+            int cap = (int)(1.3*flags[3]*std::min(1.0, ratio*1.15)) + 64;
+            cap = std::min(((cap + 31)/32)*32, ((ctx->n + 63)/32)*32);
+            if (cap > ctx->lists[k].cap) {
+                B2_TRY(alloc_lists(ctx, k, cap));
+                grown = true;
+            }
+        }
+        if (!flags[1] && !grown) {
             ctx->counters[3] = ctx->lists[0].cap;
             return B2_OK;
-        }
-        for (int k = 0; k < ctx->nlists; k++) {
-            int cap = ((int)(flags[3]*1.25) + 63)/32*32;
-            cap = std::min(cap, ((ctx->n + 63)/32)*32);
-            B2_TRY(alloc_lists(ctx, k, std::max(cap, ctx->lists[k].cap)));
         }
     }
     return b2_fail(ctx, B2_ERR_OVERFLOW, "neighbour list capacity could not be fitted");

@@ -409,7 +409,10 @@ static int launch_energy(b2_context* ctx, const PairForce& pf, POT pot, double r
         break;                                                                                              \
     case B2_PAIR_LJC: {                                                                                     \
         const int ck = (int)pf.params[1];                                                                   \
-        if (ck == 2) { LJCPot<COUL_RF, LJ_STD, SW_LJ, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; }           \
+        const bool sw = pf.params[5] != 0.0;       /* OpenMM switch on the LJ part in use? */               \
+        if (ck == 2 && !sw) { LJCPot<COUL_RF, LJ_STD, SW_NONE, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; }  \
+        else if (ck == 3 && !sw) { LJCPot<COUL_ERFC, LJ_STD, SW_NONE, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; } \
+        else if (ck == 2) { LJCPot<COUL_RF, LJ_STD, SW_LJ, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; }      \
         else if (ck == 3) { LJCPot<COUL_ERFC, LJ_STD, SW_LJ, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; }    \
         else { LJCPot<COUL_PLAIN, LJ_STD, SW_LJ, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; }                \
         break;                                                                                              \

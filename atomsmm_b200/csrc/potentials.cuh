@@ -28,7 +28,8 @@ __device__ __forceinline__ double b2_rsqrt(double x) { return 1.0/sqrt(x); }
 // 1/r and 1/r^2 from r^2.  fp32: MUFU.RSQ (<= 2 ulp) refined by one Newton step (~0.5 ulp), because the
 // r^-12 term amplifies the relative error of 1/r twelve-fold.
 __device__ __forceinline__ void b2_inverse(float r2, float& rinv, float& rinv2) {
-    float y = rsqrtf(r2);
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(r2));   // r2 is never subnormal: no range fix-up code
     const float e = fmaf(-r2*y, y, 1.0f);
     y = fmaf(0.5f*y, e, y);
     rinv = y;

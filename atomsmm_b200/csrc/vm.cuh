@@ -76,6 +76,38 @@ __device__ __forceinline__ double vm_powi(double x, int n) {
     return inv ? 1.0/r : r;
 }
 
+// Rare / heavy opcodes live in one out-of-line function so that the interpreter's hot loop (pushes,
+// + - * and stores) is a few hundred bytes of code: a scalar program is executed by ONE thread, whose
+// speed is set by instruction-cache misses, not by arithmetic (measured: ~500 cycles per VM
+// instruction when every opcode jumped into a different part of a 30 KB switch).
+static __device__ __noinline__ int vm_cold(int op, int arg, double* st, int sp, RngStream* rng) {
+    switch (op) {
+    case VM_GAUSS: st[sp++] = rng->gaussian(); break;
+    case VM_UNIF: st[sp++] = rng->uniform(); break;
+    case VM_DIV: sp--; st[sp-1] /= st[sp]; break;
+    case VM_POW: sp--; st[sp-1] = pow(st[sp-1], st[sp]); break;
+    case VM_POWI: st[sp-1] = vm_powi(st[sp-1], arg); break;
+    case VM_SQRT: st[sp-1] = sqrt(st[sp-1]); break;
+    case VM_EXP: st[sp-1] = exp(st[sp-1]); break;
+    case VM_LOG: st[sp-1] = log(st[sp-1]); break;
+    case VM_SIN: st[sp-1] = sin(st[sp-1]); break;
+    case VM_COS: st[sp-1] = cos(st[sp-1]); break;
+    case VM_TAN: st[sp-1] = tan(st[sp-1]); break;
+    case VM_ERF: st[sp-1] = erf(st[sp-1]); break;
+    case VM_ERFC: st[sp-1] = erfc(st[sp-1]); break;
+    case VM_ABS: st[sp-1] = fabs(st[sp-1]); break;
+    case VM_MIN: sp--; st[sp-1] = fmin(st[sp-1], st[sp]); break;
+    case VM_MAX: sp--; st[sp-1] = fmax(st[sp-1], st[sp]); break;
+    case VM_STEP: st[sp-1] = st[sp-1] < 0.0 ? 0.0 : 1.0; break;
+    case VM_DELTA: st[sp-1] = st[sp-1] == 0.0 ? 1.0 : 0.0; break;
+    case VM_SELECT: sp -= 2; st[sp-1] = (st[sp-1] != 0.0) ? st[sp] : st[sp+1]; break;
+    case VM_FLOOR: st[sp-1] = floor(st[sp-1]); break;
+    case VM_CEIL: st[sp-1] = ceil(st[sp-1]); break;
+    default: break;
+    }
+    return sp;
+}
+
 // MODE 0: per-DOF (tab/dof valid)   MODE 1: scalar program over globals (STOREG/JMP allowed)
 // MODE 2: custom bonded term (PUSHV reads env.vars)
 template <int MODE>
@@ -88,64 +120,30 @@ __device__ double vm_run(const int* __restrict__ code, int len, const double* __
     while (pc < len) {
         const int op = code[2*pc], arg = code[2*pc + 1];
         pc++;
-        switch (op) {
-        case VM_PUSHC: st[sp++] = consts[arg]; break;
-        case VM_PUSHG: st[sp++] = globals[arg]; break;
-        case VM_PUSHV:
-            if (MODE == 0) st[sp++] = tab->vars[arg][dof];
-            else st[sp++] = lvars[arg];
-            break;
-        case VM_PUSHM: st[sp++] = tab->mass[dof/3]; break;
-        case VM_PUSHF: {
+        if (op == VM_PUSHC) st[sp++] = consts[arg];
+        else if (op == VM_PUSHG) st[sp++] = globals[arg];
+        else if (op == VM_MUL) { sp--; st[sp-1] *= st[sp]; }
+        else if (op == VM_ADD) { sp--; st[sp-1] += st[sp]; }
+        else if (op == VM_SUB) { sp--; st[sp-1] -= st[sp]; }
+        else if (op == VM_NEG) st[sp-1] = -st[sp-1];
+        else if (op == VM_PUSHV) st[sp++] = MODE == 0 ? tab->vars[arg][dof] : lvars[arg];
+        else if (op == VM_STOREG) { if (MODE == 1) globals[arg] = st[--sp]; }
+        else if (op == VM_PUSHM) st[sp++] = tab->mass[dof/3];
+        else if (op == VM_PUSHF) {
             const float* f = reinterpret_cast<const float*>(tab->f[arg]);
             st[sp++] = (double)f[(dof/3)*4 + dof%3];
-            break;
         }
-        case VM_PUSHE: st[sp++] = energies[arg]; break;
-        case VM_GAUSS: st[sp++] = rng->gaussian(); break;
-        case VM_UNIF: st[sp++] = rng->uniform(); break;
-        case VM_ADD: sp--; st[sp-1] += st[sp]; break;
-        case VM_SUB: sp--; st[sp-1] -= st[sp]; break;
-        case VM_MUL: sp--; st[sp-1] *= st[sp]; break;
-        case VM_DIV: sp--; st[sp-1] /= st[sp]; break;
-        case VM_NEG: st[sp-1] = -st[sp-1]; break;
-        case VM_POW: sp--; st[sp-1] = pow(st[sp-1], st[sp]); break;
-        case VM_POWI: st[sp-1] = vm_powi(st[sp-1], arg); break;
-        case VM_SQRT: st[sp-1] = sqrt(st[sp-1]); break;
-        case VM_EXP: st[sp-1] = exp(st[sp-1]); break;
-        case VM_LOG: st[sp-1] = log(st[sp-1]); break;
-        case VM_SIN: st[sp-1] = sin(st[sp-1]); break;
-        case VM_COS: st[sp-1] = cos(st[sp-1]); break;
-        case VM_TAN: st[sp-1] = tan(st[sp-1]); break;
-        case VM_ERF: st[sp-1] = erf(st[sp-1]); break;
-        case VM_ERFC: st[sp-1] = erfc(st[sp-1]); break;
-        case VM_ABS: st[sp-1] = fabs(st[sp-1]); break;
-        case VM_MIN: sp--; st[sp-1] = fmin(st[sp-1], st[sp]); break;
-        case VM_MAX: sp--; st[sp-1] = fmax(st[sp-1], st[sp]); break;
-        case VM_STEP: st[sp-1] = st[sp-1] < 0.0 ? 0.0 : 1.0; break;
-        case VM_DELTA: st[sp-1] = st[sp-1] == 0.0 ? 1.0 : 0.0; break;
-        case VM_SELECT: sp -= 2; st[sp-1] = (st[sp-1] != 0.0) ? st[sp] : st[sp+1]; break;
-        case VM_FLOOR: st[sp-1] = floor(st[sp-1]); break;
-        case VM_CEIL: st[sp-1] = ceil(st[sp-1]); break;
-        case VM_CMP: {
+        else if (op == VM_PUSHE) st[sp++] = energies[arg];
+        else if (op == VM_JMP) { if (MODE == 1) pc = arg; }
+        else if (op == VM_JMPZ) { if (MODE == 1) { if (st[--sp] == 0.0) pc = arg; } }
+        else if (op == VM_CMP) {
             sp--;
             const double a = st[sp-1], b = st[sp];
-            bool r = arg == 0 ? a == b : arg == 1 ? a < b : arg == 2 ? a > b : arg == 3 ? a != b
-                   : arg == 4 ? a <= b : a >= b;
+            const bool r = arg == 0 ? a == b : arg == 1 ? a < b : arg == 2 ? a > b : arg == 3 ? a != b
+                         : arg == 4 ? a <= b : a >= b;
             st[sp-1] = r ? 1.0 : 0.0;
-            break;
         }
-        case VM_STOREG:
-            if (MODE == 1) globals[arg] = st[--sp];
-            break;
-        case VM_JMP:
-            if (MODE == 1) pc = arg;
-            break;
-        case VM_JMPZ:
-            if (MODE == 1) { if (st[--sp] == 0.0) pc = arg; }
-            break;
-        default: break;
-        }
+        else sp = vm_cold(op, arg, st, sp, rng);
     }
     return sp > 0 ? st[sp-1] : 0.0;
 }

@@ -587,6 +587,7 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
     _fuse_kicks(P)
     if fast:
         _fuse_velocity_ops(P)
+        _chain_scale_blocks(P)
     return P
 
 
@@ -702,6 +703,90 @@ def _fuse_velocity_ops(P):
             release()
             out.append(op)
     release()
+    P.ops = out
+
+
+def _chain_scale_blocks(P):
+    """Third peephole: consecutive thermostat blocks share ONE reduction.
+
+    After ``v <- s*v`` the sum ``m*v*v`` is exactly ``s*s`` times its previous value, so in
+        KICK(mvv -> X, program A) ; KICK(no terms, prescale s, mvv -> X, program B)
+    the second reduction is replaced by the scalar statement ``X <- s*s*X`` and the two programs run
+    back to back in the first kernel's tail.  The rescaling itself is deferred: the product of the
+    pending factors is kept in a private global and applied by the next velocity kernel (as its
+    pre-scale) or, failing that, by a bare scaling kernel.  A Suzuki-Yoshida chain of n Nose-Hoover
+    blocks thereby costs one reduction instead of n.  (Results differ from the literal program only
+    by the rounding of s*s*X versus the re-summed value, ~1e-16 relative.)"""
+    JUMPS = (X.OPCODES['JMP'], X.OPCODES['JMPZ'])
+    PUSHG, MUL, STOREG = X.OPCODES['PUSHG'], X.OPCODES['MUL'], X.OPCODES['STOREG']
+    product = None       # global index of the pending scale product, or None
+    chain_head = None
+    out = []
+
+    def words(start, length, shift):
+        code = list(P.bc.code[start:start + 2*length])
+        for k in range(0, len(code), 2):
+            if code[k] in JUMPS:
+                code[k+1] += shift
+        return code
+
+    def flush():
+        nonlocal product
+        if product is not None:
+            out.append([OP_KICK, 0, 0, -1, product, -1, 0, 0])
+            product = None
+
+    vs = None
+    for op in P.ops:
+        kind = op[0]
+        bare_sum = (kind == OP_KICK and op[1] == 0 and op[3] < 0 and op[4] >= 0 and op[5] >= 0)
+        head = None
+        if bare_sum:
+            # the kernel that produced X: the last op, provided only EVAL/UPDATE ops came after it
+            for prev in reversed(out):
+                if prev[0] in (OP_EVAL, OP_UPDATE_STATE):
+                    continue
+                if prev[0] == OP_KICK and prev[5] == op[5] and (product is None or prev is chain_head):
+                    head = prev
+                break
+        if head is not None:
+            if vs is None:
+                vs = P.new_global('_vscale_product', 1.0)
+            scale, target = op[4], op[5]
+            merged = words(head[6], head[7], 0)
+            shift = len(merged)//2
+            merged += [PUSHG, scale, PUSHG, scale, MUL, 0, PUSHG, target, MUL, 0, STOREG, target]
+            if product is None:
+                merged += [PUSHG, scale, STOREG, vs]
+            else:
+                merged += [PUSHG, vs, PUSHG, scale, MUL, 0, STOREG, vs]
+            shift = len(merged)//2
+            merged += words(op[6], op[7], shift)
+            head[6] = len(P.bc.code)
+            head[7] = len(merged)//2
+            P.bc.code += merged
+            product = vs
+            chain_head = head
+            continue
+        if kind in (OP_EVAL, OP_UPDATE_STATE):
+            out.append(op)
+            continue
+        if product is not None and kind == OP_KICK:
+            op = list(op)
+            if op[4] >= 0:
+                # the op's own pre-scale joins the product (computed by the chain head's program)
+                extra = [PUSHG, vs, PUSHG, op[4], MUL, 0, STOREG, vs]
+                merged = words(chain_head[6], chain_head[7], 0) + extra
+                chain_head[6] = len(P.bc.code)
+                chain_head[7] = len(merged)//2
+                P.bc.code += merged
+            op[4] = vs
+            product = None
+            out.append(op)
+            continue
+        flush()
+        out.append(op)
+    flush()
     P.ops = out
 
 

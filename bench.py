@@ -14,8 +14,13 @@ pass of the hot path over one batch.  `value` times K such calls with state resi
 `e2e` times the same through the public API with HOST buffers: upload of positions+velocities from
 pinned host memory, the MD steps, download of positions+velocities+energies, every step.
 
-N > 1: the path shards only by domain decomposition (next round) or as independent replicas; this
-bench runs N independent replicas, one per GPU, no data-path collective ("scaling": "weak").
+N > 1 (default): N independent replicas of the workload, one per GPU, no data-path collective
+("scaling": "weak") -- ensembles are how configs 1-4 shard.
+N > 1 with --dd: ONE system integrated by all ranks with spatial domain decomposition (NCCL position
+exchange before every pair-force evaluation); "scaling": "strong".  `--workload c5` selects BASELINE
+config 5 (the cell replicated 14x14x14 = 4 214 784 atoms, L = 35 nm), the configuration the
+decomposition is meant for:
+    torchrun --nproc-per-node 8 bench.py --gpus 8 --workload c5 --dd --steps 3 --md-steps 20
 """
 
 import argparse
@@ -162,9 +167,13 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, n, md_steps):
-    return dict(workload='c2: q-SPC-FW water x%d^3, %d atoms, RESPASystem near 0.7/0.5 nm force-switch + LJ/reaction-field '
-                         '1.0 nm, RESPA [4,2,1] + NoseHoover SY3, dt 4 fs' % (args.reps, n),
-                atoms=n, md_steps_per_step=md_steps, dt_fs=DT_FS, loops=LOOPS, replicas=args.gpus,
+    dd = getattr(args, 'dd', False) and args.gpus > 1
+    return dict(workload='%s: q-SPC-FW water x%d^3, %d atoms, RESPASystem near 0.7/0.5 nm force-switch + LJ/reaction-field '
+                         '1.0 nm, RESPA [4,2,1] + NoseHoover SY3, dt 4 fs' % (getattr(args, 'workload', 'c2'), args.reps, n),
+                atoms=n, md_steps_per_step=md_steps, dt_fs=DT_FS, loops=LOOPS,
+                replicas=1 if dd else args.gpus,
+                parallelism=('domain decomposition over %d ranks' % args.gpus) if dd else
+                            ('%d independent replicas' % args.gpus),
                 l2_policy='state and neighbour lists of this workload (~110 MB) do not fit a flush-free L2 reuse '
                           'pattern: every bench step streams %d MD steps x (lists 2x ~50 MB + state), far beyond '
                           'the 126 MB L2; no explicit flush' % md_steps)
@@ -180,7 +189,12 @@ def main():
     parser.add_argument('--md-steps', type=int, default=MD_STEPS_PER_CALL)
     parser.add_argument('--cpu-md-steps', type=int, default=2)
     parser.add_argument('--no-cpu-baseline', action='store_true')
+    parser.add_argument('--workload', default='c2', choices=['c2', 'c5'])
+    parser.add_argument('--dd', action='store_true', help='one system over all ranks (domain decomposition)')
+    parser.add_argument('--no-e2e', action='store_true', help='skip the host-buffer end-to-end leg')
     args = parser.parse_args()
+    if args.workload == 'c5':
+        args.reps = 14
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else max(args.warmup, 1)
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -202,8 +216,13 @@ def main():
     system, pos, vel = build_workload(args.reps)
     n = system.getNumParticles()
     integrator, dof = make_integrator(system)
-    integrator.setRandomNumberSeed(1 + rank)
-    context = mm.Context(system, integrator, mm.Platform.getPlatformByName('B200'), {'DeviceIndex': local})
+    dd = args.dd and world > 1
+    integrator.setRandomNumberSeed(1 if dd else 1 + rank)
+    properties = {'DeviceIndex': local}
+    if dd:
+        properties['DomainDecomposition'] = 'true'
+    context = mm.Context(system, integrator, mm.Platform.getPlatformByName('B200'), properties)
+    replicas = 1 if dd else world
     context.setPositions(pos)
     context.setVelocities(vel)
     md = args.md_steps
@@ -239,7 +258,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed = float(t.item())
-    value = world*n*md*args.steps/elapsed
+    value = replicas*n*md*args.steps/elapsed
 
     # ---- end to end through the public API with host buffers --------------------------------------
     host_x = torch.from_numpy(pos.copy()).pin_memory()
@@ -257,17 +276,20 @@ def main():
         host_x.copy_(torch.from_numpy(s._positions))
         host_v.copy_(torch.from_numpy(s._velocities))
         return s._potential + s._kinetic
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        energy = e2e_step()
-    barrier()
-    e2e_elapsed = time.perf_counter() - t0
-    t = torch.tensor([e2e_elapsed], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world*n*md*e2e_steps/float(t.item())
+    energy = None
+    e2e_value = None
+    if not args.no_e2e:
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            energy = e2e_step()
+        barrier()
+        e2e_elapsed = time.perf_counter() - t0
+        t = torch.tensor([e2e_elapsed], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = replicas*n*md*e2e_steps/float(t.item())
     state_bytes = 2*n*3*8
 
     # ---- roofline of the dominant kernel: CUDA events around every pair launch, eager pass --------
@@ -292,12 +314,13 @@ def main():
                          'of the same step program with CUDA events on the launch stream')
 
     line = dict(metric='atom-steps/s', value=value, unit='atom-steps/s', n_gpus=world, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1e3*elapsed/args.steps, higher_is_better=True, scaling='weak',
+                warmup=args.warmup, ms_per_step=1e3*elapsed/args.steps, higher_is_better=True,
+                scaling='strong' if dd else 'weak',
                 vs_baseline=None, dtype='f32 pair forces / f64 state', data='synthetic',
                 config=workload_config(args, n, md), ns_per_day=md*args.steps*DT_FS*1e-6*86400/elapsed,
                 clocks=clocks, gpu_launches=int(launches),
-                e2e=dict(value=e2e_value, unit='atom-steps/s', h2d_bytes_per_step=state_bytes,
-                         d2h_bytes_per_step=state_bytes + 16, final_energy=energy),
+                e2e=(dict(value=e2e_value, unit='atom-steps/s', h2d_bytes_per_step=state_bytes,
+                          d2h_bytes_per_step=state_bytes + 16, final_energy=energy) if e2e_value is not None else None),
                 roofline=roofline, engine=dict(kernels_per_md_step=after['kernels_per_step'],
                                                list_rebuilds=after['rebuilds'], list_capacity=after['list_capacity']))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

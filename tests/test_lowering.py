@@ -65,8 +65,11 @@ def test_nose_hoover_block_is_one_velocity_kernel():
     assert kinds.count(lowering.OP_SUM) == 0 and kinds.count(lowering.OP_SCALE) == 0
     assert kinds.count(lowering.OP_GLOBAL) == 1
     reductions = [op for op in program.ops if op[0] == lowering.OP_KICK and op[5] >= 0]
-    assert len(reductions) == 6 and all(op[7] > 0 for op in reductions)
-    assert kinds.count(lowering.OP_KICK) == 9 + 6      # 9 RESPA kicks (one carries a reduction) + 5 bare + final scale
+    # ... and a Suzuki-Yoshida chain of 3 blocks shares ONE reduction (m*v*v scales by s*s), with the
+    # product of the three factors applied by the next velocity kernel
+    assert len(reductions) == 2 and all(op[7] > 100 for op in reductions)
+    assert kinds.count(lowering.OP_KICK) == 9 + 2      # 9 RESPA kicks + opening reduction + closing scale
+    assert '_vscale_product' in program.global_names
 
 
 def test_bussi_program_keeps_rejection_loop_on_device():
