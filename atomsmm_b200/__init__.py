@@ -44,6 +44,7 @@ from .propagators import TrotterSuzukiPropagator  # noqa: F401
 from .propagators import VelocityBoostPropagator  # noqa: F401
 from .propagators import VelocityRescalingPropagator  # noqa: F401
 from .propagators import VelocityVerletPropagator  # noqa: F401
+from .systems import AlchemicalSystem  # noqa: F401
 from .systems import ComputingSystem  # noqa: F401
 from .systems import RESPASystem  # noqa: F401
 from .utils import InputError  # noqa: F401

@@ -277,6 +277,7 @@ extern "C" int b2_add_pair_force(b2_context* ctx, int family, int group, int par
     pf.family = family; pf.group = group; pf.set = param_set; pf.cutoff = cutoff; pf.nparams = nparams;
     for (int k = 0; k < nparams; k++) pf.params[k] = params[k];
     pf.econst = energy_constant;
+    for (int k = 0; k < B2_MAX_PAIR_PARAMS; k++) pf.bind[k] = -1;
     // the list radius only needs to cover the range of the potential
     double range = cutoff;
     if (family == B2_PAIR_NEAR || family == B2_PAIR_DAMPED) range = std::min(range, params[2]);
@@ -296,6 +297,20 @@ extern "C" int b2_update_pair_force(b2_context* ctx, int handle, const double* p
     for (int k = 0; k < nparams; k++) pf.params[k] = params[k];
     pf.econst = energy_constant;
     for (int g = 0; g < B2_FSLOTS; g++) ctx->fvalid[g] = -1;
+    ctx->deriv_version = -1;
+    program_release(ctx);
+    return B2_OK;
+}
+
+extern "C" int b2_bind_pair_parameter(b2_context* ctx, int handle, int param, int global_index) {
+    if (!ctx || handle < 0 || handle >= (int)ctx->pair_forces.size()) return b2_fail(ctx, B2_ERR_ARG, "bad pair force handle");
+    PairForce& pf = ctx->pair_forces[handle];
+    if (pf.family != B2_PAIR_SOFTCORE || (param != 1 && param != 2))
+        return b2_fail(ctx, B2_ERR_UNSUPPORTED, "only the soft-core couplings (parameters 1, 2) can be bound to integrator globals");
+    if (global_index >= ctx->nglobals) return b2_fail(ctx, B2_ERR_ARG, "global index out of range");
+    pf.bind[param] = global_index;
+    for (int g = 0; g < B2_FSLOTS; g++) ctx->fvalid[g] = -1;
+    ctx->deriv_version = -1;
     program_release(ctx);
     return B2_OK;
 }
@@ -662,6 +677,8 @@ extern "C" int b2_load_program(b2_context* ctx, const int* ops, int nops, const 
     if (!ctx || ctx->n == 0) return b2_fail(ctx, B2_ERR_STATE, "set particles first");
     if (nperdof > B2_MAX_PERDOF) return b2_fail(ctx, B2_ERR_UNSUPPORTED, "at most %d per-DOF variables", B2_MAX_PERDOF);
     program_release(ctx);
+    for (PairForce& pf : ctx->pair_forces)
+        for (int k = 0; k < B2_MAX_PAIR_PARAMS; k++) pf.bind[k] = -1;
     ctx->ops.resize(nops);
     for (int k = 0; k < nops; k++) {
         const int* w = ops + (size_t)k*B2_OP_WORDS;

@@ -43,6 +43,7 @@ struct PairForce {
     int nparams;
     double params[B2_MAX_PAIR_PARAMS];
     double econst;
+    int bind[B2_MAX_PAIR_PARAMS];     // global-variable index a parameter is read from at run time, or -1
 };
 
 struct BondedForce {
@@ -110,6 +111,7 @@ struct b2_context {
     float4* fbuf[B2_FSLOTS] = {nullptr};
     long long fvalid[B2_FSLOTS];                  // position version for which fbuf[g] is valid
     long long pos_version = 1;
+    long long deriv_version = -1;                 // position version the parameter derivatives belong to
     std::vector<double*> perdof;
     double* scratch3 = nullptr;                   // [n][3] staging for permuted copies
 

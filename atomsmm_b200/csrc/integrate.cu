@@ -31,6 +31,8 @@ static PerDofTable make_table(b2_context* ctx) {
 
 __global__ void k_step_begin(unsigned long long* rng_state) { rng_state[2] += 1ull; }
 
+__global__ void k_fold_derivatives(double* e) { e[64] += e[74]; e[65] += e[75]; }
+
 __global__ void k_perdof(int dof_lo, int dof_hi, PerDofTable tab, int target, const int* __restrict__ code, int len,
                          const double* __restrict__ consts, double* globals,
                          const unsigned long long* __restrict__ rng_state, int serial, int mark_x) {
@@ -643,6 +645,29 @@ static int run_one_step(b2_context* ctx) {
             break;
         case B2_OP_UPDATE_STATE:
             break;
+        case B2_OP_INVALIDATE:
+            for (int g = 0; g < B2_FSLOTS; g++) ctx->fvalid[g] = -1;
+            ctx->deriv_version = -1;
+            break;
+        case B2_OP_ENERGY: {
+            if (ctx->deriv_version == ctx->pos_version) break;      // nothing moved since the last evaluation
+            ctx->deriv_version = ctx->pos_version;
+            B2_CUDA(cudaMemsetAsync(ctx->d_energy + 64, 0, 2*sizeof(double), s));
+            bool prepared = false;
+            for (const PairForce& pf : ctx->pair_forces) {
+                if (pf.family != B2_PAIR_SOFTCORE) continue;
+                if (!prepared) {
+                    B2_TRY(dist_sync_positions(ctx));
+                    B2_TRY(nl_prepare(ctx, false));
+                    prepared = true;
+                }
+                B2_TRY(pair_eval_energy(ctx, pf, pf.group));
+                B2_TRY(dist_allreduce(ctx, ctx->d_energy + 72, 4));
+                k_fold_derivatives<<<1, 1, 0, s>>>(ctx->d_energy);
+                B2_LAUNCH_CHECK();
+            }
+            break;
+        }
         default:
             return b2_fail(ctx, B2_ERR_UNSUPPORTED, "unknown program op %d", op.kind);
         }

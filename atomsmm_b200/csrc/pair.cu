@@ -23,7 +23,7 @@
 #define WPB 4   // warps per block
 
 template <typename T>
-static PotParams<T> make_params(const PairForce& pf, float* rc2_out) {
+static PotParams<T> make_params(const b2_context* ctx, const PairForce& pf, float* rc2_out) {
     PotParams<T> p;
     memset(&p, 0, sizeof(p));
     p.sign = T(1);
@@ -81,6 +81,9 @@ static PotParams<T> make_params(const PairForce& pf, float* rc2_out) {
         // Kc, lambda_vdw, lambda_coul, use_switch, rswitch, rcut
         p.kc = T(a[0]); p.lam_v = T(a[1]); p.lam_c = T(a[2]);
         set_switch(a[3] != 0.0, a[4], a[5]);
+        p.gmode = T(pf.nparams > 6 ? a[6] : 0.0);
+        if (ctx->globals && pf.bind[1] >= 0) p.lam_v_dev = ctx->globals + pf.bind[1];
+        if (ctx->globals && pf.bind[2] >= 0) p.lam_c_dev = ctx->globals + pf.bind[2];
         break;
     }
     }
@@ -431,8 +434,8 @@ struct DoubleOf<SoftcorePot<float>> { typedef SoftcorePot<double> type; };
 
 int pair_eval_forces(b2_context* ctx, const PairForce& pf, float4* out, bool accumulate) {
     float rc2, unused;
-    PotParams<float> p = make_params<float>(pf, &rc2);
-    PotParams<double> pd = make_params<double>(pf, &unused);
+    PotParams<float> p = make_params<float>(ctx, pf, &rc2);
+    PotParams<double> pd = make_params<double>(ctx, pf, &unused);
 #define CALL_FORCE { typename DoubleOf<decltype(pot)>::type potd{pd}; B2_TRY(launch_force(ctx, pf, pot, potd, rc2, out, accumulate)); }
     DISPATCH(float, CALL_FORCE, CALL_FORCE);
 #undef CALL_FORCE
@@ -441,7 +444,7 @@ int pair_eval_forces(b2_context* ctx, const PairForce& pf, float4* out, bool acc
 
 int pair_eval_energy(b2_context* ctx, const PairForce& pf, int group) {
     float rc2f;
-    PotParams<double> p = make_params<double>(pf, &rc2f);
+    PotParams<double> p = make_params<double>(ctx, pf, &rc2f);
     double rc = pf.cutoff;
     if (pf.family == B2_PAIR_NEAR) rc = std::min(rc, pf.params[2]);
     if (pf.family == B2_PAIR_DAMPED) rc = std::min(rc, pf.params[2]);

@@ -60,6 +60,10 @@ struct PotParams {
     T inv_rc0;       // 1/rc0 (shift variant)
     T b, f12c, f6c, f1c, c12, c6, c1;   // force-switch energy constants (forces.py:552-563)
     T lam_v, lam_c;  // soft-core
+    T gmode;         // soft-core: 1 = interaction-group mode, charges are +-1 set labels and only pairs of
+                     // unlike labels interact (OpenMM addInteractionGroup(A, complement of A))
+    const double* lam_v_dev;   // when not null the couplings are read from device memory at run time:
+    const double* lam_c_dev;   // integrator globals (AFED extended variables), no host round trip
 };
 
 template <typename T>
@@ -177,24 +181,32 @@ struct SoftcorePot {
     }
 
     __device__ __forceinline__ void eval(T r2, T qq, T sig, T eps, T& rF, T& e, T& dEdlv, T& dEdlc) const {
+        const T lam_v = p.lam_v_dev ? T(*p.lam_v_dev) : p.lam_v;
+        const T lam_c = p.lam_c_dev ? T(*p.lam_c_dev) : p.lam_c;
+        T pair_scale = T(1);
+        if (p.gmode != T(0)) {            // qq = +1 (same set: no interaction) or -1 (solute-solvent)
+            pair_scale = T(0.5)*(T(1) - qq);
+            qq = T(0);
+        }
         const T rinv = b2_rsqrt(r2);
         const T r = r2*rinv;
         const T is2 = T(1)/(sig*sig);
         const T q2 = r2*is2;
         const T r6s = q2*q2*q2;
-        const T x = r6s + T(0.5)*(T(1) - p.lam_v);
+        const T x = r6s + T(0.5)*(T(1) - lam_v);
         const T ix = T(1)/x;
         const T g = (T(1) - x)*ix*ix;              // (1-x)/x^2
         const T dg = (x - T(2))*ix*ix*ix;          // d/dx
-        const T elj = T(4)*p.lam_v*eps*g;
-        const T rflj = -T(4)*p.lam_v*eps*dg*T(6)*r6s;
-        const T ec = p.kc*p.lam_c*qq*rinv;
+        const T elj = T(4)*lam_v*eps*g;
+        const T rflj = -T(4)*lam_v*eps*dg*T(6)*r6s;
+        const T ec = p.kc*lam_c*qq*rinv;
         T S = T(1), rdS = T(0);
         if (p.iw != T(0)) switch_eval(p, SWF_LINEAR, r, r2, S, rdS);
         const T V = elj + ec;
         rF = S*(rflj + ec) - rdS*V;
         e = S*V;
-        dEdlv = S*(T(4)*eps*g - T(2)*p.lam_v*eps*dg);
+        dEdlv = S*(T(4)*eps*g - T(2)*lam_v*eps*dg);
         dEdlc = S*p.kc*qq*rinv;
+        rF *= pair_scale; e *= pair_scale; dEdlv *= pair_scale; dEdlc *= pair_scale;
     }
 };

@@ -28,11 +28,14 @@ enum {
     B2_OP_SCALE = 7,
     // UpdateContextState hook (no-op: no barostat / CMMotionRemover in the engine yet)
     B2_OP_UPDATE_STATE = 8,
-    // energies of groups in mask a -> device energy slots (used by `energy` / deriv(energy,.))
+    // dE/d(parameter) of the soft-core pair forces -> device energy slots 64 (lambda_vdw) and 65
+    // (lambda_coul), read by VM_PUSHE: the `deriv(energy, lambda)` of AFED (integrators.py:735-737)
     B2_OP_ENERGY = 9,
     // fused RESPA inner loop: see integrate.cu.  a: iterations, b: g-index of kick coefficient,
     //   c: g-index of drift coefficient, d: force slot of the inner group
     B2_OP_FUSED_INNER = 10,
+    // a scalar program has moved a context parameter that forces depend on: every cached force is stale
+    B2_OP_INVALIDATE = 11,
 };
 
 // VM opcodes (two ints per instruction: opcode, argument)

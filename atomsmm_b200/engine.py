@@ -39,6 +39,7 @@ _SIGNATURES = {
     'b2_add_pair_force': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_double_p,
                           ctypes.c_int, ctypes.c_double, c_int_p],
     'b2_update_pair_force': [c_void, ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_double],
+    'b2_bind_pair_parameter': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int],
     'b2_add_bonded_force': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p, c_double_p, ctypes.c_int,
                             ctypes.c_int, c_double_p, ctypes.c_int, c_int_p],
     'b2_add_custom_bonded_force': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p, c_double_p,
@@ -337,6 +338,14 @@ class Context(object):
                     raise mm.OpenMMException('CustomNonbondedForce must have exactly as many particles as the System')
                 family, cutoff, params, info = lowering.classify_pair_force(force, self._parameters)
                 table = np.array(force._particles, dtype=np.float64).reshape(n, -1)
+                if table.shape[1] == 2:
+                    # (sigma, epsilon) only; with an interaction group the charge column carries the
+                    # +1/-1 set labels the soft-core kernel uses to keep only unlike pairs
+                    labels = np.zeros(n)
+                    if info.get('partition') is not None:
+                        labels[:] = -1.0
+                        labels[info['partition']] = 1.0
+                    table = np.concatenate([labels[:, None], table], axis=1)
                 pairs = frozenset((min(i, j), max(i, j)) for i, j in force._exclusions)
                 exclusions = self._merge_exclusions(exclusions, pairs)
                 set_id = self._param_set(table[:, 0], table[:, 1], table[:, 2])
@@ -511,10 +520,15 @@ class Context(object):
         if not isinstance(integrator, mm.CustomIntegrator):
             self._program = None
             return
-        if self._has_constraints and integrator.getNumComputations() > 0:
-            raise lowering.UnsupportedDescription('Systems with distance constraints cannot be integrated yet '
-                                                  '(SHAKE/RATTLE/SETTLE are not implemented)')
-        program = lowering.lower_program(integrator, self._all_groups, self._parameters, self._fast)
+        derivative_slots = {}
+        for _, info, force in self._pair_handles.values():
+            if info.get('name') == 'softcore':
+                if info.get('lambda_vdw'):
+                    derivative_slots[info['lambda_vdw']] = lowering.ENERGY_SLOT_DLAMBDA_VDW
+                if info.get('lambda_coul'):
+                    derivative_slots[info['lambda_coul']] = lowering.ENERGY_SLOT_DLAMBDA_COUL
+        program = lowering.lower_program(integrator, self._all_groups, self._parameters, self._fast,
+                                         constrained=self._has_constraints, derivative_slots=derivative_slots)
         self._program = program
         ops = program.packed_ops()
         code = np.array(program.bc.code if program.bc.code else [0, 0], dtype=np.int32)
@@ -523,6 +537,17 @@ class Context(object):
         self._call('b2_load_program', _iptr(ops), len(ops), _iptr(code), len(program.bc.code), _dptr(consts),
                    len(program.bc.consts), _dptr(values), len(values), len(program.perdof_names),
                    ctypes.c_uint64(integrator.getRandomNumberSeed() & 0xffffffffffffffff))
+        # context parameters the integrator moves itself (AFED): the pair kernels read them on the device
+        self._device_parameters = set()
+        assigned = set(integrator.getComputationStep(k)[1] for k in range(integrator.getNumComputations()))
+        for handle, info, force in self._pair_handles.values():
+            if info.get('name') != 'softcore':
+                continue
+            for slot, key in ((1, 'lambda_vdw'), (2, 'lambda_coul')):
+                name = info.get(key)
+                if name and name in assigned and name in program.global_names:
+                    self._call('b2_bind_pair_parameter', handle, slot, program.gindex(name))
+                    self._device_parameters.add(name)
         for k, value in enumerate(integrator._perdof_values):
             if not np.isscalar(value) and self._have_positions:
                 self._set_perdof(integrator._perdof_names[k], value)
@@ -589,9 +614,13 @@ class Context(object):
         return [tuple(g) for g in self._molecule_groups]
 
     def getParameter(self, name):
+        if name in getattr(self, '_device_parameters', ()):
+            self._parameters[name] = self._get_global(name)     # moved by the integrator on the device
         return self._parameters[name]
 
     def getParameters(self):
+        for name in getattr(self, '_device_parameters', ()):
+            self._parameters[name] = self._get_global(name)
         return dict(self._parameters)
 
     def setParameter(self, name, value):
@@ -687,7 +716,7 @@ class Context(object):
         if need_state and not self._have_positions:
             raise mm.OpenMMException('Particle positions have not been set')
         fields = dict(_positions=None, _velocities=None, _forces=None, _potential=None, _kinetic=None,
-                      _box=self._box.copy(), _parameters=self._parameters if getParameters else {},
+                      _box=self._box.copy(), _parameters=self.getParameters() if getParameters else {},
                       _derivatives={}, _time=self._time)
         with torch.cuda.stream(self._stream):
             if getPositions:

@@ -26,7 +26,8 @@ from . import mm
 PAIR_NEAR, PAIR_DAMPED, PAIR_LJC, PAIR_LJ_VIRIAL, PAIR_SOFTCORE = 1, 2, 3, 4, 5
 BOND_HARMONIC, ANGLE_HARMONIC, TORSION_PERIODIC, BOND_LJC, BOND_CUSTOM, ANGLE_CUSTOM = 1, 2, 3, 4, 5, 6
 (OP_PERDOF, OP_SUM, OP_GLOBAL, OP_EVAL, OP_KICK, OP_DRIFT, OP_SCALE, OP_UPDATE_STATE, OP_ENERGY,
- OP_FUSED_INNER) = range(1, 11)
+ OP_FUSED_INNER, OP_INVALIDATE) = range(1, 12)
+ENERGY_SLOT_DLAMBDA_VDW, ENERGY_SLOT_DLAMBDA_COUL = 64, 65
 OP_WORDS = 8
 
 
@@ -114,13 +115,21 @@ def _matches(user, closed, radii, tol=2e-7):
 def classify_pair_force(force, parameters=None):
     """Return (family, cutoff, params, info) for a CustomNonbondedForce description."""
     names = [force.getPerParticleParameterName(k) for k in range(force.getNumPerParticleParameters())]
-    if names != ['charge', 'sigma', 'epsilon']:
-        raise UnsupportedDescription('per-particle parameters %r: only (charge, sigma, epsilon) without '
-                                     'parameter offsets are supported on the hot path' % (names,))
+    if names not in (['charge', 'sigma', 'epsilon'], ['sigma', 'epsilon']):
+        raise UnsupportedDescription('per-particle parameters %r: only (charge, sigma, epsilon) or (sigma, epsilon) '
+                                     'without parameter offsets are supported on the hot path' % (names,))
     if force.getNonbondedMethod() != mm.CustomNonbondedForce.CutoffPeriodic:
         raise UnsupportedDescription('pair forces must use CutoffPeriodic')
+    partition = None
     if force.getNumInteractionGroups() > 0:
-        raise UnsupportedDescription('interaction groups are not supported')
+        # the one shape atomsmm builds (systems.py:392): a set of atoms against its complement
+        if force.getNumInteractionGroups() != 1:
+            raise UnsupportedDescription('only a single interaction group is supported')
+        set1, set2 = force.getInteractionGroupParameters(0)
+        everything = set(range(force.getNumParticles()))
+        if set(set1) & set(set2) or set(set1) | set(set2) != everything:
+            raise UnsupportedDescription('interaction groups must be a set of atoms against its complement')
+        partition = sorted(set1)
     globals_ = {force.getGlobalParameterName(k): force.getGlobalParameterDefaultValue(k)
                 for k in range(force.getNumGlobalParameters())}
     if parameters:
@@ -180,8 +189,13 @@ def classify_pair_force(force, parameters=None):
             closed = lambda r, qq, s, e: softcore_closed_form(r, qq, s, e, k, lam_v, lam_c)
             samples_ok = _matches(user, closed, radii, 2e-9)
             if samples_ok:
-                return PAIR_SOFTCORE, cutoff, [k, lam_v, lam_c, 1.0 if omm_switch else 0.0, rswitch, cutoff], \
-                    dict(name='softcore', lambda_vdw=lv, lambda_coul=lc)
+                if partition is not None and k != 0.0:
+                    raise UnsupportedDescription('interaction groups are only supported without a Coulomb term')
+                return PAIR_SOFTCORE, cutoff, [k, lam_v, lam_c, 1.0 if omm_switch else 0.0, rswitch, cutoff,
+                                               1.0 if partition is not None else 0.0], \
+                    dict(name='softcore', lambda_vdw=lv, lambda_coul=lc, partition=partition)
+    if partition is not None:
+        raise UnsupportedDescription('interaction groups are only supported for the soft-core family')
     # --- plain LJ + Coulomb ------------------------------------------------------------------
     if kc is not None:
         closed = lambda r, qq, s, e: _ljc(r, qq, s, e, kc)
@@ -379,7 +393,8 @@ class Program(object):
         return np.array(self.ops, dtype=np.int32).reshape(-1, OP_WORDS)
 
 
-def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=True):
+def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=True, constrained=True,
+                  derivative_slots=None):
     """CustomIntegrator description -> Program (ops + bytecode + initial globals)."""
     P = Program()
     P.global_values[0] = integrator._dt
@@ -391,7 +406,12 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
     P.perdof_names = [integrator.getPerDofVariableName(k) for k in range(integrator.getNumPerDofVariables())]
     steps = [tuple(integrator.getComputationStep(k)) for k in range(integrator.getNumComputations())]
     if any(s[0] in (CI.ConstrainPositions, CI.ConstrainVelocities) for s in steps):
-        raise UnsupportedDescription('distance constraints (SHAKE/RATTLE) are not implemented in this engine yet')
+        if constrained:
+            raise UnsupportedDescription('distance constraints (SHAKE/RATTLE) are not implemented in this engine yet')
+        # a System without constraints: constraining positions / velocities does nothing
+        steps = [s for s in steps if s[0] not in (CI.ConstrainPositions, CI.ConstrainVelocities)]
+    context_parameters = set(parameters or {})
+    derivative_slots = dict(derivative_slots or {})
     body = _unroll(_tree(steps).body)
     body = _fold_force_copies(body, P)
     body, dead_stores = _strip_dead_constant_stores(body)
@@ -418,6 +438,11 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
             return 'UNIF', 0
         if name in P.global_names:
             return 'PUSHG', P.gindex(name)
+        if name.startswith('__dE_'):
+            if name[5:] not in derivative_slots:
+                raise UnsupportedDescription('deriv(energy, %s): no force of the System has a derivative with '
+                                             'respect to this parameter' % name[5:])
+            return 'PUSHE', derivative_slots[name[5:]]
         raise UnsupportedDescription('unknown variable %r in integrator expression' % name)
 
     def resolve_global(name):
@@ -499,7 +524,34 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
         return True
 
     def lower_global_run(items):
-        """Consecutive global statements and global-only blocks -> one scalar-VM op."""
+        """Consecutive global statements and global-only blocks -> one scalar-VM op.  A run is cut at
+        statements that read deriv(energy, p) (the derivative must be evaluated first, with the
+        parameters as they are at that point) and after statements that move a context parameter
+        (forces depend on it)."""
+        pieces, current = [], []
+        for item in items:
+            flat = not isinstance(item, _Block)
+            reads = flat and 'deriv(' in item[2]
+            writes = (item[1] in context_parameters) if flat else bool(_assigned(item.body) & context_parameters)
+            if not flat and any('deriv(' in t for t in _block_texts(item)):
+                raise UnsupportedDescription('deriv(energy, .) inside an if/while block is not supported')
+            if reads and current:
+                pieces.append((current, False, False))
+                current = []
+            current.append(item)
+            if reads or writes:
+                pieces.append((current, reads, writes))
+                current = []
+        if current:
+            pieces.append((current, False, False))
+        for piece, reads, writes in pieces:
+            if reads:
+                P.op(OP_ENERGY)
+            _lower_global_piece(piece)
+            if writes:
+                P.op(OP_INVALIDATE)
+
+    def _lower_global_piece(items):
         start = len(P.bc.code)
         base = start//2
 
@@ -524,7 +576,7 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
                     _, variable, expression = item
                     if variable not in P.global_names:
                         raise UnsupportedDescription('assignment to unknown global %r' % variable)
-                    X.compile_ast(X.parse_inlined(expression), resolve_global, P.bc)
+                    X.compile_ast(_replace_deriv(X.parse_inlined(expression)), resolve_global, P.bc)
                     P.bc.emit('STOREG', P.gindex(variable))
         emit_items(items)
         del base
@@ -592,6 +644,27 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
 
 
 MAX_KICK_TERMS = 6
+
+
+def _replace_deriv(node):
+    """deriv(energy, p) -> pseudo variable __dE_p (resolved to a VM_PUSHE of the derivative slot)."""
+    if not isinstance(node, tuple):
+        return node
+    if node[0] == 'call' and node[1] == 'deriv':
+        target, parameter = node[2]
+        if target != ('var', 'energy') or parameter[0] != 'var':
+            raise UnsupportedDescription('only deriv(energy, parameter) is supported')
+        return ('var', '__dE_' + parameter[1])
+    if node[0] == 'call':
+        return ('call', node[1], [_replace_deriv(a) for a in node[2]])
+    return tuple(_replace_deriv(c) if isinstance(c, tuple) else c for c in node)
+
+
+def _block_texts(block):
+    out = [block.condition]
+    for item in block.body:
+        out += _block_texts(item) if isinstance(item, _Block) else [item[2]]
+    return out
 
 
 def _fuse_kicks(P):

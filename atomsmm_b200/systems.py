@@ -4,9 +4,10 @@ System builders: ``RESPASystem`` (force-group layout for multiple-time-scale int
 
 Same names, arguments and resulting force-group layout as the reference's
 ``atomsmm.systems`` (reference: src/atomsmm/systems.py:34-238, 868-944; rows a8/a9 of
-SURVEY 8a).  The alchemical builders of the reference (SolvationSystem, AlchemicalSystem,
-AlchemicalRespaSystem) are system-construction bookkeeping outside the hot path and are not
-provided.
+SURVEY 8a).  ``AlchemicalSystem`` (systems.py:318-410) is provided with its default ``softcore``
+coupling because it is the system of the AFED configuration (BASELINE config 4, row a20); the other
+alchemical builders of the reference (SolvationSystem, AlchemicalRespaSystem and the
+non-softcore couplings) are system-construction bookkeeping outside the hot path and are not provided.
 """
 
 import copy
@@ -135,6 +136,71 @@ class RESPASystem(mm.System):
             self._special_angle_force = special
         for i, j, k, theta0, K0 in changed:
             self._special_angle_force.addAngle(i, j, k, (theta0, K0, angle, K0 if K is None else K))
+
+
+class AlchemicalSystem(mm.System):
+    """A copy of ``system`` prepared for solvation free-energy / AFED runs (systems.py:318-410).
+
+    The solute ``atoms`` are decoupled from the NonbondedForce (charge and epsilon zeroed, their
+    mutual interactions kept as exceptions) and re-coupled to the rest of the system through a
+    CustomNonbondedForce restricted to solute-solvent pairs by an interaction group, with the
+    Beutler soft core ``4*lambda_vdw*epsilon*(1-x)/x^2; x=(r/sigma)^6+0.5*(1-lambda_vdw)`` and an
+    energy derivative with respect to the context parameter ``lambda_vdw``.
+    """
+
+    def __init__(self, system, atoms, coupling='softcore', group=0, use_lrc=False):
+        import itertools
+        import math
+        super().__init__()
+        self._adopt(system)
+        from .utils import findNonbondedForce, InputError
+        if coupling != 'softcore':
+            raise InputError('only the softcore coupling is available on the B200 engine')
+        atoms = set(int(i) for i in atoms)
+        nonbonded = self.getForce(findNonbondedForce(self))
+        potential = 'U_softcore'
+        potential += '; U_softcore = 4*lambda_vdw*epsilon*(1 - x)/x^2'
+        potential += '; x = (r/sigma)^6 + 0.5*(1 - lambda_vdw)'
+        potential += '; sigma = 0.5*(sigma1 + sigma2)'
+        potential += '; epsilon = sqrt(epsilon1*epsilon2)'
+        softcore = mm.CustomNonbondedForce(potential)
+        if nonbonded.getNonbondedMethod() == mm.NonbondedForce.NoCutoff:
+            softcore.setNonbondedMethod(mm.CustomNonbondedForce.NoCutoff)
+        else:
+            softcore.setNonbondedMethod(mm.CustomNonbondedForce.CutoffPeriodic)
+        softcore.setCutoffDistance(nonbonded.getCutoffDistance())
+        softcore.setUseSwitchingFunction(nonbonded.getUseSwitchingFunction())
+        softcore.setSwitchingDistance(nonbonded.getSwitchingDistance())
+        softcore.setUseLongRangeCorrection(use_lrc)
+        softcore.addGlobalParameter('lambda_vdw', 1.0)
+        softcore.addPerParticleParameter('sigma')
+        softcore.addPerParticleParameter('epsilon')
+        all_atoms = range(nonbonded.getNumParticles())
+        for index in all_atoms:
+            _, sigma, epsilon = nonbonded.getParticleParameters(index)
+            softcore.addParticle([sigma, epsilon])
+        for index in range(nonbonded.getNumExceptions()):
+            i, j = nonbonded.getExceptionParameters(index)[:2]
+            softcore.addExclusion(i, j)
+        softcore.addInteractionGroup(atoms, set(all_atoms) - atoms)
+        softcore.setForceGroup(group)
+        softcore.addEnergyParameterDerivative('lambda_vdw')
+        self.addForce(softcore)
+        parameters = {}
+        for i in atoms:
+            parameters[i] = nonbonded.getParticleParameters(i)
+            nonbonded.setParticleParameters(i, 0.0, 1.0, 0.0)
+        exception_pairs = []
+        for index in range(nonbonded.getNumExceptions()):
+            i, j = nonbonded.getExceptionParameters(index)[:2]
+            if {i, j} <= atoms:
+                exception_pairs.append({i, j})
+        for i, j in itertools.combinations(sorted(atoms), 2):
+            if {i, j} not in exception_pairs:
+                q1, sig1, eps1 = [unit.md_value(v) for v in parameters[i]]
+                q2, sig2, eps2 = [unit.md_value(v) for v in parameters[j]]
+                nonbonded.addException(i, j, q1*q2, (sig1 + sig2)/2, math.sqrt(eps1*eps2))
+                softcore.addExclusion(i, j)  # keeps the exclusion list equal to the exception list
 
 
 class ComputingSystem(_AtomsMM_System):

@@ -61,7 +61,8 @@ enum {
      * (systems.py:894-898).  params: use_switch, rswitch, rcut */
     B2_PAIR_LJ_VIRIAL = 4,
     /* SoftcoreForce / SoftcoreLennardJonesForce (forces.py:727-793).  params: Kc, lambda_vdw,
-     * lambda_coul, use_switch, rswitch, rcut, form (0: (1-x)/x^2 ; 1: x*(x-1) with x=1/(..)) */
+     * lambda_coul, use_switch, rswitch, rcut, group_mode (1: the charges are +1/-1 labels of an
+     * interaction group A x complement(A), systems.py:392; only unlike pairs interact) */
     B2_PAIR_SOFTCORE = 5
 };
 
@@ -114,6 +115,12 @@ B2_API int b2_add_pair_force(b2_context* ctx, int family, int group, int param_s
 /* updateParametersInContext / Context.setParameter for a pair force */
 B2_API int b2_update_pair_force(b2_context* ctx, int handle, const double* params, int nparams,
                          double energy_constant);
+/* A context parameter that the integrator itself moves (AFED extended variables,
+ * integrators.py:670-744: `lambda <- lambda + 0.5*dt*v_lambda` is a ComputeGlobal on a context
+ * parameter): from now on parameter `param` of pair force `handle` (1 = lambda_vdw, 2 = lambda_coul of
+ * B2_PAIR_SOFTCORE) is read on the device from global variable `global_index` of the loaded program
+ * at every evaluation.  Call after b2_load_program (which clears all bindings). */
+B2_API int b2_bind_pair_parameter(b2_context* ctx, int handle, int param, int global_index);
 /* HarmonicBondForce / HarmonicAngleForce / PeriodicTorsionForce / CustomBondForce.addBond
  * (forces.py:384-388).  atoms: arity*nterms indices; params: stride*nterms doubles;
  * gparams: family globals. */

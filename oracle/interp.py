@@ -70,11 +70,27 @@ class Interpreter(object):
     def kinetic_energy(self):
         return 0.5*float(np.sum(self.mass*self.v*self.v))
 
+    def energy_derivative(self, name, h=1e-6):
+        """deriv(energy, name): central difference of the float64 potential energy (the energy is a
+        smooth function of the context parameters atomsmm differentiates; error ~1e-9 relative)."""
+        key = ('deriv', name, self._version, self.parameters.get(name))
+        if key not in self._force_cache:
+            base = dict(self.parameters)
+            value = float(base[name])
+            up = refmath.evaluate_system(self.system, self.x, self.box, None, dict(base, **{name: value + h})).energy
+            dn = refmath.evaluate_system(self.system, self.x, self.box, None, dict(base, **{name: value - h})).energy
+            self._force_cache[key] = (up - dn)/(2*h)
+        return self._force_cache[key]
+
     def _compile(self, text):
         if text not in self._compiled:
+            # deriv(energy, p) -> a pseudo variable resolved by energy_derivative
+            text_in = text
+            text = re.sub(r'deriv\(\s*energy\s*,\s*([A-Za-z_]\w*)\s*\)', r'__dE_\1', text)
             expression = refmath.parse_energy(text)
             symbols = sorted(expression.free_symbols, key=lambda s: s.name)
-            self._compiled[text] = ([s.name for s in symbols], refmath._lambdify(symbols, expression))
+            self._compiled[text_in] = ([s.name for s in symbols], refmath._lambdify(symbols, expression))
+            return self._compiled[text_in]
         return self._compiled[text]
 
     def _value(self, name, per_dof):
@@ -97,6 +113,8 @@ class Interpreter(object):
             return self.globals[name]
         if name in self.parameters:
             return self.parameters[name]
+        if name.startswith('__dE_'):
+            return self.energy_derivative(name[5:])
         raise KeyError('unknown variable %r' % name)
 
     def _evaluate(self, text, per_dof):
@@ -137,12 +155,16 @@ class Interpreter(object):
                     if variable in self.globals:
                         self.globals[variable] = value
                     else:
+                        if self.parameters.get(variable) != value:
+                            self._force_cache = {}      # forces depend on context parameters
                         self.parameters[variable] = value
                 elif kind == 2:    # sum
                     value = np.broadcast_to(self._evaluate(expression, True), (self.n, 3))
                     self.globals[variable] = float(np.sum(value))
                 elif kind in (3, 4):
-                    raise NotImplementedError('constraints')
+                    if self.system.getNumConstraints() > 0:
+                        raise NotImplementedError('constraints')
+                    # a System without constraints: nothing to do
                 elif kind == 6:
                     if not self._condition(expression):
                         pc = self._end[pc]

@@ -195,6 +195,17 @@ def eval_custom_nonbonded(force, pos, box, params=None, want_pairs=False):
     i, j, d, r = all_pairs(pos, box, cutoff, periodic)
     excl = [force.getExclusionParticles(k) for k in range(force.getNumExclusions())]
     keep = _exclusion_filter(n, i, j, excl)
+    # interaction groups (OpenMM CustomNonbondedForce.addInteractionGroup): a pair interacts iff one
+    # atom is in set1 and the other in set2 of some group (reference call site: systems.py:392)
+    ngroups = force.getNumInteractionGroups() if hasattr(force, 'getNumInteractionGroups') else 0
+    if ngroups:
+        allowed = np.zeros(len(i), bool)
+        for g in range(ngroups):
+            set1, set2 = force.getInteractionGroupParameters(g)
+            in1 = np.zeros(n, bool); in1[list(set1)] = True
+            in2 = np.zeros(n, bool); in2[list(set2)] = True
+            allowed |= (in1[i] & in2[j]) | (in2[i] & in1[j])
+        keep &= allowed
     i, j, d, r = i[keep], j[keep], d[keep], r[keep]
     args = [r] + [table[i, k] for k in range(len(names))] + [table[j, k] for k in range(len(names))]
     e = np.broadcast_to(fe(*args), r.shape).astype(float)

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import atomsmm_b200 as atomsmm
-from atomsmm_b200 import lowering, mm, unit
+from atomsmm_b200 import app, lowering, mm, unit
 
 import systems
 
@@ -91,3 +91,51 @@ def test_constraints_are_refused():
     integrator = atomsmm.GlobalThermostatIntegrator(1*fs, atomsmm.VelocityVerletPropagator())
     with pytest.raises(lowering.UnsupportedDescription):
         lowering.lower_program(integrator, 1)
+
+
+def test_afed_program_lowering():
+    """AdiabaticDynamicsIntegrator on an AlchemicalSystem: deriv(energy, lambda) becomes a derivative
+    evaluation + VM_PUSHE, moving lambda invalidates the cached forces, constraint steps of an
+    unconstrained System vanish (integrators.py:735-737,782-860; systems.py:318-410)."""
+    from atomsmm_b200 import mm
+    pdb, ff = systems.fixtures.load('methane-in-water')
+    system = ff.createSystem(pdb.topology, nonbondedMethod=app.CutoffPeriodic, constraints=None, rigidWater=False)
+    alchemical = atomsmm.AlchemicalSystem(system, {0})
+    softcore = [f for f in alchemical.getForces() if isinstance(f, mm.CustomNonbondedForce)][0]
+    family, cutoff, params, info = lowering.classify_pair_force(softcore, {'lambda_vdw': 0.7})
+    assert family == lowering.PAIR_SOFTCORE and params[1] == 0.7 and params[6] == 1.0 and info['partition'] == [0]
+    nvt = atomsmm.TrotterSuzukiPropagator(
+        atomsmm.VelocityVerletPropagator(),
+        atomsmm.NoseHooverPropagator(300*K, atomsmm.countDegreesOfFreedom(alchemical), 10*fs)).integrator(1*fs)
+    variable = atomsmm.ExtendedSystemVariable('lambda_vdw', 1000, 5, 40*fs)
+    integrator = atomsmm.AdiabaticDynamicsIntegrator(nvt, 2, [variable])
+    with pytest.raises(lowering.UnsupportedDescription):
+        lowering.lower_program(integrator, 1, {'lambda_vdw': 1.0}, True, constrained=True)
+    program = lowering.lower_program(integrator, 1, {'lambda_vdw': 1.0}, True, constrained=False,
+                                     derivative_slots={'lambda_vdw': lowering.ENERGY_SLOT_DLAMBDA_VDW})
+    kinds = [op[0] for op in program.ops]
+    assert kinds.count(lowering.OP_ENERGY) == 8           # one per lambda kick: 2 per inner iteration x 4
+    assert kinds.count(lowering.OP_INVALIDATE) == 4       # two half moves of lambda, each with a wall check
+    assert 35 in program.bc.code[::2]                     # VM_PUSHE
+    with pytest.raises(lowering.UnsupportedDescription):  # nobody provides d/d(lambda) of the energy
+        lowering.lower_program(integrator, 1, {'lambda_vdw': 1.0}, True, constrained=False)
+
+
+def test_alchemical_system_oracle_interaction_group():
+    """The soft-core force only couples the solute to the solvent, and at lambda = 1 it is plain LJ."""
+    from oracle import refmath
+    from atomsmm_b200 import mm
+    pdb, ff = systems.fixtures.load('methane-in-water')
+    system = ff.createSystem(pdb.topology, nonbondedMethod=app.CutoffPeriodic, constraints=None, rigidWater=False)
+    alchemical = atomsmm.AlchemicalSystem(system, {0})
+    index = [k for k, f in enumerate(alchemical.getForces()) if isinstance(f, mm.CustomNonbondedForce)][0]
+    pos = systems.positions_of(pdb)
+    result = refmath.eval_custom_nonbonded(alchemical.getForce(index), pos, refmath.system_box(alchemical),
+                                           {'lambda_vdw': 1.0}, want_pairs=True)
+    i, j, r = result.pairs
+    assert len(i) > 50 and np.all((i == 0) ^ (j == 0))
+    nb = system.getForce(atomsmm.findNonbondedForce(system))
+    table = np.array([[v.value_in_md_units() for v in nb.getParticleParameters(k)] for k in range(len(pos))])
+    sig = 0.5*(table[i, 1] + table[j, 1])
+    eps = np.sqrt(table[i, 2]*table[j, 2])
+    assert result.energy == pytest.approx(float(np.sum(4*eps*((sig/r)**12 - (sig/r)**6))), rel=1e-12)
