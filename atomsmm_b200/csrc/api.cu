@@ -104,6 +104,7 @@ extern "C" int b2_create(int device, b2_context** out) {
         cudaMalloc(&ctx->rng_state, sizeof(unsigned long long)*4) != cudaSuccess ||
         cudaMalloc(&ctx->sum_partial, sizeof(double)*1024) != cudaSuccess ||
         cudaMalloc(&ctx->ticket, sizeof(unsigned)*4) != cudaSuccess ||
+        cudaMalloc(&ctx->nl_flags, sizeof(int)*16) != cudaSuccess ||
         cudaMalloc(&ctx->band_pairs, sizeof(int)*2*ctx->band_capacity) != cudaSuccess ||
         cudaMalloc(&ctx->band_count, sizeof(unsigned)) != cudaSuccess) {
         delete ctx;
@@ -112,6 +113,7 @@ extern "C" int b2_create(int device, b2_context** out) {
     cudaMemset(ctx->d_energy, 0, sizeof(double)*96);
     cudaMemset(ctx->rng_state, 0, sizeof(unsigned long long)*4);
     cudaMemset(ctx->ticket, 0, sizeof(unsigned)*4);
+    cudaMemset(ctx->nl_flags, 0, sizeof(int)*16);
     ctx->sum_partial_size = 1024;
     *out = ctx;
     return B2_OK;
@@ -140,6 +142,7 @@ extern "C" int b2_destroy(b2_context* ctx) {
     cudaFree(ctx->globals); cudaFree(ctx->sum_partial); cudaFree(ctx->rng_state);
     cudaFree(ctx->band_pairs); cudaFree(ctx->band_count); cudaFree(ctx->ticket);
     cudaFree(ctx->chunk_start); cudaFree(ctx->chunk_term_ptr); cudaFree(ctx->chunk_terms);
+    cudaFree(ctx->con_ptr); cudaFree(ctx->con_pairs); cudaFree(ctx->con_d2); cudaFree(ctx->xcon);
     for (BondedForce& bf : ctx->bonded_forces) free_bonded(bf);
     for (PmeForce& pm : ctx->pme_forces) pme_release(pm);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -159,10 +162,12 @@ extern "C" int b2_synchronize(b2_context* ctx) {
     if (!ctx) return B2_ERR_ARG;
     B2_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->nl_flags) {
-        int flags[8];
+        int flags[10];
         B2_CUDA(cudaMemcpy(flags, ctx->nl_flags, sizeof(flags), cudaMemcpyDeviceToHost));
         ctx->counters[1] = flags[2];
         ctx->counters[4] = flags[3];
+        if (flags[9])
+            return b2_fail(ctx, B2_ERR_OVERFLOW, "SHAKE/RATTLE did not converge to the constraint tolerance %g", ctx->con_tol);
         if (flags[1])
             return b2_fail(ctx, B2_ERR_OVERFLOW, "neighbour-list capacity %d exceeded (largest list %d): results "
                            "since the last rebuild are invalid; set positions again to refit", ctx->lists[0].cap, flags[3]);
@@ -543,6 +548,7 @@ extern "C" int b2_set_positions(b2_context* ctx, const double* x_dev) {
         B2_TRY(upload_static(ctx));
         B2_TRY(dist_partition(ctx));
         ctx->inner_built = false;
+        ctx->con_built = false;
         for (size_t k = 0; k < carried.size(); k++) {
             B2_TRY(state_permute_to_sorted(ctx, tmp[k], carried[k]));
         }

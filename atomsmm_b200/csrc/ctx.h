@@ -142,6 +142,17 @@ struct b2_context {
     int *chunk_start = nullptr, *chunk_term_ptr = nullptr;
     int2* chunk_terms = nullptr;
 
+    // ---- distance constraints (constraint.cu) -----------------------------------------------
+    std::vector<int> h_con_atoms;                 // pairs, caller numbering
+    std::vector<double> h_con_dist;
+    double con_tol = 1e-5;
+    bool con_built = false;
+    int nclusters = 0;
+    int* con_ptr = nullptr;                       // [nclusters+1] first constraint of every cluster
+    int2* con_pairs = nullptr;                    // atoms in the engine's order
+    double* con_d2 = nullptr;                     // squared target distances
+    double* xcon = nullptr;                       // [n][3] last constrained configuration
+
     // ---- cutoff-band pairs settled in float64 (pair.cu) -----------------------------------
     int* band_pairs = nullptr;
     unsigned* band_count = nullptr;
@@ -226,6 +237,10 @@ int dist_allreduce(b2_context* ctx, double* values, int count);
 void dist_release(b2_context* ctx);
 int forces_ensure(b2_context* ctx, uint32_t mask, int slot);
 int inner_prepare(b2_context* ctx);
+int con_prepare(b2_context* ctx);
+int con_snapshot(b2_context* ctx);
+int con_positions(b2_context* ctx);
+int con_velocities(b2_context* ctx);
 int program_run(b2_context* ctx, int nsteps);
 int program_release(b2_context* ctx);
 int state_permute_to_sorted(b2_context* ctx, const double* user, double* sorted);

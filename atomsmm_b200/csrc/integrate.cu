@@ -593,6 +593,10 @@ static int run_one_step(b2_context* ctx) {
     cudaStream_t s = ctx->stream;
     k_step_begin<<<1, 1, 0, s>>>(ctx->rng_state);
     B2_LAUNCH_CHECK();
+    // the configuration at the start of a step satisfies the constraints: it is the reference for the
+    // first position constraint of the step (OpenMM keeps `oldPos` the same way)
+    for (const b2_op& op : ctx->ops)
+        if (op.kind == B2_OP_CONSTRAIN_X) { B2_TRY(con_snapshot(ctx)); break; }
     for (size_t k = 0; k < ctx->ops.size(); k++) {
         const b2_op& op = ctx->ops[k];
         switch (op.kind) {
@@ -644,6 +648,12 @@ static int run_one_step(b2_context* ctx) {
             B2_LAUNCH_CHECK();
             break;
         case B2_OP_UPDATE_STATE:
+            break;
+        case B2_OP_CONSTRAIN_X:
+            B2_TRY(con_positions(ctx));
+            break;
+        case B2_OP_CONSTRAIN_V:
+            B2_TRY(con_velocities(ctx));
             break;
         case B2_OP_INVALIDATE:
             for (int g = 0; g < B2_FSLOTS; g++) ctx->fvalid[g] = -1;
@@ -700,6 +710,7 @@ int program_run(b2_context* ctx, int nsteps) {
     // restores the steady-state pattern.  The first step always runs eagerly (it also performs
     // all lazy allocations, which are illegal during capture).
     B2_TRY(inner_prepare(ctx));
+    B2_TRY(con_prepare(ctx));
     B2_TRY(ensure_partials(ctx, (ctx->a_hi - ctx->a_lo + 255)/256 + 1));
     static const bool graph_allowed = getenv("B2_NO_GRAPH") == nullptr;
     const bool use_graph = graph_allowed && !ctx->profiling;

@@ -36,6 +36,9 @@ enum {
     B2_OP_FUSED_INNER = 10,
     // a scalar program has moved a context parameter that forces depend on: every cached force is stale
     B2_OP_INVALIDATE = 11,
+    // CustomIntegrator.addConstrainPositions / addConstrainVelocities (SHAKE / RATTLE, constraint.cu)
+    B2_OP_CONSTRAIN_X = 12,
+    B2_OP_CONSTRAIN_V = 13,
 };
 
 // VM opcodes (two ints per instruction: opcode, argument)

@@ -48,6 +48,7 @@ _SIGNATURES = {
     'b2_add_pme': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                    ctypes.c_double, ctypes.c_double, c_int_p],
     'b2_set_skin': [c_void, ctypes.c_double],
+    'b2_set_constraints': [c_void, ctypes.c_int, c_int_p, c_double_p, ctypes.c_double],
     'b2_set_positions': [c_void, c_void],
     'b2_set_velocities': [c_void, c_void],
     'b2_get_positions': [c_void, c_void],
@@ -520,6 +521,7 @@ class Context(object):
         if not isinstance(integrator, mm.CustomIntegrator):
             self._program = None
             return
+        self._upload_constraints()
         derivative_slots = {}
         for _, info, force in self._pair_handles.values():
             if info.get('name') == 'softcore':
@@ -554,9 +556,19 @@ class Context(object):
             elif np.isscalar(value) and value != 0.0 and self._have_positions:
                 self._set_perdof(integrator._perdof_names[k], np.full((self._n, 3), float(value)))
 
+    def _upload_constraints(self):
+        constraints = self._system._constraints
+        if not constraints:
+            return
+        pairs = np.array([[c[0], c[1]] for c in constraints], dtype=np.int32)
+        lengths = np.array([c[2] for c in constraints], dtype=np.float64)
+        tolerance = self._integrator.getConstraintTolerance() if self._integrator is not None else 1e-5
+        self._call('b2_set_constraints', len(pairs), _iptr(pairs), _dptr(lengths), float(tolerance))
+
     def _integrator_changed(self):
         if self._program is not None:
             self._set_global('dt', self._integrator._dt)
+            self._upload_constraints()
 
     def _get_global(self, name):
         out = ctypes.c_double()

@@ -26,7 +26,7 @@ from . import mm
 PAIR_NEAR, PAIR_DAMPED, PAIR_LJC, PAIR_LJ_VIRIAL, PAIR_SOFTCORE = 1, 2, 3, 4, 5
 BOND_HARMONIC, ANGLE_HARMONIC, TORSION_PERIODIC, BOND_LJC, BOND_CUSTOM, ANGLE_CUSTOM = 1, 2, 3, 4, 5, 6
 (OP_PERDOF, OP_SUM, OP_GLOBAL, OP_EVAL, OP_KICK, OP_DRIFT, OP_SCALE, OP_UPDATE_STATE, OP_ENERGY,
- OP_FUSED_INNER, OP_INVALIDATE) = range(1, 12)
+ OP_FUSED_INNER, OP_INVALIDATE, OP_CONSTRAIN_X, OP_CONSTRAIN_V) = range(1, 14)
 ENERGY_SLOT_DLAMBDA_VDW, ENERGY_SLOT_DLAMBDA_COUL = 64, 65
 OP_WORDS = 8
 
@@ -405,9 +405,7 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
             P.new_global(name, value)
     P.perdof_names = [integrator.getPerDofVariableName(k) for k in range(integrator.getNumPerDofVariables())]
     steps = [tuple(integrator.getComputationStep(k)) for k in range(integrator.getNumComputations())]
-    if any(s[0] in (CI.ConstrainPositions, CI.ConstrainVelocities) for s in steps):
-        if constrained:
-            raise UnsupportedDescription('distance constraints (SHAKE/RATTLE) are not implemented in this engine yet')
+    if not constrained:
         # a System without constraints: constraining positions / velocities does nothing
         steps = [s for s in steps if s[0] not in (CI.ConstrainPositions, CI.ConstrainVelocities)]
     context_parameters = set(parameters or {})
@@ -595,6 +593,10 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
         kind, variable, expression = item
         if kind == CI.UpdateContextState:
             P.op(OP_UPDATE_STATE)
+        elif kind == CI.ConstrainPositions:
+            P.op(OP_CONSTRAIN_X)
+        elif kind == CI.ConstrainVelocities:
+            P.op(OP_CONSTRAIN_V)
         elif kind == CI.ComputeSum:
             ast = X.parse_inlined(expression)
             if variable not in P.global_names:

@@ -607,6 +607,15 @@ class Integrator(object):
         self._dt = float(_md(stepSize))
         self._context = None
         self._seed = 0
+        self._constraint_tolerance = 1e-5
+
+    def getConstraintTolerance(self):
+        return self._constraint_tolerance
+
+    def setConstraintTolerance(self, tolerance):
+        self._constraint_tolerance = float(tolerance)
+        if self._context is not None:
+            self._context._integrator_changed()
 
     def getStepSize(self):
         return self._dt*unit.picosecond

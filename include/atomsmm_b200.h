@@ -139,6 +139,12 @@ B2_API int b2_add_custom_bonded_force(b2_context* ctx, int family, int group, in
  * self_energy = -Kc alpha/sqrt(pi) sum q^2 is added to the group energy. */
 B2_API int b2_add_pme(b2_context* ctx, int group, int param_set, double alpha, int nx, int ny, int nz, double kc,
                       double self_energy, int* handle);
+/* System.addConstraint (app.ForceField.createSystem with rigidWater / HBonds ...) and
+ * Integrator.setConstraintTolerance: `count` pairs with their distances (nm); both atoms of a
+ * constraint must belong to the same molecule.  Enforced by the CustomIntegrator steps
+ * ConstrainPositions / ConstrainVelocities (propagators.py:245-252,270-273). */
+B2_API int b2_set_constraints(b2_context* ctx, int count, const int* pairs, const double* distances,
+                              double tolerance);
 /* neighbour-list skin (nm); lists are rebuilt when an atom moved more than skin/2 */
 B2_API int b2_set_skin(b2_context* ctx, double skin);
 

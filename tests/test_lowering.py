@@ -87,10 +87,13 @@ def test_bussi_program_keeps_rejection_loop_on_device():
     assert 33 in program.bc.code[::2]                    # VM_JMPZ: while/if compiled into the scalar VM
 
 
-def test_constraints_are_refused():
+def test_constraint_steps_are_lowered():
     integrator = atomsmm.GlobalThermostatIntegrator(1*fs, atomsmm.VelocityVerletPropagator())
-    with pytest.raises(lowering.UnsupportedDescription):
-        lowering.lower_program(integrator, 1)
+    program = lowering.lower_program(integrator, 1)
+    kinds = [op[0] for op in program.ops]
+    assert kinds.count(lowering.OP_CONSTRAIN_X) == 1 and kinds.count(lowering.OP_CONSTRAIN_V) == 1
+    free = lowering.lower_program(integrator, 1, constrained=False)       # a System without constraints
+    assert lowering.OP_CONSTRAIN_X not in [op[0] for op in free.ops]
 
 
 def test_afed_program_lowering():
@@ -109,8 +112,6 @@ def test_afed_program_lowering():
         atomsmm.NoseHooverPropagator(300*K, atomsmm.countDegreesOfFreedom(alchemical), 10*fs)).integrator(1*fs)
     variable = atomsmm.ExtendedSystemVariable('lambda_vdw', 1000, 5, 40*fs)
     integrator = atomsmm.AdiabaticDynamicsIntegrator(nvt, 2, [variable])
-    with pytest.raises(lowering.UnsupportedDescription):
-        lowering.lower_program(integrator, 1, {'lambda_vdw': 1.0}, True, constrained=True)
     program = lowering.lower_program(integrator, 1, {'lambda_vdw': 1.0}, True, constrained=False,
                                      derivative_slots={'lambda_vdw': lowering.ENERGY_SLOT_DLAMBDA_VDW})
     kinds = [op[0] for op in program.ops]
