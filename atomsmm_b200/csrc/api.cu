@@ -106,7 +106,7 @@ extern "C" int b2_create(int device, b2_context** out) {
         cudaMalloc(&ctx->ticket, sizeof(unsigned)*4) != cudaSuccess ||
         cudaMalloc(&ctx->nl_flags, sizeof(int)*16) != cudaSuccess ||
         cudaMalloc(&ctx->band_pairs, sizeof(int)*2*ctx->band_capacity) != cudaSuccess ||
-        cudaMalloc(&ctx->band_count, sizeof(unsigned)) != cudaSuccess) {
+        cudaMalloc(&ctx->band_count, sizeof(unsigned)*2) != cudaSuccess) {
         delete ctx;
         return b2_fail(nullptr, B2_ERR_CUDA, "device allocation failed");
     }
@@ -114,6 +114,7 @@ extern "C" int b2_create(int device, b2_context** out) {
     cudaMemset(ctx->rng_state, 0, sizeof(unsigned long long)*4);
     cudaMemset(ctx->ticket, 0, sizeof(unsigned)*4);
     cudaMemset(ctx->nl_flags, 0, sizeof(int)*16);
+    cudaMemset(ctx->band_count, 0, sizeof(unsigned)*2);
     ctx->sum_partial_size = 1024;
     *out = ctx;
     return B2_OK;
@@ -162,8 +163,11 @@ extern "C" int b2_synchronize(b2_context* ctx) {
     if (!ctx) return B2_ERR_ARG;
     B2_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->nl_flags) {
-        int flags[10];
+        int flags[11];
         B2_CUDA(cudaMemcpy(flags, ctx->nl_flags, sizeof(flags), cudaMemcpyDeviceToHost));
+        if (flags[10])
+            return b2_fail(ctx, B2_ERR_OVERFLOW, "cutoff-band buffer overflow (%u pairs): forces since then are incomplete",
+                           ctx->band_capacity);
         ctx->counters[1] = flags[2];
         ctx->counters[4] = flags[3];
         if (flags[9])

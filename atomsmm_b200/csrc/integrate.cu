@@ -141,8 +141,10 @@ __device__ void run_scalar_program_staged(ScalarStage& st, const int* __restrict
 
 // stand-alone scalar program (prologue of a step, Bussi's rejection loop, AFED wall reflection ...)
 __global__ void k_global(const int* __restrict__ code, int len, const double* __restrict__ consts, int nconsts,
-                         double* globals, int nglobals, unsigned long long* rng_state, const double* energies) {
+                         double* globals, int nglobals, unsigned long long* rng_state, const double* energies,
+                         int begin_step) {
     __shared__ ScalarStage stage;
+    if (begin_step && threadIdx.x == 0) rng_state[2] += 1ull;      // MD step counter of the RNG streams
     run_scalar_program_staged(stage, code, len, consts, nconsts, globals, nglobals, rng_state, energies);
 }
 
@@ -502,7 +504,7 @@ static int launch_vel(b2_context* ctx, const b2_op& op) {
         B2_TRY(dist_allreduce(ctx, ctx->globals + ka.mvv, 1));
         if (op.g > 0) {
             k_global<<<1, 64, 0, s>>>(ctx->code + op.f, op.g, ctx->consts, ctx->nconsts, ctx->globals,
-                                       ctx->nglobals, ctx->rng_state, ctx->d_energy);
+                                       ctx->nglobals, ctx->rng_state, ctx->d_energy, 0);
             B2_LAUNCH_CHECK();
         }
     }
@@ -591,8 +593,13 @@ static int run_one_step(b2_context* ctx) {
     const int T = 256;
     const int lo = ctx->a_lo, hi = ctx->a_hi, n = hi - lo, ndof = 3*n;   // owned range
     cudaStream_t s = ctx->stream;
-    k_step_begin<<<1, 1, 0, s>>>(ctx->rng_state);
-    B2_LAUNCH_CHECK();
+    // the step counter of the RNG streams is advanced by the first kernel of the step when that is the
+    // scalar prologue, otherwise by a kernel of its own
+    const bool folded_begin = !ctx->ops.empty() && ctx->ops[0].kind == B2_OP_GLOBAL;
+    if (!folded_begin) {
+        k_step_begin<<<1, 1, 0, s>>>(ctx->rng_state);
+        B2_LAUNCH_CHECK();
+    }
     // the configuration at the start of a step satisfies the constraints: it is the reference for the
     // first position constraint of the step (OpenMM keeps `oldPos` the same way)
     for (const b2_op& op : ctx->ops)
@@ -628,7 +635,7 @@ static int run_one_step(b2_context* ctx) {
         }
         case B2_OP_GLOBAL:
             k_global<<<1, 64, 0, s>>>(ctx->code + op.b, op.c, ctx->consts, ctx->nconsts, ctx->globals,
-                                       ctx->nglobals, ctx->rng_state, ctx->d_energy);
+                                       ctx->nglobals, ctx->rng_state, ctx->d_energy, (k == 0 && folded_begin) ? 1 : 0);
             B2_LAUNCH_CHECK();
             break;
         case B2_OP_KICK: {

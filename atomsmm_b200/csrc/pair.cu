@@ -151,7 +151,7 @@ __device__ __forceinline__ float3 rel_pos(const double* __restrict__ x, int a, d
 }
 
 template <class POT>
-__global__ void __launch_bounds__(32*WPB) k_pair_force(int n, int g_lo, int ngroups, const double* __restrict__ x,
+__global__ void __launch_bounds__(32*WPB, 8) k_pair_force(int n, int g_lo, int ngroups, const double* __restrict__ x,
                                                       const float4* __restrict__ par,
                                                       const int* __restrict__ entries,
                                                       const int* __restrict__ counts,
