@@ -451,10 +451,11 @@ static int compute_order(b2_context* ctx, const std::vector<double>& hx) {
     }
     std::vector<std::pair<uint64_t, int>> keys;
     keys.reserve(nmol);
-    // curve resolution: cells of 0.28-0.57 nm along the longest box edge
+    // curve resolution: cells of 0.16-0.32 nm along the longest box edge (about one water molecule per
+    // cell: consecutive molecules are then nearest neighbours and 8-atom groups stay ~0.5 nm wide)
     const double longest = std::max(ctx->box[0], std::max(ctx->box[1], ctx->box[2]));
     int bits = 1;
-    while (bits < 20 && longest/(double)(1u << bits) > 0.57) bits++;
+    while (bits < 20 && longest/(double)(1u << bits) > 0.32) bits++;
     for (int m = 0; m < nmol; m++) {
         if (mols[m].empty()) continue;
         uint32_t c[3];
@@ -782,6 +783,18 @@ extern "C" int b2_get_profile(b2_context* ctx, int handle, double* total_ms, lon
         for (int v : c) total += v;
         *entries = total;
     }
+    return B2_OK;
+}
+
+extern "C" int b2_get_list_stats(b2_context* ctx, long long out_host[4]) {
+    if (!ctx || !ctx->nl_flags) return B2_ERR_ARG;
+    int flags[16];
+    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    B2_CUDA(cudaMemcpy(flags, ctx->nl_flags, sizeof(flags), cudaMemcpyDeviceToHost));
+    out_host[0] = flags[2];      // rebuilds
+    out_host[1] = flags[3];      // largest list
+    out_host[2] = flags[8];      // fat groups at the last rebuild
+    out_host[3] = ctx->ngroups;
     return B2_OK;
 }
 

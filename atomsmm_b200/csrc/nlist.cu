@@ -15,6 +15,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <type_traits>
@@ -584,6 +585,7 @@ int nl_prepare(b2_context* ctx, bool force) {
         return B2_OK;
     }
     const int n = ctx->n, ng = ctx->ngroups, T = 256;
+    static const double fat_factor = getenv("B2_FAT_FACTOR") ? atof(getenv("B2_FAT_FACTOR")) : 1.2;
     Grid g = make_grid(ctx);
     cudaStream_t s = ctx->stream;
     double limit = 0.5*ctx->skin;
@@ -592,7 +594,7 @@ int nl_prepare(b2_context* ctx, bool force) {
                                                (ctx->lists_built && !force) ? 1 : 0);
     B2_LAUNCH_CHECK();
     k_group_geom<<<(8*ng + T - 1)/T, T, 0, s>>>(n, ng, ctx->x, g, ctx->prel, ctx->gcen, ctx->ghalf, ctx->gcell,
-                                                 ctx->cell_count, hmax, (float)(0.75*ctx->cellsize[0]),
+                                                 ctx->cell_count, hmax, (float)(fat_factor*ctx->cellsize[0]),
                                                  ctx->nl_flags);
     B2_LAUNCH_CHECK();
     k_cell_scan<<<1, 1024, 0, s>>>(ctx->ncells, ctx->cell_count, ctx->cell_start, ng, ctx->gcell, ctx->fat_list,

@@ -66,6 +66,7 @@ _SIGNATURES = {
     'b2_get_perdof': [c_void, ctypes.c_int, c_void],
     'b2_run': [c_void, ctypes.c_int],
     'b2_get_counters': [c_void, ctypes.POINTER(ctypes.c_longlong)],
+    'b2_get_list_stats': [c_void, ctypes.POINTER(ctypes.c_longlong)],
     'b2_set_profiling': [c_void, ctypes.c_int],
     'b2_get_profile': [c_void, ctypes.c_int, c_double_p, ctypes.POINTER(ctypes.c_longlong),
                        ctypes.POINTER(ctypes.c_longlong)],
@@ -801,6 +802,11 @@ class Context(object):
         self._call('b2_get_counters', out)
         return dict(launches=out[0], rebuilds=out[1], pair_launches=out[2], list_capacity=out[3],
                     list_max=out[4], graph_launches=out[5], kernels_per_step=out[6])
+
+    def list_stats(self):
+        out = (ctypes.c_longlong*4)()
+        self._call('b2_get_list_stats', out)
+        return dict(rebuilds=out[0], largest_list=out[1], fat_groups=out[2], groups=out[3])
 
     def set_profiling(self, on):
         self._call('b2_set_profiling', 1 if on else 0)

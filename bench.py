@@ -322,7 +322,8 @@ def main():
                 e2e=(dict(value=e2e_value, unit='atom-steps/s', h2d_bytes_per_step=state_bytes,
                           d2h_bytes_per_step=state_bytes + 16, final_energy=energy) if e2e_value is not None else None),
                 roofline=roofline, engine=dict(kernels_per_md_step=after['kernels_per_step'],
-                                               list_rebuilds=after['rebuilds'], list_capacity=after['list_capacity']))
+                                               list_rebuilds=after['rebuilds'], list_capacity=after['list_capacity'],
+                                               list_stats=context.list_stats()))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cport
         cores = os.cpu_count()

@@ -191,6 +191,11 @@ B2_API int b2_run(b2_context* ctx, int nsteps);
  * launches, [3] list capacity (entries per 8-atom group, largest list), [4] largest count seen */
 B2_API int b2_get_counters(b2_context* ctx, long long out_host[8]);
 
+/* neighbour-list diagnostics: [0] rebuilds so far, [1] largest list (entries per 8-atom group),
+ * [2] groups too extended for the cell grid at the last rebuild ("fat": every list build tests them
+ * directly), [3] number of groups */
+B2_API int b2_get_list_stats(b2_context* ctx, long long out_host[4]);
+
 /* profiling aid for bench.py: while on, steps run eagerly (no CUDA graph) and every pair-force
  * launch is bracketed by CUDA events on the context's stream.  b2_get_profile returns the summed
  * duration and launch count of pair force `handle`, and the current number of list entries it
