@@ -78,13 +78,14 @@ class ClockSampler(object):
 
     def __init__(self, index):
         self.index = index
-        self.lines = []
+        self.lines = []           # (host time, csv line)
         self.proc = None
+        self.window = [None, None]
 
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -93,7 +94,13 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.window[0] = time.perf_counter()
+
+    def mark_end(self):
+        self.window[1] = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -105,7 +112,11 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for line in self.lines:
+        inside = [line for t, line in self.lines
+                  if self.window[0] is None or (self.window[0] <= t <= (self.window[1] or t))]
+        if not inside:            # a timed region shorter than the sampling period: nearest samples
+            inside = [line for _, line in self.lines[-3:]]
+        for line in inside:
             parts = [p.strip() for p in line.split(',')]
             if len(parts) < 9:
                 continue
@@ -234,13 +245,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- resident-state timing ---------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()               # nvidia-smi needs a moment to come up: start it before the warm-up
     for _ in range(args.warmup):
         integrator.step(md)
     context.synchronize()
     before = context.counters()
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
+    sampler.mark_begin()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         start.record(stream)
@@ -248,6 +260,7 @@ def main():
             integrator.step(md)
         stop.record(stream)
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     context.synchronize()
     elapsed = start.elapsed_time(stop)*1e-3
