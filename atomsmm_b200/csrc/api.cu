@@ -56,7 +56,8 @@ __global__ void k_maxdisp(int n, const double* __restrict__ a, const double* __r
     if (i >= n) return;
     double dx = a[3*i] - b[3*i], dy = a[3*i+1] - b[3*i+1], dz = a[3*i+2] - b[3*i+2];
     double d2 = dx*dx + dy*dy + dz*dz;
-    if (d2 > 0.09) atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(d2));
+    // atoms that have strayed more than 0.5 nm from where they were when the order was computed
+    if (d2 > 0.25) atomicAdd(reinterpret_cast<unsigned long long*>(out), 1ull);
 }
 
 __global__ void k_fold_energy(double* e, int group, double econst, int soft) {
@@ -190,6 +191,7 @@ extern "C" int b2_set_box(b2_context* ctx, const double box[3], int periodic) {
     }
     ctx->periodic = periodic;
     ctx->lists_built = false;
+    ctx->lists_fitted = false;
     ctx->have_order = false;
     program_release(ctx);
     return B2_OK;
@@ -294,6 +296,7 @@ extern "C" int b2_add_pair_force(b2_context* ctx, int family, int group, int par
     if (pf.list < 0) return b2_fail(ctx, B2_ERR_UNSUPPORTED, "more than %d distinct cutoffs", B2_MAX_LISTS);
     ctx->pair_forces.push_back(pf);
     ctx->lists_built = false;
+    ctx->lists_fitted = false;
     program_release(ctx);
     if (handle) *handle = (int)ctx->pair_forces.size() - 1;
     return B2_OK;
@@ -407,6 +410,7 @@ extern "C" int b2_set_skin(b2_context* ctx, double skin) {
     if (!ctx || !(skin >= 0)) return B2_ERR_ARG;
     ctx->skin = skin;
     ctx->lists_built = false;
+    ctx->lists_fitted = false;
     ctx->have_order = false;
     return B2_OK;
 }
@@ -522,16 +526,18 @@ extern "C" int b2_set_positions(b2_context* ctx, const double* x_dev) {
     const int n = ctx->n, T = 256;
     bool resort = !ctx->have_order;
     if (!resort) {
-        // far from the configuration the order was built for?
+        // has the configuration drifted away from the one the order was built for?
         B2_TRY(state_permute_to_sorted(ctx, x_dev, ctx->scratch3));
         double* flag = ctx->d_energy + 80;
         B2_CUDA(cudaMemsetAsync(flag, 0, sizeof(double), ctx->stream));
         k_maxdisp<<<(n + T - 1)/T, T, 0, ctx->stream>>>(n, ctx->scratch3, ctx->xsort, flag);
         B2_LAUNCH_CHECK();
-        double h = 0;
-        B2_CUDA(cudaMemcpyAsync(&h, flag, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        unsigned long long strayed = 0;
+        B2_CUDA(cudaMemcpyAsync(&strayed, flag, sizeof(strayed), cudaMemcpyDeviceToHost, ctx->stream));
         B2_CUDA(cudaStreamSynchronize(ctx->stream));
-        resort = h != 0.0;
+        // the order only matters for speed (compact groups, short lists): refresh it when more than 2 %
+        // of the atoms have strayed, not for the first fast hydrogen
+        resort = strayed*50ull > (unsigned long long)n;
     }
     if (resort) {
         std::vector<double> hx(3*(size_t)n);

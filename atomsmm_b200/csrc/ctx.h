@@ -127,7 +127,7 @@ struct b2_context {
     float4 *cgc = nullptr, *cgh = nullptr;             // the same in cell order (w of cgc = group id)
     float4* prel = nullptr;                            // per atom: position relative to its group's centre
     int* nl_flags = nullptr;     // [0] rebuild needed, [1] overflow, [2] rebuild counter, [3] max count
-    bool lists_built = false;
+    bool lists_built = false, lists_fitted = false;
 
     // ---- domain decomposition (dist.cu) ------------------------------------------------------
     int rank = 0, nranks = 1;

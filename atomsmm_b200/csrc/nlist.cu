@@ -636,8 +636,13 @@ int nl_initial_build(b2_context* ctx) {
         int guess = (int)(1.3*rho*4.18879*r*r*r) + 64;
         guess = std::min(guess, ctx->n + 32);
         guess = ((guess + 31)/32)*32;
-        if (ctx->lists[k].entries == nullptr || ctx->lists[k].cap < guess) B2_TRY(alloc_lists(ctx, k, guess));
+        if (ctx->lists[k].entries == nullptr || (!ctx->lists_fitted && ctx->lists[k].cap < guess))
+            B2_TRY(alloc_lists(ctx, k, guess));
     }
+    // First build of a context: fit the capacity to 1.3 x the largest list (density fluctuations during a
+    // run).  Later builds (re-ordering at setPositions) keep the buffers and only grow them, by 1.5 x, when
+    // a list actually overflowed: no allocation, one synchronisation.
+    const bool first = !ctx->lists_fitted;
     for (int attempt = 0; attempt < 6; attempt++) {
         int zero[8] = {0};
         int flags[8];
@@ -649,22 +654,25 @@ int nl_initial_build(b2_context* ctx) {
         B2_CUDA(cudaMemcpyAsync(flags, ctx->nl_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
         B2_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->counters[4] = flags[3];
-        // capacity = 1.3 x the largest list seen now (density fluctuations during a run), scaled per list
-        // by the ratio of list volumes
         double rbig = 0;
         for (int k = 0; k < ctx->nlists; k++) rbig = std::max(rbig, ctx->lists[k].cutoff + ctx->skin);
         bool grown = false;
-        for (int k = 0; k < ctx->nlists; k++) {
-            const double ratio = pow((ctx->lists[k].cutoff + ctx->skin)/rbig, 3.0);
-            int cap = (int)(1.3*flags[3]*std::min(1.0, ratio*1.15)) + 64;
-            cap = std::min(((cap + 31)/32)*32, ((ctx->n + 63)/32)*32);
-            if (cap > ctx->lists[k].cap) {
-                B2_TRY(alloc_lists(ctx, k, cap));
-                grown = true;
+        if (first || flags[1]) {
+            const double margin = first ? 1.3 : 1.5;
+            for (int k = 0; k < ctx->nlists; k++) {
+                // scaled per list by the ratio of list volumes
+                const double ratio = pow((ctx->lists[k].cutoff + ctx->skin)/rbig, 3.0);
+                int cap = (int)(margin*flags[3]*std::min(1.0, ratio*1.15)) + 64;
+                cap = std::min(((cap + 31)/32)*32, ((ctx->n + 63)/32)*32);
+                if (cap > ctx->lists[k].cap) {
+                    B2_TRY(alloc_lists(ctx, k, cap));
+                    grown = true;
+                }
             }
         }
         if (!flags[1] && !grown) {
             ctx->counters[3] = ctx->lists[0].cap;
+            ctx->lists_fitted = true;
             return B2_OK;
         }
     }
