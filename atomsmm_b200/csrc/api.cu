@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <numeric>
 
 #include "ctx.h"
@@ -144,6 +145,8 @@ extern "C" int b2_destroy(b2_context* ctx) {
     cudaFree(ctx->globals); cudaFree(ctx->sum_partial); cudaFree(ctx->rng_state);
     cudaFree(ctx->band_pairs); cudaFree(ctx->band_count); cudaFree(ctx->ticket);
     cudaFree(ctx->chunk_start); cudaFree(ctx->chunk_term_ptr); cudaFree(ctx->chunk_terms);
+    for (double* p : ctx->carry_tmp) cudaFree(p);
+    cudaFree(ctx->order_tmp);
     cudaFree(ctx->con_ptr); cudaFree(ctx->con_pairs); cudaFree(ctx->con_d2); cudaFree(ctx->xcon);
     for (BondedForce& bf : ctx->bonded_forces) free_bonded(bf);
     for (PmeForce& pm : ctx->pme_forces) pme_release(pm);
@@ -524,7 +527,8 @@ static int upload_static(b2_context* ctx) {
 extern "C" int b2_set_positions(b2_context* ctx, const double* x_dev) {
     if (!ctx || ctx->n == 0 || !x_dev) return b2_fail(ctx, B2_ERR_STATE, "set particles first");
     const int n = ctx->n, T = 256;
-    bool resort = !ctx->have_order;
+    bool resort = !ctx->have_order || ctx->force_resort;
+    ctx->force_resort = false;
     if (!resort) {
         // has the configuration drifted away from the one the order was built for?
         B2_TRY(state_permute_to_sorted(ctx, x_dev, ctx->scratch3));
@@ -539,6 +543,16 @@ extern "C" int b2_set_positions(b2_context* ctx, const double* x_dev) {
         // of the atoms have strayed, not for the first fast hydrogen
         resort = strayed*50ull > (unsigned long long)n;
     }
+    static const bool timing = getenv("B2_DEBUG_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_mark = now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(ctx->stream);
+        const double t = now();
+        fprintf(stderr, "[b2 resort] %-18s %8.2f ms\n", what, t - t_mark);
+        t_mark = t;
+    };
     if (resort) {
         std::vector<double> hx(3*(size_t)n);
         B2_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -548,15 +562,24 @@ extern "C" int b2_set_positions(b2_context* ctx, const double* x_dev) {
         if (ctx->have_order) {
             carried.push_back(ctx->v);
             for (double* p : ctx->perdof) carried.push_back(p);
+            // with several ranks each holds only its owned range: complete the arrays first, because
+            // the ownership ranges change with the order
+            for (double* p : carried) B2_TRY(dist_gather3(ctx, p));
         }
-        std::vector<double*> tmp(carried.size(), nullptr);
-        for (size_t k = 0; k < carried.size(); k++) {
-            B2_CUDA(cudaMalloc(&tmp[k], sizeof(double)*3*n));
-            B2_TRY(state_permute_to_user(ctx, carried[k], tmp[k]));
+        // staging buffers are kept for the life of the context: no allocation on this path
+        std::vector<double*>& tmp = ctx->carry_tmp;
+        while (tmp.size() < carried.size()) {
+            double* p = nullptr;
+            B2_CUDA(cudaMalloc(&p, sizeof(double)*3*n));
+            tmp.push_back(p);
         }
+        for (size_t k = 0; k < carried.size(); k++) B2_TRY(state_permute_to_user(ctx, carried[k], tmp[k]));
         B2_CUDA(cudaStreamSynchronize(ctx->stream));
+        lap("download+carry");
         B2_TRY(compute_order(ctx, hx));
+        lap("compute_order");
         B2_TRY(upload_static(ctx));
+        lap("upload_static");
         B2_TRY(dist_partition(ctx));
         ctx->inner_built = false;
         ctx->con_built = false;
@@ -564,20 +587,50 @@ extern "C" int b2_set_positions(b2_context* ctx, const double* x_dev) {
             B2_TRY(state_permute_to_sorted(ctx, tmp[k], carried[k]));
         }
         B2_CUDA(cudaStreamSynchronize(ctx->stream));
-        for (double* p : tmp) cudaFree(p);
         ctx->have_order = true;
         B2_TRY(state_permute_to_sorted(ctx, x_dev, ctx->x));
         B2_CUDA(cudaMemcpyAsync(ctx->xsort, ctx->x, sizeof(double)*3*n, cudaMemcpyDeviceToDevice, ctx->stream));
         ctx->lists_built = false;
         program_release(ctx);
+        lap("permute+release");
     } else {
         B2_CUDA(cudaMemcpyAsync(ctx->x, ctx->scratch3, sizeof(double)*3*n, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     ctx->have_positions = true;
     ctx->pos_version++;
     ctx->x_synced = ctx->pos_version;     // the caller passes the full configuration on every rank
-    if (!ctx->lists_built && ctx->nlists > 0) B2_TRY(nl_initial_build(ctx));
+    if (!ctx->lists_built && ctx->nlists > 0) {
+        B2_TRY(nl_initial_build(ctx));
+        lap("list build");
+    }
     return B2_OK;
+}
+
+// Called between MD steps of a long run: molecules diffuse, so the spatial order the groups, chunks
+// and ownership ranges were built for decays (lists stay exact but grow).  When enough atoms have
+// strayed, go through the re-ordering path of b2_set_positions with the current configuration.
+int order_refresh(b2_context* ctx) {
+    if (!ctx->have_order || !ctx->have_positions) return B2_OK;
+    const int n = ctx->n, T = 256;
+    B2_TRY(dist_sync_positions(ctx));
+    double* flag = ctx->d_energy + 80;
+    B2_CUDA(cudaMemsetAsync(flag, 0, sizeof(double), ctx->stream));
+    k_maxdisp<<<(n + T - 1)/T, T, 0, ctx->stream>>>(n, ctx->x, ctx->xsort, flag);
+    B2_LAUNCH_CHECK();
+    unsigned long long strayed = 0;
+    B2_CUDA(cudaMemcpyAsync(&strayed, flag, sizeof(strayed), cudaMemcpyDeviceToHost, ctx->stream));
+    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (strayed*50ull <= (unsigned long long)n) return B2_OK;
+    if (ctx->order_tmp == nullptr) B2_CUDA(cudaMalloc(&ctx->order_tmp, sizeof(double)*3*n));
+    double* user = ctx->order_tmp;
+    int r = state_permute_to_user(ctx, ctx->x, user);
+    if (r == B2_OK) {
+        ctx->force_resort = true;
+        r = b2_set_positions(ctx, user);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    ctx->counters[7] += 1000000;       // visible in b2_comm_info / counters: re-orderings during runs x 1e6
+    return r;
 }
 
 extern "C" int b2_set_velocities(b2_context* ctx, const double* v_dev) {

@@ -98,7 +98,8 @@ struct b2_context {
     int excl_span = 0;                            // largest distance in the engine's order between excluded atoms
 
     // ---- device state ----------------------------------------------------------------------
-    bool have_order = false, have_positions = false;
+    bool have_order = false, have_positions = false, force_resort = false;
+    int steps_since_order_check = 0;
     std::vector<int> h_orig;                      // sorted -> caller index
     double *x = nullptr, *v = nullptr, *xref = nullptr, *xsort = nullptr;
     float4* par[B2_MAX_SETS] = {nullptr};
@@ -114,6 +115,8 @@ struct b2_context {
     long long deriv_version = -1;                 // position version the parameter derivatives belong to
     std::vector<double*> perdof;
     double* scratch3 = nullptr;                   // [n][3] staging for permuted copies
+    std::vector<double*> carry_tmp;               // staging of v / per-DOF variables across a re-ordering
+    double* order_tmp = nullptr;                  // positions in caller order for the in-run re-ordering
 
     // ---- neighbour lists -------------------------------------------------------------------
     int nlists = 0;
@@ -237,6 +240,7 @@ int dist_allreduce(b2_context* ctx, double* values, int count);
 void dist_release(b2_context* ctx);
 int forces_ensure(b2_context* ctx, uint32_t mask, int slot);
 int inner_prepare(b2_context* ctx);
+int order_refresh(b2_context* ctx);
 int con_prepare(b2_context* ctx);
 int con_snapshot(b2_context* ctx);
 int con_positions(b2_context* ctx);

@@ -698,6 +698,7 @@ int program_release(b2_context* ctx) {
         ctx->graph_exec = nullptr;
     }
     ctx->graph_ready = false;
+    ctx->eager_steps = 0;      // one eager step restores the steady-state force validity before the capture
     return B2_OK;
 }
 
@@ -721,7 +722,14 @@ int program_run(b2_context* ctx, int nsteps) {
     B2_TRY(ensure_partials(ctx, (ctx->a_hi - ctx->a_lo + 255)/256 + 1));
     static const bool graph_allowed = getenv("B2_NO_GRAPH") == nullptr;
     const bool use_graph = graph_allowed && !ctx->profiling;
+    static const int order_period = getenv("B2_ORDER_PERIOD") ? atoi(getenv("B2_ORDER_PERIOD")) : 250;
     for (int done = 0; done < nsteps; done++) {
+        if (order_period > 0 && ++ctx->steps_since_order_check >= order_period) {
+            ctx->steps_since_order_check = 0;
+            B2_TRY(order_refresh(ctx));          // may re-sort: chunks, clusters and the graph are rebuilt
+            B2_TRY(inner_prepare(ctx));
+            B2_TRY(con_prepare(ctx));
+        }
         const unsigned long long entry = valid_mask(ctx);
         const bool synced = ctx->x_synced == ctx->pos_version;
         if (use_graph && ctx->graph_ready && (entry & ctx->graph_entry_mask) == ctx->graph_entry_mask &&

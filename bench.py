@@ -295,9 +295,14 @@ def main():
         e2e_step()
         barrier()
         t0 = time.perf_counter()
+        laps = []
         for _ in range(e2e_steps):
+            lap = time.perf_counter()
             energy = e2e_step()
+            laps.append(round(1e3*(time.perf_counter() - lap), 1))
         barrier()
+        if os.environ.get('B2_BENCH_VERBOSE'):
+            sys.stderr.write('e2e laps (ms): %s\n' % laps)
         e2e_elapsed = time.perf_counter() - t0
         t = torch.tensor([e2e_elapsed], dtype=torch.float64, device='cuda')
         if world > 1:

@@ -170,3 +170,29 @@ def test_langevin_and_bussi_statistics(cuda_platform):
                 unit.nanometer/unit.picosecond))
         assert np.array_equal(finals[0], finals[1])
         assert not np.allclose(finals[0], finals[2])
+
+
+def test_long_run_refreshes_the_spatial_order(cuda_platform):
+    """Molecules diffuse away from the order the groups were built for; the engine re-sorts between
+    steps of a long run (state carried across, lists stay exact) instead of letting the lists grow
+    until they overflow."""
+    import os
+    respa, pdb = systems.respa_water()
+    pos = positions_of(pdb)
+    vel = thermal_velocities(respa, 600.0, 5)            # hot: fast diffusion
+    integrator = atomsmm.RespaPropagator([4, 2, 1]).integrator(4*fs)
+    context = mm.Context(respa, integrator, cuda_platform)
+    context.setPositions(pos)
+    context.setVelocities(vel)
+    e0 = context.getState(getEnergy=True)
+    total0 = (e0.getPotentialEnergy() + e0.getKineticEnergy()).value_in_unit(unit.kilojoules_per_mole)
+    integrator.step(3000)                                # 12 ps
+    state = context.getState(getEnergy=True, getPositions=True)
+    total = (state.getPotentialEnergy() + state.getKineticEnergy()).value_in_unit(unit.kilojoules_per_mole)
+    dof = atomsmm.countDegreesOfFreedom(respa)
+    assert abs(total - total0)/dof < 0.05                # energy conserved across the re-orderings
+    out = (__import__('ctypes').c_longlong*8)()
+    context._call('b2_get_counters', out)
+    assert out[7] >= 1000000                             # at least one re-ordering happened
+    stats = context.list_stats()
+    assert stats['largest_list'] < 1800
