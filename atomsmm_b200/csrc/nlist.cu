@@ -75,7 +75,8 @@ __global__ void k_skin_check(int n, const double* __restrict__ x, const double* 
 // cell of the centre.  Groups, not atoms, are binned: 8x less sorting work.
 __global__ void k_group_geom(int n, int ngroups, const double* __restrict__ x, Grid g, float4* __restrict__ prel,
                              float4* __restrict__ gcen, float4* __restrict__ ghalf, int* __restrict__ gcell,
-                             int* cell_count, int* hmax_bits, float fat_limit, const int* flags) {
+                             int* cell_count, int* hmax_bits, float fat_limit, int* __restrict__ fat_list,
+                             int fat_capacity, int* flags) {
     if (!flags[0]) return;
     const int t = blockIdx.x*blockDim.x + threadIdx.x;
     const int grp = t >> 3, a = t & 7;
@@ -125,6 +126,8 @@ __global__ void k_group_geom(int n, int ngroups, const double* __restrict__ x, G
         // the cells: every i-group tests them directly, so they do not inflate everybody's search region
         if (fmaxf(h[0], fmaxf(h[1], h[2])) > fat_limit) {
             gcell[grp] = -1;
+            const int slot = atomicAdd(&flags[11], 1);       // arrival order; sorted by k_cell_scan
+            if (slot < fat_capacity) fat_list[slot] = grp;
         } else {
             const int cidx = (cell[2]*g.nc[1] + cell[1])*g.nc[0] + cell[0];
             gcell[grp] = cidx;
@@ -161,7 +164,24 @@ __global__ void k_cell_scan(int ncells, int* cell_count, int* cell_start, int ng
         run += c;
     }
     if (t == blockDim.x - 1) cell_start[ncells] = part[t];
-    // the fat groups, compacted in index order (deterministic)
+    // the fat groups arrive in arbitrary order: sort them by index (deterministic lists).  They are rare
+    // (< 0.1 % of the groups), so an odd-even transposition sort by one block is enough; in the unlikely
+    // case that there are more than the block can sort, fall back to a compaction pass over all groups.
+    const int nfat = flags[11];
+    if (nfat <= 2*(int)blockDim.x) {
+        __shared__ int keys[2048];
+        for (int k = t; k < 2*(int)blockDim.x; k += blockDim.x) keys[k] = k < nfat ? fat_list[k] : 0x7fffffff;
+        __syncthreads();
+        const int rounds = nfat;
+        for (int r = 0; r < rounds; r++) {
+            const int i = 2*t + (r & 1);
+            if (i + 1 < 2*(int)blockDim.x && keys[i] > keys[i+1]) { const int tmp = keys[i]; keys[i] = keys[i+1]; keys[i+1] = tmp; }
+            __syncthreads();
+        }
+        for (int k = t; k < nfat; k += blockDim.x) fat_list[k] = keys[k];
+        if (t == 0) { flags[8] = nfat; flags[11] = 0; }
+        return;
+    }
     __shared__ int wsum[32];
     __shared__ int base;
     if (t == 0) base = 0;
@@ -183,7 +203,7 @@ __global__ void k_cell_scan(int ncells, int* cell_count, int* cell_start, int ng
         if (t == 0) base += total;
         __syncthreads();
     }
-    if (t == 0) flags[8] = base;
+    if (t == 0) { flags[8] = base; flags[11] = 0; }
 }
 
 __global__ void k_cell_fill(int ngroups, const int* gcell, const int* cell_start, int* cell_count, int* cell_groups,
@@ -559,7 +579,7 @@ int nl_setup(b2_context* ctx) {
     }
     if (ctx->nl_flags == nullptr) {
         // [0] rebuild needed [1] overflow [2] rebuild counter [3] max count [4] ticket [5..7] max half extent
-        // [8] number of fat groups
+        // [8] number of fat groups  [9] constraint failure  [10] band overflow  [11] fat arrival counter
         B2_CUDA(cudaMalloc(&ctx->nl_flags, sizeof(int)*16));
         B2_CUDA(cudaMemsetAsync(ctx->nl_flags, 0, sizeof(int)*16, ctx->stream));
     }
@@ -595,7 +615,7 @@ int nl_prepare(b2_context* ctx, bool force) {
     B2_LAUNCH_CHECK();
     k_group_geom<<<(8*ng + T - 1)/T, T, 0, s>>>(n, ng, ctx->x, g, ctx->prel, ctx->gcen, ctx->ghalf, ctx->gcell,
                                                  ctx->cell_count, hmax, (float)(fat_factor*ctx->cellsize[0]),
-                                                 ctx->nl_flags);
+                                                 ctx->fat_list, ng, ctx->nl_flags);
     B2_LAUNCH_CHECK();
     k_cell_scan<<<1, 1024, 0, s>>>(ctx->ncells, ctx->cell_count, ctx->cell_start, ng, ctx->gcell, ctx->fat_list,
                                    ctx->nl_flags);

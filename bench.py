@@ -62,6 +62,65 @@ def build_workload(reps):
     return big, pos, vel
 
 
+def build_c3(reps):
+    """BASELINE config 3: emim/B(CN)4 ionic liquid replicated reps^3 (4 -> 179 200 atoms), DampedSmoothedForce
+    (alpha 2.9/nm, rc 1.0, rs 0.95 nm) in group 1, NonbondedExceptionsForce + bonded terms in group 0,
+    RESPA [4,1] at 2 fs with Bussi velocity rescaling (tau 0.1 ps)."""
+    import numpy as np
+    import atomsmm_b200 as atomsmm
+    from atomsmm_b200 import app, unit
+    import systems
+    pdb, ff = systems.fixtures.load('emim_BCN4_Jiung2014')
+    system = ff.createSystem(pdb.topology, nonbondedMethod=app.CutoffPeriodic, constraints=None, rigidWater=False,
+                             removeCMMotion=False)
+    nb = atomsmm.hijackForce(system, atomsmm.findNonbondedForce(system))
+    exceptions = atomsmm.forces.NonbondedExceptionsForce()
+    exceptions.importFrom(nb)
+    exceptions.setForceGroup(0)
+    system.addForce(exceptions)
+    damped = atomsmm.DampedSmoothedForce(2.9/unit.nanometer, 1.0*unit.nanometer, 0.95*unit.nanometer)
+    damped.importFrom(nb)
+    damped.setForceGroup(1)
+    system.addForce(damped)
+    box = np.array([v.value_in_md_units()[k] for k, v in enumerate(system.getDefaultPeriodicBoxVectors())])
+    pos = systems.positions_of(pdb)
+    big, pos = systems.replicate(system, pos, box, reps) if reps > 1 else (system, pos)
+    n = big.getNumParticles()
+    mass = np.array([big.getParticleMass(i).value_in_md_units() for i in range(n)])
+    rng = np.random.Generator(np.random.Philox(1234))
+    vel = rng.standard_normal((n, 3))*np.sqrt(8.314472471220217e-3*300.0/mass)[:, None]
+    vel -= (mass[:, None]*vel).sum(0)/mass.sum()
+    dof = atomsmm.countDegreesOfFreedom(big)
+    bussi = atomsmm.VelocityRescalingPropagator(300*unit.kelvin, dof, 0.1*unit.picoseconds)
+    integrator = atomsmm.TrotterSuzukiPropagator(atomsmm.RespaPropagator([4, 1]), bussi).integrator(2*unit.femtoseconds)
+    return big, pos, vel, integrator
+
+
+def build_c4():
+    """BASELINE config 4: AFED on methane in water (1 498 atoms), soft-core solute-solvent coupling with
+    lambda_vdw as extended variable (the construction of the reference's tests/test_afed.py:21-35)."""
+    import numpy as np
+    import atomsmm_b200 as atomsmm
+    from atomsmm_b200 import app, unit
+    import systems
+    pdb, ff = systems.fixtures.load('methane-in-water')
+    system = ff.createSystem(pdb.topology, nonbondedMethod=app.CutoffPeriodic, constraints=None, rigidWater=False,
+                             removeCMMotion=False)
+    solute = set(i for i, atom in enumerate(pdb.topology.atoms()) if atom.residue.name == 'C1')
+    alchemical = atomsmm.AlchemicalSystem(system, solute)
+    fs = unit.femtoseconds
+    nvt = atomsmm.TrotterSuzukiPropagator(
+        atomsmm.VelocityVerletPropagator(),
+        atomsmm.NoseHooverPropagator(300*unit.kelvin, atomsmm.countDegreesOfFreedom(alchemical), 10*fs)).integrator(1*fs)
+    variable = atomsmm.ExtendedSystemVariable('lambda_vdw', 1000, 5, 40*fs)
+    integrator = atomsmm.AdiabaticDynamicsIntegrator(nvt, 2, [variable])
+    n = alchemical.getNumParticles()
+    mass = np.array([alchemical.getParticleMass(i).value_in_md_units() for i in range(n)])
+    rng = np.random.Generator(np.random.Philox(1234))
+    vel = rng.standard_normal((n, 3))*np.sqrt(8.314472471220217e-3*300.0/mass)[:, None]
+    return alchemical, systems.positions_of(pdb), vel, integrator
+
+
 def make_integrator(system):
     import atomsmm_b200 as atomsmm
     from atomsmm_b200 import unit
@@ -177,10 +236,12 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def workload_config(args, n, md_steps):
+def workload_config(args, n, md_steps, what=None):
     dd = getattr(args, 'dd', False) and args.gpus > 1
-    return dict(workload='%s: q-SPC-FW water x%d^3, %d atoms, RESPASystem near 0.7/0.5 nm force-switch + LJ/reaction-field '
-                         '1.0 nm, RESPA [4,2,1] + NoseHoover SY3, dt 4 fs' % (getattr(args, 'workload', 'c2'), args.reps, n),
+    text = what % n if what else ('%s: q-SPC-FW water x%d^3, %d atoms, RESPASystem near 0.7/0.5 nm force-switch + '
+                                  'LJ/reaction-field 1.0 nm, RESPA [4,2,1] + NoseHoover SY3, dt 4 fs'
+                                  % (getattr(args, 'workload', 'c2'), args.reps, n))
+    return dict(workload=text,
                 atoms=n, md_steps_per_step=md_steps, dt_fs=DT_FS, loops=LOOPS,
                 replicas=1 if dd else args.gpus,
                 parallelism=('domain decomposition over %d ranks' % args.gpus) if dd else
@@ -200,7 +261,7 @@ def main():
     parser.add_argument('--md-steps', type=int, default=MD_STEPS_PER_CALL)
     parser.add_argument('--cpu-md-steps', type=int, default=2)
     parser.add_argument('--no-cpu-baseline', action='store_true')
-    parser.add_argument('--workload', default='c2', choices=['c2', 'c5'])
+    parser.add_argument('--workload', default='c2', choices=['c2', 'c3', 'c4', 'c5'])
     parser.add_argument('--dd', action='store_true', help='one system over all ranks (domain decomposition)')
     parser.add_argument('--no-e2e', action='store_true', help='skip the host-buffer end-to-end leg')
     args = parser.parse_args()
@@ -224,9 +285,18 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
-    system, pos, vel = build_workload(args.reps)
+    dt_fs, what = DT_FS, None
+    if args.workload == 'c3':
+        system, pos, vel, integrator = build_c3(args.reps)
+        dt_fs, what = 2.0, ('c3: emim/B(CN)4 ionic liquid x%d^3, %%d atoms, DampedSmoothedForce + NonbondedExceptionsForce, '
+                            'RESPA [4,1] + Bussi, dt 2 fs' % args.reps)
+    elif args.workload == 'c4':
+        system, pos, vel, integrator = build_c4()
+        dt_fs, what = 4.0, 'c4: AFED, methane in water, %d atoms, soft-core lambda_vdw extended variable, outer step 4 x 1 fs'
+    else:
+        system, pos, vel = build_workload(args.reps)
+        integrator, dof = make_integrator(system)
     n = system.getNumParticles()
-    integrator, dof = make_integrator(system)
     dd = args.dd and world > 1
     integrator.setRandomNumberSeed(1 if dd else 1 + rank)
     properties = {'DeviceIndex': local}
@@ -335,14 +405,14 @@ def main():
                 warmup=args.warmup, ms_per_step=1e3*elapsed/args.steps, higher_is_better=True,
                 scaling='strong' if dd else 'weak',
                 vs_baseline=None, dtype='f32 pair forces / f64 state', data='synthetic',
-                config=workload_config(args, n, md), ns_per_day=md*args.steps*DT_FS*1e-6*86400/elapsed,
+                config=workload_config(args, n, md, what), ns_per_day=md*args.steps*dt_fs*1e-6*86400/elapsed,
                 clocks=clocks, gpu_launches=int(launches),
                 e2e=(dict(value=e2e_value, unit='atom-steps/s', h2d_bytes_per_step=state_bytes,
                           d2h_bytes_per_step=state_bytes + 16, final_energy=energy) if e2e_value is not None else None),
                 roofline=roofline, engine=dict(kernels_per_md_step=after['kernels_per_step'],
                                                list_rebuilds=after['rebuilds'], list_capacity=after['list_capacity'],
                                                list_stats=context.list_stats()))
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload in ('c2', 'c5'):
         from oracle import cport
         cores = os.cpu_count()
         port = cport.CPort(system, threads=cores, verify=False)
