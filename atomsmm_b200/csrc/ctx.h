@@ -131,6 +131,7 @@ struct b2_context {
     float4* prel = nullptr;                            // per atom: position relative to its group's centre
     int* nl_flags = nullptr;     // [0] rebuild needed, [1] overflow, [2] rebuild counter, [3] max count
     bool lists_built = false, lists_fitted = false;
+    long long nl_checked_version = -1;            // position version of the last skin test
 
     // ---- domain decomposition (dist.cu) ------------------------------------------------------
     int rank = 0, nranks = 1;

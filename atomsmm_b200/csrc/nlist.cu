@@ -604,6 +604,10 @@ int nl_prepare(b2_context* ctx, bool force) {
     if (ctx->nlists == 0) {
         return B2_OK;
     }
+    // the lists were already checked (and rebuilt if necessary) for these very positions: RESPA evaluates
+    // the near and the far force back to back at the end of a step
+    if (!force && ctx->lists_built && ctx->nl_checked_version == ctx->pos_version) return B2_OK;
+    ctx->nl_checked_version = ctx->pos_version;
     const int n = ctx->n, ng = ctx->ngroups, T = 256;
     static const double fat_factor = getenv("B2_FAT_FACTOR") ? atof(getenv("B2_FAT_FACTOR")) : 1.2;
     Grid g = make_grid(ctx);
