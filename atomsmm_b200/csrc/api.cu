@@ -101,13 +101,19 @@ extern "C" int b2_create(int device, b2_context** out) {
         return b2_fail(nullptr, B2_ERR_CUDA, "cannot initialise device %d", device);
     }
     ctx->own_stream = ctx->stream;
+    if (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        delete ctx;
+        return b2_fail(nullptr, B2_ERR_CUDA, "cannot create the side stream");
+    }
     for (int g = 0; g < B2_FSLOTS; g++) ctx->fvalid[g] = -1;
     if (cudaMalloc(&ctx->d_energy, sizeof(double)*96) != cudaSuccess ||
         cudaMalloc(&ctx->rng_state, sizeof(unsigned long long)*4) != cudaSuccess ||
         cudaMalloc(&ctx->sum_partial, sizeof(double)*1024) != cudaSuccess ||
         cudaMalloc(&ctx->ticket, sizeof(unsigned)*4) != cudaSuccess ||
         cudaMalloc(&ctx->nl_flags, sizeof(int)*16) != cudaSuccess ||
-        cudaMalloc(&ctx->band_pairs, sizeof(int)*2*ctx->band_capacity) != cudaSuccess ||
+        cudaMalloc(&ctx->band_pairs, sizeof(int)*4*ctx->band_capacity) != cudaSuccess ||
         cudaMalloc(&ctx->band_count, sizeof(unsigned)*2) != cudaSuccess) {
         delete ctx;
         return b2_fail(nullptr, B2_ERR_CUDA, "device allocation failed");
@@ -150,6 +156,9 @@ extern "C" int b2_destroy(b2_context* ctx) {
     cudaFree(ctx->con_ptr); cudaFree(ctx->con_pairs); cudaFree(ctx->con_d2); cudaFree(ctx->xcon);
     for (BondedForce& bf : ctx->bonded_forces) free_bonded(bf);
     for (PmeForce& pm : ctx->pme_forces) pme_release(pm);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return B2_OK;

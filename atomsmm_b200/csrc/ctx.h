@@ -79,6 +79,8 @@ struct b2_context {
     int device = 0;
     cudaStream_t stream = 0;
     cudaStream_t own_stream = 0;
+    cudaStream_t side_stream = 0;                 // second lane: two independent pair forces run concurrently
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     long long counters[8] = {0};
 
@@ -224,7 +226,7 @@ int b2_free_all(b2_context* ctx);
 int nl_setup(b2_context* ctx);                        // cells + list allocation for current box
 int nl_prepare(b2_context* ctx, bool force);          // wrap + skin test + conditional rebuild
 int nl_initial_build(b2_context* ctx);                // sized build with capacity fitting (syncs)
-int pair_eval_forces(b2_context* ctx, const PairForce& pf, float4* out, bool accumulate);
+int pair_eval_forces(b2_context* ctx, const PairForce& pf, float4* out, bool accumulate, int lane = 0);
 int pair_eval_energy(b2_context* ctx, const PairForce& pf, int group);
 int pair_count_set(b2_context* ctx, const PairForce& pf, long long* count, unsigned long long* checksum,
                    int* pairs_dev, long long capacity);

@@ -441,6 +441,45 @@ int forces_ensure(b2_context* ctx, uint32_t mask, int slot) {
     return B2_OK;
 }
 
+static bool has_pair_force(const b2_context* ctx, uint32_t mask) {
+    for (const PairForce& pf : ctx->pair_forces)
+        if (mask & (1u << pf.group)) return true;
+    return false;
+}
+
+// Two force slots that both need pair work at the same positions (RESPA evaluates the near and the
+// far force back to back at the end of a step): their pair kernels are independent -- different
+// lists, different outputs -- and run concurrently on two streams, which become two branches of
+// the step's CUDA graph.  Each kernel alone leaves ~30 % of the issue slots idle and has its own tail.
+static int forces_ensure_dual(b2_context* ctx, uint32_t mask_a, int slot_a, uint32_t mask_b, int slot_b) {
+    B2_TRY(dist_sync_positions(ctx));
+    B2_TRY(nl_prepare(ctx, false));
+    B2_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    B2_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+    bool written_a = false, written_b = false;
+    for (const PairForce& pf : ctx->pair_forces) {
+        if (!(mask_b & (1u << pf.group))) continue;
+        B2_TRY(pair_eval_forces(ctx, pf, ctx->fbuf[slot_b], written_b, 1));
+        written_b = true;
+    }
+    for (const PairForce& pf : ctx->pair_forces) {
+        if (!(mask_a & (1u << pf.group))) continue;
+        B2_TRY(pair_eval_forces(ctx, pf, ctx->fbuf[slot_a], written_a, 0));
+        written_a = true;
+    }
+    B2_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+    B2_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    const uint32_t masks[2] = {mask_a, mask_b};
+    const int slots[2] = {slot_a, slot_b};
+    for (int k = 0; k < 2; k++) {
+        B2_TRY(bonded_eval_forces(ctx, masks[k], ctx->fbuf[slots[k]]));
+        for (PmeForce& pm : ctx->pme_forces)
+            if (masks[k] & (1u << pm.group)) B2_TRY(pme_eval(ctx, pm, ctx->fbuf[slots[k]], nullptr));
+        ctx->fvalid[slots[k]] = ctx->pos_version;
+    }
+    return B2_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // program execution
 // ---------------------------------------------------------------------------------------------
@@ -607,9 +646,27 @@ static int run_one_step(b2_context* ctx) {
     for (size_t k = 0; k < ctx->ops.size(); k++) {
         const b2_op& op = ctx->ops[k];
         switch (op.kind) {
-        case B2_OP_EVAL:
-            B2_TRY(forces_ensure(ctx, (uint32_t)op.a, op.b));
+        case B2_OP_EVAL: {
+            static const bool dual_allowed = getenv("B2_NO_DUAL") == nullptr;
+            const bool stale = ctx->fbuf[op.b] && ctx->fvalid[op.b] != ctx->pos_version;
+            int partner = -1;
+            if (dual_allowed && stale && !ctx->profiling && has_pair_force(ctx, (uint32_t)op.a)) {
+                // a later evaluation at the same positions that also needs pair work?
+                for (size_t q = k + 1; q < ctx->ops.size() && ctx->ops[q].kind == B2_OP_EVAL; q++) {
+                    const b2_op& o = ctx->ops[q];
+                    if (o.b != op.b && ctx->fbuf[o.b] && ctx->fvalid[o.b] != ctx->pos_version &&
+                        has_pair_force(ctx, (uint32_t)o.a) && !((uint32_t)o.a & (uint32_t)op.a)) {
+                        partner = (int)q;
+                        break;
+                    }
+                }
+            }
+            if (partner >= 0)
+                B2_TRY(forces_ensure_dual(ctx, (uint32_t)op.a, op.b, (uint32_t)ctx->ops[partner].a, ctx->ops[partner].b));
+            else
+                B2_TRY(forces_ensure(ctx, (uint32_t)op.a, op.b));
             break;
+        }
         case B2_OP_PERDOF: {
             PerDofTable tab = make_table(ctx);
             k_perdof<<<(ndof + T - 1)/T, T, 0, s>>>(3*lo, 3*hi, tab, op.a, ctx->code + op.b, op.c, ctx->consts,

@@ -355,30 +355,32 @@ static double effective_cutoff(const PairForce& pf) {
 
 template <class POT, class POTD>
 static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, POTD potd, float rc2, float4* out,
-                        bool accumulate) {
+                        bool accumulate, int lane) {
     const double rcd = effective_cutoff(pf);
-    BandBuffer bb{ctx->band_pairs, ctx->band_count, ctx->band_capacity};
-    B2_CUDA(cudaMemsetAsync(ctx->band_count, 0, sizeof(unsigned), ctx->stream));
+    // lane 1 = the side stream, with its own half of the band buffer
+    cudaStream_t stream = lane ? ctx->side_stream : ctx->stream;
+    BandBuffer bb{ctx->band_pairs + (lane ? 2*(size_t)ctx->band_capacity : 0), ctx->band_count + lane, ctx->band_capacity};
+    B2_CUDA(cudaMemsetAsync(bb.count, 0, sizeof(unsigned), stream));
     const NList& L = ctx->lists[pf.list];
     const int blocks = (ctx->g_hi - ctx->g_lo + WPB - 1)/WPB;
     if (blocks == 0) return B2_OK;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->profiling) {
         cudaEventCreate(&ev0); cudaEventCreate(&ev1);
-        cudaEventRecord(ev0, ctx->stream);
+        cudaEventRecord(ev0, stream);
     }
-    k_pair_force<POT><<<blocks, 32*WPB, 0, ctx->stream>>>(ctx->n, ctx->g_lo, ctx->g_hi, ctx->x, ctx->par[pf.set],
+    k_pair_force<POT><<<blocks, 32*WPB, 0, stream>>>(ctx->n, ctx->g_lo, ctx->g_hi, ctx->x, ctx->par[pf.set],
                                                           L.entries, L.counts, L.gflags, L.cap, out,
                                                           accumulate ? 1 : 0, pot, rc2, bb, ctx->box[0], ctx->box[1],
                                                           ctx->box[2]);
     if (ctx->profiling) {
-        cudaEventRecord(ev1, ctx->stream);
+        cudaEventRecord(ev1, stream);
         ctx->prof_events.push_back(ev0); ctx->prof_events.push_back(ev1);
         ctx->prof_tags.push_back((int)(&pf - ctx->pair_forces.data()));
     }
     ctx->counters[2]++;
     B2_LAUNCH_CHECK();
-    k_pair_band<POTD><<<8, 128, 0, ctx->stream>>>(ctx->x, ctx->pard[pf.set], bb, potd, rcd*rcd, ctx->box[0],
+    k_pair_band<POTD><<<8, 128, 0, stream>>>(ctx->x, ctx->pard[pf.set], bb, potd, rcd*rcd, ctx->box[0],
                                                   ctx->box[1], ctx->box[2], out);
     B2_LAUNCH_CHECK();
     return B2_OK;
@@ -432,11 +434,11 @@ struct DoubleOf<LJCPot<A, B, C, D, E, float>> { typedef LJCPot<A, B, C, D, E, do
 template <>
 struct DoubleOf<SoftcorePot<float>> { typedef SoftcorePot<double> type; };
 
-int pair_eval_forces(b2_context* ctx, const PairForce& pf, float4* out, bool accumulate) {
+int pair_eval_forces(b2_context* ctx, const PairForce& pf, float4* out, bool accumulate, int lane) {
     float rc2, unused;
     PotParams<float> p = make_params<float>(ctx, pf, &rc2);
     PotParams<double> pd = make_params<double>(ctx, pf, &unused);
-#define CALL_FORCE { typename DoubleOf<decltype(pot)>::type potd{pd}; B2_TRY(launch_force(ctx, pf, pot, potd, rc2, out, accumulate)); }
+#define CALL_FORCE { typename DoubleOf<decltype(pot)>::type potd{pd}; B2_TRY(launch_force(ctx, pf, pot, potd, rc2, out, accumulate, lane)); }
     DISPATCH(float, CALL_FORCE, CALL_FORCE);
 #undef CALL_FORCE
     return B2_OK;
