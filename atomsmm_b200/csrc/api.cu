@@ -783,6 +783,10 @@ extern "C" int b2_load_program(b2_context* ctx, const int* ops, int nops, const 
     B2_CUDA(cudaMemcpy(ctx->rng_state, st, sizeof(st), cudaMemcpyHostToDevice));
     ctx->program_loaded = true;
     ctx->eager_steps = 0;
+    ctx->prologue_valid = false;
+    ctx->uses_random = false;
+    for (int k = 0; k + 1 < ncode; k += 2)
+        if (code[k] == VM_GAUSS || code[k] == VM_UNIF) ctx->uses_random = true;
     return B2_OK;
 }
 
@@ -790,6 +794,10 @@ extern "C" int b2_set_globals(b2_context* ctx, int first, int count, const doubl
     if (!ctx || first < 0 || first + count > ctx->nglobals) return b2_fail(ctx, B2_ERR_ARG, "global index out of range");
     B2_CUDA(cudaMemcpyAsync(ctx->globals + first, values_host, sizeof(double)*count, cudaMemcpyHostToDevice, ctx->stream));
     B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->prologue_valid) {           // coefficients derived from globals must be recomputed
+        ctx->prologue_valid = false;
+        program_release(ctx);
+    }
     return B2_OK;
 }
 

@@ -184,6 +184,8 @@ struct b2_context {
     unsigned* ticket = nullptr;                   // last-block-done counter of the velocity kernel
     unsigned long long* rng_state = nullptr;      // [0] seed, [1] draw counter
     bool program_loaded = false;
+    bool uses_random = false;                     // the program draws random numbers (needs the step counter)
+    bool prologue_valid = false;                  // the invariant coefficient prologue has been evaluated
     cudaGraphExec_t graph_exec = nullptr;
     bool graph_ready = false;
     int eager_steps = 0;

@@ -634,8 +634,10 @@ static int run_one_step(b2_context* ctx) {
     cudaStream_t s = ctx->stream;
     // the step counter of the RNG streams is advanced by the first kernel of the step when that is the
     // scalar prologue, otherwise by a kernel of its own
-    const bool folded_begin = !ctx->ops.empty() && ctx->ops[0].kind == B2_OP_GLOBAL;
-    if (!folded_begin) {
+    const bool run_prologue = !ctx->ops.empty() && ctx->ops[0].kind == B2_OP_GLOBAL &&
+                              !(ctx->ops[0].d == 1 && ctx->prologue_valid);
+    const bool folded_begin = run_prologue;
+    if (!folded_begin && ctx->uses_random) {
         k_step_begin<<<1, 1, 0, s>>>(ctx->rng_state);
         B2_LAUNCH_CHECK();
     }
@@ -691,9 +693,11 @@ static int run_one_step(b2_context* ctx) {
             break;
         }
         case B2_OP_GLOBAL:
+            if (k == 0 && !run_prologue) break;          // invariant coefficients already in place
             k_global<<<1, 64, 0, s>>>(ctx->code + op.b, op.c, ctx->consts, ctx->nconsts, ctx->globals,
                                        ctx->nglobals, ctx->rng_state, ctx->d_energy, (k == 0 && folded_begin) ? 1 : 0);
             B2_LAUNCH_CHECK();
+            if (k == 0 && op.d == 1) ctx->prologue_valid = true;
             break;
         case B2_OP_KICK: {
             int consumed = 0;

@@ -637,7 +637,9 @@ def lower_program(integrator, group_mask_all=0xffffffff, parameters=None, fast=T
         for slot, ast in prologue:
             X.compile_ast(ast, resolve_global, P.bc)
             P.bc.emit('STOREG', slot)
-        P.ops.insert(0, [OP_GLOBAL, 0, start, (len(P.bc.code) - start)//2, 0, 0, 0, 0])
+        # d = 1 marks the prologue: it only depends on globals the program never assigns, so the engine
+        # runs it once and again only after the host changed a global
+        P.ops.insert(0, [OP_GLOBAL, 0, start, (len(P.bc.code) - start)//2, 1, 0, 0, 0])
     _fuse_kicks(P)
     if fast:
         _fuse_velocity_ops(P)
