@@ -392,7 +392,14 @@ def main():
     bytes_per_launch = n*(24 + 16 + 16) + 4*dominant['entries']
     achieved = bytes_per_launch/avg_s/1e9
     pair_ms_per_md_step = sum(p['total_ms'] for p in used)/8.0
-    roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved/peak, traffic=None,
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as handle:
+            if args.workload == 'c2' and args.reps == 4:
+                traffic = json.load(handle).get(dominant['name'])
+    except (OSError, ValueError):
+        pass
+    roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved/peak, traffic=traffic,
                     peak_kind=peak_kind, kernel='k_pair_force<%s> group %d' % (dominant['name'], dominant['group']),
                     avg_launch_us=avg_s*1e6, algorithmic_bytes_per_launch=bytes_per_launch,
                     list_entries=dominant['entries'],
