@@ -89,3 +89,13 @@ def replicate(system, positions, box, reps, jitter=0.002, seed=1):
                              for t in force._torsions]
         big.addForce(new)
     return big, pos
+
+
+def subset(case, nresidues):
+    """(structure, forcefield) with only the first ``nresidues`` residues of a data set, in the original
+    box: a small cluster for CPU-only tests of host logic (not a physical liquid)."""
+    structure, ff = fixtures.load(case)
+    record = fixtures._CACHE[case]
+    natoms = sum(len(r[2]) for r in record['residues'][:nresidues])
+    small = dict(record, residues=record['residues'][:nresidues], positions=record['positions'][:natoms])
+    return fixtures.Structure(small), ff
