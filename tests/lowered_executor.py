@@ -203,3 +203,99 @@ class Executor(object):
                     raise NotImplementedError('op %d' % kind)
 
     program_derivative_slots = None
+
+
+class DistributedExecutor(Executor):
+    """The domain-decomposition protocol of csrc/dist.cu on top of torch.distributed (gloo on CPU): each
+    rank integrates only the atoms of its ownership range (engine.partition_ranges over whole molecules),
+    positions are exchanged before a force evaluation, sums over degrees of freedom are all-reduced, and
+    every rank runs the scalar programs redundantly.  Getters gather the full state."""
+
+    def __init__(self, system, integrator, positions, velocities, dist, pair_mask=0xffffffff, **kwargs):
+        super().__init__(system, integrator, positions, velocities, **kwargs)
+        import torch
+        from atomsmm_b200 import engine
+        self.dist, self.torch = dist, torch
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        molecule, _ = engine._molecules(system)
+        self.ranges = engine.partition_ranges(molecule, self.world)     # caller order = engine order here
+        self.lo, self.hi = int(self.ranges[self.rank]), int(self.ranges[self.rank + 1])
+        self.owned = np.zeros((self.n, 1), bool)
+        self.owned[self.lo:self.hi] = True
+        self.pair_mask = pair_mask      # force groups that contain pair forces: only those need foreign atoms
+        self.synced = self.version
+        self.exchanges = 0
+
+    def gather(self, array):
+        """All ranks end up with every rank's owned segment (the grouped broadcasts of dist.cu)."""
+        t = self.torch.from_numpy(np.ascontiguousarray(array))
+        for r in range(self.world):
+            segment = t[int(self.ranges[r]):int(self.ranges[r + 1])]
+            if segment.numel():
+                self.dist.broadcast(segment, src=r)
+        return t.numpy()
+
+    def all_reduced(self, value):
+        t = self.torch.tensor([float(np.sum(np.where(self.owned, value, 0.0)))], dtype=self.torch.float64)
+        self.dist.all_reduce(t)
+        return float(t)
+
+    def ensure(self, mask, slot):
+        cached = self.forces.get(slot)
+        if cached is not None and cached[0] == self.version:
+            return
+        if (mask & self.pair_mask) and self.synced != self.version:
+            self.x = self.gather(self.x)
+            self.synced = self.version
+            self.exchanges += 1
+        super().ensure(mask, slot)
+
+    def step(self, count=1):
+        """Executor.step with every update masked to the owned range and every sum all-reduced."""
+        massive = (self.mass > 0)[:, None] & self.owned
+        w = np.where(self.mass > 0, 1.0/np.where(self.mass > 0, self.mass, 1.0), 0.0)[:, None]
+        for _ in range(count):
+            for op in self.program.ops:
+                kind = op[0]
+                if kind == L.OP_EVAL:
+                    self.ensure(op[1], op[2])
+                elif kind == L.OP_GLOBAL:
+                    self.run_vm(op[2], op[3])
+                elif kind == L.OP_PERDOF:
+                    value = np.broadcast_to(self.run_vm(op[2], op[3], True), (self.n, 3)).astype(np.float64)
+                    if op[1] == 0:
+                        self.x = np.where(massive, value, self.x)
+                        self.version += 1
+                    elif op[1] == 1:
+                        self.v = np.where(massive, value, self.v)
+                    else:
+                        self.perdof[op[1] - 2] = np.where(self.owned, value, self.perdof[op[1] - 2])
+                elif kind == L.OP_SUM:
+                    value = np.broadcast_to(self.run_vm(op[2], op[3], True), (self.n, 3))
+                    self.globals[op[1]] = self.all_reduced(value)
+                elif kind == L.OP_KICK:
+                    nterms, offset, drift, prescale, mvv, cstart, clen = op[1:8]
+                    if prescale >= 0:
+                        self.v = np.where(massive, self.v*self.globals[prescale], self.v)
+                    if nterms > 0:
+                        a = np.zeros_like(self.v)
+                        for t in range(nterms):
+                            slot, coef, sign = self.code[offset + 3*t: offset + 3*t + 3]
+                            version, f = self.forces[slot]
+                            assert version == self.version
+                            a += sign*self.globals[coef]*f
+                        self.v = np.where(massive, self.v + a*w, self.v)
+                    if drift >= 0:
+                        self.x = np.where(massive, self.x + self.globals[drift]*self.v, self.x)
+                        self.version += 1
+                    if mvv >= 0:
+                        self.globals[mvv] = self.all_reduced(self.mass[:, None]*self.v*self.v)
+                        if clen > 0:
+                            self.run_vm(cstart, clen)
+                elif kind == L.OP_UPDATE_STATE:
+                    pass
+                else:
+                    raise NotImplementedError('op %d in the distributed executor' % kind)
+
+    def full_state(self):
+        return self.gather(self.x.copy()), self.gather(self.v.copy())

@@ -2,8 +2,10 @@
 The N > 1 path.
 
 CPU (gloo, world_size 2): the host-side logic of the spatial decomposition -- ownership ranges from
-the C library's pure-host entry point, the communicator-id broadcast, and the max-over-ranks /
-sum-over-ranks aggregation the benchmark uses.
+the C library's pure-host entry point, the communicator-id broadcast, the max-over-ranks /
+sum-over-ranks aggregation the benchmark uses -- and the exchange protocol of csrc/dist.cu itself
+(owned-range updates, position exchange before pair forces, all-reduced sums) executed on the lowered
+RESPA + Nose-Hoover program by tests/lowered_executor.py.
 
 GPU (NCCL, world_size 2, skipped on a single-GPU box): ONE RESPA water system integrated by two
 ranks with domain decomposition must reproduce the single-GPU trajectory and single-point
@@ -72,6 +74,61 @@ def _host_worker(rank, world, port, out):
         out.put((rank, repr(error)))
     finally:
         dist.destroy_process_group()
+
+
+def _protocol_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    dist = _init(rank, world, port, 'gloo')
+    try:
+        import atomsmm_b200 as atomsmm
+        from atomsmm_b200 import unit
+        from lowered_executor import DistributedExecutor, Executor
+        import test_lowered_programs as T
+        system, pos = T.water_cluster(40)
+        respa = atomsmm.RESPASystem(system, 7*unit.angstroms, 5*unit.angstroms)
+        dof = atomsmm.countDegreesOfFreedom(respa)
+        vel = T.velocities(respa, 9)
+
+        def factory():
+            nh = atomsmm.NoseHooverPropagator(300*T.K, dof, 100*T.fs)
+            return atomsmm.TrotterSuzukiPropagator(atomsmm.RespaPropagator([4, 2, 1]),
+                                                   atomsmm.SuzukiYoshidaPropagator(nh, 3)).integrator(4*T.fs)
+        mask = 0b111 | (1 << 31)
+        shared = DistributedExecutor(respa, factory(), pos, vel, dist, pair_mask=0b110 | (1 << 31), group_mask=mask)
+        single = Executor(respa, factory(), pos, vel, group_mask=mask)
+        shared.step(2)
+        single.step(2)
+        x, v = shared.full_state()
+        assert 0 < shared.hi - shared.lo < len(pos)
+        assert np.max(np.abs(x - single.x)) < 1e-12 and np.max(np.abs(v - single.v)) < 1e-10
+        # two exchanges per RESPA[4,2,1] step: before the mid-step near force and before the end-of-step
+        # near + far forces (which share one)
+        assert shared.exchanges == 2*2
+        names = shared.program.global_names
+        assert shared.globals[names.index('p_eta')] == pytest.approx(single.globals[names.index('p_eta')], rel=1e-10)
+        out.put((rank, 'ok'))
+    except Exception as error:    # pragma: no cover
+        import traceback
+        out.put((rank, traceback.format_exc() + repr(error)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_domain_decomposition_protocol_world_size_2_gloo():
+    """The exchange / ownership / all-reduce protocol of csrc/dist.cu, executed on the CPU by two gloo
+    ranks on the lowered RESPA + Nose-Hoover program, reproduces the single-process result."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_protocol_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, 'ok'), (1, 'ok')], results
 
 
 def test_host_logic_world_size_2_gloo():
