@@ -72,7 +72,7 @@ struct NList {
     int cap = 0;                  // entries per group
     int* entries = nullptr;       // [ngroups][cap]
     int* counts = nullptr;        // [ngroups]
-    unsigned char* gflags = nullptr;  // [ngroups] bit0: per-pair minimum image needed; bit1: list reaches another rank's atoms
+    unsigned char* gflags = nullptr;  // [ngroups] bit0: group needs per-pair minimum image
 };
 
 struct b2_context {
@@ -226,12 +226,9 @@ int b2_free_all(b2_context* ctx);
 
 // ---- cross-file entry points (host) ---------------------------------------------------------
 int nl_setup(b2_context* ctx);                        // cells + list allocation for current box
-int nl_prepare(b2_context* ctx, bool force);          // skin test + conditional rebuild
-int nl_check(b2_context* ctx, int lo, int hi, bool force);   // skin test over a range of atoms
-int nl_latch(b2_context* ctx);                        // flags[12] = rebuild decision of this evaluation
-int nl_rebuild(b2_context* ctx);                      // the device-conditional rebuild pipeline
+int nl_prepare(b2_context* ctx, bool force);          // wrap + skin test + conditional rebuild
 int nl_initial_build(b2_context* ctx);                // sized build with capacity fitting (syncs)
-int pair_eval_forces(b2_context* ctx, const PairForce& pf, float4* out, bool accumulate, int lane = 0, int phase = 0);
+int pair_eval_forces(b2_context* ctx, const PairForce& pf, float4* out, bool accumulate, int lane = 0);
 int pair_eval_energy(b2_context* ctx, const PairForce& pf, int group);
 int pair_count_set(b2_context* ctx, const PairForce& pf, long long* count, unsigned long long* checksum,
                    int* pairs_dev, long long capacity);
@@ -245,7 +242,6 @@ int dist_sync_positions(b2_context* ctx);
 int dist_gather3(b2_context* ctx, double* array);
 int dist_gather_forces(b2_context* ctx, float4* array);
 int dist_allreduce(b2_context* ctx, double* values, int count);
-int dist_allreduce_flag(b2_context* ctx, int* flag);
 void dist_release(b2_context* ctx);
 int forces_ensure(b2_context* ctx, uint32_t mask, int slot);
 int inner_prepare(b2_context* ctx);

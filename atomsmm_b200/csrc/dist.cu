@@ -157,12 +157,6 @@ int dist_sync_positions(b2_context* ctx) {
 int dist_gather3(b2_context* ctx, double* array) { return allgather_segments(ctx, array, 3*sizeof(double)); }
 int dist_gather_forces(b2_context* ctx, float4* array) { return allgather_segments(ctx, array, sizeof(float4)); }
 
-int dist_allreduce_flag(b2_context* ctx, int* flag) {
-    if (ctx->nranks == 1) return B2_OK;
-    B2_NCCL(g_nccl.AllReduce(flag, flag, 1, ncclInt, ncclMax, (ncclComm_t)ctx->comm, ctx->stream));
-    return B2_OK;
-}
-
 int dist_allreduce(b2_context* ctx, double* values, int count) {
     if (ctx->nranks == 1) return B2_OK;
     B2_NCCL(g_nccl.AllReduce(values, values, count, ncclDouble, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));

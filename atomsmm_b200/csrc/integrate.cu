@@ -412,51 +412,6 @@ int inner_prepare(b2_context* ctx) {
 // ---------------------------------------------------------------------------------------------
 // force-slot management
 // ---------------------------------------------------------------------------------------------
-// Domain decomposition: pair forces of one or two slots with the position exchange hidden behind the
-// interior work.  (1) Every rank tests the skin on its OWNED atoms and the decision is all-reduced (one
-// int) and latched; (2) on the side stream the pair kernels run over the interior groups -- those whose
-// lists only reach owned atoms, ~90 % of the groups of a compact Hilbert domain -- unless a rebuild is
-// pending; (3) meanwhile the main stream exchanges the positions and runs the (conditional) rebuild
-// pipeline; (4) the main stream then handles the boundary groups, or all groups after a rebuild.
-static int forces_ensure_overlapped(b2_context* ctx, const uint32_t* masks, const int* slots, int count) {
-    static const bool overlap = getenv("B2_NO_OVERLAP") == nullptr;
-    const bool check = !(ctx->lists_built && ctx->nl_checked_version == ctx->pos_version);
-    if (check) {
-        ctx->nl_checked_version = ctx->pos_version;
-        B2_TRY(nl_check(ctx, ctx->a_lo, ctx->a_hi, false));
-        B2_TRY(dist_allreduce_flag(ctx, ctx->nl_flags));
-    }
-    B2_TRY(nl_latch(ctx));
-    const bool split = overlap && ctx->x_synced != ctx->pos_version;     // something to hide
-    if (split) {
-        B2_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        B2_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
-        for (int k = 0; k < count; k++) {
-            bool written = false;
-            for (const PairForce& pf : ctx->pair_forces) {
-                if (!(masks[k] & (1u << pf.group))) continue;
-                B2_TRY(pair_eval_forces(ctx, pf, ctx->fbuf[slots[k]], written, 1, 1));
-                written = true;
-            }
-        }
-        B2_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
-    }
-    B2_TRY(dist_sync_positions(ctx));
-    if (check) B2_TRY(nl_rebuild(ctx));
-    if (split) B2_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-    for (int k = 0; k < count; k++) {
-        bool written = false;
-        for (const PairForce& pf : ctx->pair_forces) {
-            if (!(masks[k] & (1u << pf.group))) continue;
-            B2_TRY(pair_eval_forces(ctx, pf, ctx->fbuf[slots[k]], written, 0, split ? 2 : 0));
-            written = true;
-        }
-        B2_TRY(bonded_eval_forces(ctx, masks[k], ctx->fbuf[slots[k]]));
-        ctx->fvalid[slots[k]] = ctx->pos_version;
-    }
-    return B2_OK;
-}
-
 int forces_ensure(b2_context* ctx, uint32_t mask, int slot) {
     if (slot < 0 || slot >= B2_FSLOTS) return b2_fail(ctx, B2_ERR_ARG, "bad force slot %d", slot);
     if (ctx->fbuf[slot] == nullptr) {
@@ -468,14 +423,6 @@ int forces_ensure(b2_context* ctx, uint32_t mask, int slot) {
     bool any_pair = false;
     for (const PairForce& pf : ctx->pair_forces)
         if (mask & (1u << pf.group)) any_pair = true;
-    // opt-in (B2_OVERLAP=1): measured on config 5 it does not pay yet -- 1.00 G atom-steps/s at 8 GPUs
-    // against 1.04 G for the plain exchange-then-compute sequence
-    static const bool overlapped = getenv("B2_OVERLAP") != nullptr;
-    if (overlapped && any_pair && ctx->nranks > 1 && !ctx->profiling) {
-        const uint32_t masks[1] = {mask};
-        const int slots[1] = {slot};
-        return forces_ensure_overlapped(ctx, masks, slots, 1);
-    }
     if (any_pair) {
         B2_TRY(dist_sync_positions(ctx));
         B2_TRY(nl_prepare(ctx, false));
@@ -716,12 +663,7 @@ static int run_one_step(b2_context* ctx) {
                     }
                 }
             }
-            static const bool overlapped = getenv("B2_OVERLAP") != nullptr;
-            if (partner >= 0 && ctx->nranks > 1 && overlapped) {
-                const uint32_t masks[2] = {(uint32_t)op.a, (uint32_t)ctx->ops[partner].a};
-                const int slots[2] = {op.b, ctx->ops[partner].b};
-                B2_TRY(forces_ensure_overlapped(ctx, masks, slots, 2));
-            } else if (partner >= 0)
+            if (partner >= 0)
                 B2_TRY(forces_ensure_dual(ctx, (uint32_t)op.a, op.b, (uint32_t)ctx->ops[partner].a, ctx->ops[partner].b));
             else
                 B2_TRY(forces_ensure(ctx, (uint32_t)op.a, op.b));

@@ -32,7 +32,6 @@ struct BuildArgs {
     int* counts[B2_MAX_LISTS];
     unsigned char* gflags[B2_MAX_LISTS];
     int cap[B2_MAX_LISTS];
-    int own_lo, own_hi;           // atoms owned by this rank
 };
 
 struct Grid {
@@ -58,10 +57,10 @@ __device__ __forceinline__ bool is_excluded(int oi, int oj, unsigned long long m
 }
 
 // K8: skin test, one pass over x and xref (48 B/atom), before every pair-force evaluation.
-__global__ void k_skin_check(int lo, int hi, const double* __restrict__ x, const double* __restrict__ xref, double limit2,
+__global__ void k_skin_check(int n, const double* __restrict__ x, const double* __restrict__ xref, double limit2,
                              int* flags, int have_ref) {
-    int i = lo + blockIdx.x*blockDim.x + threadIdx.x;
-    if (i >= hi) return;
+    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
     if (have_ref) {
         double dx = x[3*i] - xref[3*i], dy = x[3*i+1] - xref[3*i+1], dz = x[3*i+2] - xref[3*i+2];
         if (dx*dx + dy*dy + dz*dz > limit2) flags[0] = 1;
@@ -315,7 +314,14 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
         if (all[d]) { c_lo[d] = 0; c_n[d] = g.nc[d]; }
         else { c_lo[d] = a0; c_n[d] = cover; }
     }
-    unsigned remote[B2_MAX_LISTS] = {0, 0, 0, 0};     // some list entry belongs to another rank
+    if (lane == 0) {
+        for (int k = 0; k < a.nlists; k++) {
+            unsigned char f = 0;
+            for (int d = 0; d < 3; d++)
+                if ((double)(2.f*hi[d]) + a.rlist[k] > 0.5*g.box[d] - 1e-4) f = 1;
+            a.gflags[k][warp] = f;
+        }
+    }
     float rl2[B2_MAX_LISTS];
     for (int k = 0; k < B2_MAX_LISTS; k++) { const float r = (float)a.rlist[k] + NL_MARGIN; rl2[k] = r*r; }
     const float rmax2 = rmax*rmax;
@@ -372,7 +378,6 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
                     if (pos < a.cap[k]) a.entries[k][(size_t)warp*a.cap[k] + pos] = (int)((m << 24) | (unsigned)j);
                 }
                 count[k] += __popc(ballot);
-                remote[k] |= __ballot_sync(FULL, in && (j < a.own_lo || j >= a.own_hi));
             }
         }
     };
@@ -492,13 +497,6 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
     }
     if (lane == 0) {
         for (int k = 0; k < a.nlists; k++) {
-            // bit 0: the group is so extended that pairs need the minimum image individually;
-            // bit 1: the list reaches atoms owned by another rank ("boundary" group)
-            unsigned char f = 0;
-            for (int d = 0; d < 3; d++)
-                if ((double)(2.f*hi[d]) + a.rlist[k] > 0.5*g.box[d] - 1e-4) f = 1;
-            if (remote[k]) f |= 2;
-            a.gflags[k][warp] = f;
             a.counts[k][warp] = min(count[k], a.cap[k]);
             if (count[k] > a.cap[k]) flags[1] = 1;
             if (count[k] > flags[3]) atomicMax(&flags[3], count[k]);
@@ -601,28 +599,6 @@ static int alloc_lists(b2_context* ctx, int k, int cap) {
     return B2_OK;
 }
 
-__global__ void k_latch_flag(int* flags) { flags[12] = flags[0]; }
-
-// skin test over the atoms [lo, hi) (all atoms on one GPU; the owned range under domain decomposition,
-// where the caller then all-reduces flags[0]) and a latched copy of the decision in flags[12]
-int nl_check(b2_context* ctx, int lo, int hi, bool force) {
-    if (ctx->nlists == 0 || hi <= lo) return B2_OK;
-    const int T = 256;
-    const double limit = 0.5*ctx->skin;
-    k_skin_check<<<(hi - lo + T - 1)/T, T, 0, ctx->stream>>>(lo, hi, ctx->x, ctx->xref, limit*limit, ctx->nl_flags,
-                                                               (ctx->lists_built && !force) ? 1 : 0);
-    B2_LAUNCH_CHECK();
-    return B2_OK;
-}
-
-int nl_latch(b2_context* ctx) {
-    k_latch_flag<<<1, 1, 0, ctx->stream>>>(ctx->nl_flags);
-    B2_LAUNCH_CHECK();
-    return B2_OK;
-}
-
-int nl_rebuild(b2_context* ctx);
-
 // enqueue: skin test, then the (device-conditional) rebuild pipeline
 int nl_prepare(b2_context* ctx, bool force) {
     if (ctx->nlists == 0) {
@@ -632,18 +608,15 @@ int nl_prepare(b2_context* ctx, bool force) {
     // the near and the far force back to back at the end of a step
     if (!force && ctx->lists_built && ctx->nl_checked_version == ctx->pos_version) return B2_OK;
     ctx->nl_checked_version = ctx->pos_version;
-    B2_TRY(nl_check(ctx, 0, ctx->n, force));
-    return nl_rebuild(ctx);
-}
-
-// the rebuild pipeline; every kernel returns at once unless flags[0] is set
-int nl_rebuild(b2_context* ctx) {
-    if (ctx->nlists == 0) return B2_OK;
     const int n = ctx->n, ng = ctx->ngroups, T = 256;
     static const double fat_factor = getenv("B2_FAT_FACTOR") ? atof(getenv("B2_FAT_FACTOR")) : 1.2;
     Grid g = make_grid(ctx);
     cudaStream_t s = ctx->stream;
+    double limit = 0.5*ctx->skin;
     int* hmax = ctx->nl_flags + 5;
+    k_skin_check<<<(n + T - 1)/T, T, 0, s>>>(n, ctx->x, ctx->xref, limit*limit, ctx->nl_flags,
+                                               (ctx->lists_built && !force) ? 1 : 0);
+    B2_LAUNCH_CHECK();
     k_group_geom<<<(8*ng + T - 1)/T, T, 0, s>>>(n, ng, ctx->x, g, ctx->prel, ctx->gcen, ctx->ghalf, ctx->gcell,
                                                  ctx->cell_count, hmax, (float)(fat_factor*ctx->cellsize[0]),
                                                  ctx->fat_list, ng, ctx->nl_flags);
@@ -660,7 +633,6 @@ int nl_rebuild(b2_context* ctx) {
     B2_LAUNCH_CHECK();
     BuildArgs a;
     a.nlists = ctx->nlists;
-    a.own_lo = ctx->a_lo; a.own_hi = ctx->a_hi;
     for (int k = 0; k < B2_MAX_LISTS; k++) {
         const NList& L = ctx->lists[k < ctx->nlists ? k : 0];
         double r = L.cutoff + ctx->skin;

@@ -157,17 +157,11 @@ __global__ void __launch_bounds__(32*WPB, 8) k_pair_force(int n, int g_lo, int n
                                                       const int* __restrict__ counts,
                                                       const unsigned char* __restrict__ gflags, int cap,
                                                       float4* __restrict__ out, int accumulate, POT pot,
-                                                      float rc2, BandBuffer bb, double bx, double by, double bz,
-                                                      int phase, const int* __restrict__ latch) {
+                                                      float rc2, BandBuffer bb, double bx, double by, double bz) {
     __shared__ float4 sx[WPB][2][32];
     __shared__ float4 sp[WPB][2][32];
     const int warp = g_lo + ((blockIdx.x*blockDim.x + threadIdx.x) >> 5);
     if (warp >= ngroups) return;
-    // domain decomposition: phase 1 = interior groups only (all list entries owned by this rank), runs while
-    // the positions of the other ranks are still in flight, and not at all when the lists are about to be
-    // rebuilt; phase 2 = the boundary groups, or every group if the lists have just been rebuilt
-    if (phase == 1) { if (latch[12] || (gflags[warp] & 2)) return; }
-    else if (phase == 2) { if (!latch[12] && !(gflags[warp] & 2)) return; }
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int il = lane >> 2, jj = lane & 3;
     const int i = warp*B2_GROUP + il;
@@ -361,7 +355,7 @@ static double effective_cutoff(const PairForce& pf) {
 
 template <class POT, class POTD>
 static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, POTD potd, float rc2, float4* out,
-                        bool accumulate, int lane, int phase) {
+                        bool accumulate, int lane) {
     const double rcd = effective_cutoff(pf);
     // lane 1 = the side stream, with its own half of the band buffer
     cudaStream_t stream = lane ? ctx->side_stream : ctx->stream;
@@ -378,7 +372,7 @@ static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, POTD potd
     k_pair_force<POT><<<blocks, 32*WPB, 0, stream>>>(ctx->n, ctx->g_lo, ctx->g_hi, ctx->x, ctx->par[pf.set],
                                                           L.entries, L.counts, L.gflags, L.cap, out,
                                                           accumulate ? 1 : 0, pot, rc2, bb, ctx->box[0], ctx->box[1],
-                                                          ctx->box[2], phase, ctx->nl_flags);
+                                                          ctx->box[2]);
     if (ctx->profiling) {
         cudaEventRecord(ev1, stream);
         ctx->prof_events.push_back(ev0); ctx->prof_events.push_back(ev1);
@@ -440,11 +434,11 @@ struct DoubleOf<LJCPot<A, B, C, D, E, float>> { typedef LJCPot<A, B, C, D, E, do
 template <>
 struct DoubleOf<SoftcorePot<float>> { typedef SoftcorePot<double> type; };
 
-int pair_eval_forces(b2_context* ctx, const PairForce& pf, float4* out, bool accumulate, int lane, int phase) {
+int pair_eval_forces(b2_context* ctx, const PairForce& pf, float4* out, bool accumulate, int lane) {
     float rc2, unused;
     PotParams<float> p = make_params<float>(ctx, pf, &rc2);
     PotParams<double> pd = make_params<double>(ctx, pf, &unused);
-#define CALL_FORCE { typename DoubleOf<decltype(pot)>::type potd{pd}; B2_TRY(launch_force(ctx, pf, pot, potd, rc2, out, accumulate, lane, phase)); }
+#define CALL_FORCE { typename DoubleOf<decltype(pot)>::type potd{pd}; B2_TRY(launch_force(ctx, pf, pot, potd, rc2, out, accumulate, lane)); }
     DISPATCH(float, CALL_FORCE, CALL_FORCE);
 #undef CALL_FORCE
     return B2_OK;
