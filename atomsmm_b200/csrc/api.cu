@@ -455,6 +455,25 @@ static uint64_t hilbert_key(const uint32_t cell[3], int bits) {
     return key;
 }
 
+// Pure host helper (no GPU needed): the Hilbert index the engine sorts molecules by, for a point in a
+// periodic box; exported so that the ordering can be tested on the CPU.
+extern "C" int b2_hilbert_index(const double position[3], const double box[3], unsigned long long* out_key) {
+    if (!position || !box || !out_key) return B2_ERR_ARG;
+    const double longest = std::max(box[0], std::max(box[1], box[2]));
+    int bits = 1;
+    while (bits < 20 && longest/(double)(1u << bits) > 0.32) bits++;
+    uint32_t c[3];
+    for (int d = 0; d < 3; d++) {
+        const double L = box[d];
+        if (!(L > 0)) return B2_ERR_ARG;
+        const double w = position[d] - L*floor(position[d]/L);
+        const int k = (int)(w/L*(double)(1u << bits));
+        c[d] = (uint32_t)std::min(std::max(k, 0), (1 << bits) - 1);
+    }
+    *out_key = hilbert_key(c, bits);
+    return B2_OK;
+}
+
 static int compute_order(b2_context* ctx, const std::vector<double>& hx) {
     const int n = ctx->n;
     // molecules in caller order
@@ -467,22 +486,11 @@ static int compute_order(b2_context* ctx, const std::vector<double>& hx) {
     }
     std::vector<std::pair<uint64_t, int>> keys;
     keys.reserve(nmol);
-    // curve resolution: cells of 0.16-0.32 nm along the longest box edge (about one water molecule per
-    // cell: consecutive molecules are then nearest neighbours and 8-atom groups stay ~0.5 nm wide)
-    const double longest = std::max(ctx->box[0], std::max(ctx->box[1], ctx->box[2]));
-    int bits = 1;
-    while (bits < 20 && longest/(double)(1u << bits) > 0.32) bits++;
     for (int m = 0; m < nmol; m++) {
         if (mols[m].empty()) continue;
-        uint32_t c[3];
-        const int a = mols[m][0];
-        for (int d = 0; d < 3; d++) {
-            const double L = ctx->box[d];
-            const double w = hx[3*a+d] - L*floor(hx[3*a+d]/L);
-            const int k = (int)(w/L*(double)(1u << bits));      // the box maps onto the full 2^bits cube
-            c[d] = (uint32_t)std::min(std::max(k, 0), (1 << bits) - 1);
-        }
-        keys.emplace_back(hilbert_key(c, bits), m);
+        unsigned long long key = 0;
+        b2_hilbert_index(&hx[3*(size_t)mols[m][0]], ctx->box, &key);     // by the molecule's first atom
+        keys.emplace_back((uint64_t)key, m);
     }
     std::stable_sort(keys.begin(), keys.end());
     ctx->h_orig.clear();

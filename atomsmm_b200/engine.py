@@ -73,6 +73,7 @@ _SIGNATURES = {
     'b2_comm_unique_id': [ctypes.c_char_p],
     'b2_comm_init': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_char_p],
     'b2_partition_ranges': [ctypes.c_int, c_int_p, ctypes.c_int, c_int_p],
+    'b2_hilbert_index': [c_double_p, c_double_p, ctypes.POINTER(ctypes.c_ulonglong)],
     'b2_comm_info': [c_void, c_int_p, c_int_p, c_int_p, c_int_p, ctypes.POINTER(ctypes.c_longlong)],
 }
 
@@ -117,6 +118,16 @@ def partition_ranges(molecule_sorted, nranks):
     if code != 0:
         raise EngineError('b2_partition_ranges failed (code %d)' % code)
     return out
+
+
+def hilbert_index(position, box):
+    """Index of a point along the Hilbert curve the engine orders molecules by (pure host logic)."""
+    key = ctypes.c_ulonglong()
+    code = library().b2_hilbert_index(_dptr(np.asarray(position, dtype=np.float64)), _dptr(np.asarray(box, dtype=np.float64)),
+                                      ctypes.byref(key))
+    if code != 0:
+        raise EngineError('b2_hilbert_index failed (code %d)' % code)
+    return key.value
 
 
 def broadcast_bytes(payload, src=0, group=None):

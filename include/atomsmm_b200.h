@@ -215,6 +215,10 @@ B2_API int b2_comm_init(b2_context* ctx, int nranks, int rank, const char id128[
  * molecule id of each atom in the engine's spatial order; out_ranges[nranks+1] receives boundaries
  * that fall on molecule boundaries nearest to k*n/nranks. */
 B2_API int b2_partition_ranges(int n, const int* molecule_sorted, int nranks, int* out_ranges);
+/* Pure host helper: index along the Hilbert curve (one-molecule resolution) by which the engine
+ * orders molecules; consecutive indices are face-adjacent cells, so runs of consecutive atoms -- the
+ * 8-atom i-groups, the molecule chunks, the ranks' ownership ranges -- are spatially compact. */
+B2_API int b2_hilbert_index(const double position[3], const double box[3], unsigned long long* out_key);
 /* ownership range [lo, hi) of this rank in the engine's spatial order, and the number of
  * position exchanges performed so far */
 B2_API int b2_comm_info(b2_context* ctx, int* rank, int* nranks, int* lo, int* hi, long long* exchanges);
