@@ -120,3 +120,36 @@ def test_afed_program():
                                   parameters={'lambda_vdw': 0.9995}, derivative_slots=slots, tol=1e-8)
     assert executor.parameters['lambda_vdw'] == pytest.approx(reference.parameters['lambda_vdw'], abs=1e-9)
     assert 0.0 <= executor.parameters['lambda_vdw'] <= 1.0
+
+
+def _nh(dof, nloops=1):
+    return atomsmm.NoseHooverPropagator(300*K, dof, 100*fs, nloops)
+
+
+CASES = {
+    # propagator algebra + thermostats of SURVEY rows a11-a19, each through the whole lowering pipeline
+    'nhc-trotter': lambda dof: atomsmm.TrotterSuzukiPropagator(
+        atomsmm.RespaPropagator([2, 2, 1]), atomsmm.NoseHooverChainPropagator(300*K, dof, 100*fs)).integrator(2*fs),
+    'nh-nloops4-sy7': lambda dof: atomsmm.TrotterSuzukiPropagator(
+        atomsmm.RespaPropagator([2, 1, 1]), atomsmm.SuzukiYoshidaPropagator(_nh(dof, 4), 7)).integrator(2*fs),
+    'nhl-stochastic': lambda dof: atomsmm.TrotterSuzukiPropagator(
+        atomsmm.RespaPropagator([2, 1, 1]),
+        atomsmm.NoseHooverLangevinPropagator(300*K, dof, 100*fs, 10/ps)).integrator(2*fs),
+    'chained-split': lambda dof: atomsmm.ChainedPropagator(
+        [atomsmm.RespaPropagator([2, 1, 1]), atomsmm.SplitPropagator(_nh(dof), 2)]).integrator(2*fs),
+    'mts-xo-respa': lambda dof: atomsmm.MultipleTimeScaleIntegrator(2*fs, [2, 1, 1], bath=_nh(dof), scheme='xo-respa'),
+    'mts-xi-respa': lambda dof: atomsmm.MultipleTimeScaleIntegrator(2*fs, [2, 1, 1], bath=_nh(dof), scheme='xi-respa'),
+    'mts-side-nsy3': lambda dof: atomsmm.MultipleTimeScaleIntegrator(2*fs, [2, 1, 1], bath=_nh(dof), scheme='side',
+                                                                   location=1, nsy=3),
+    'mts-middle-nres2': lambda dof: atomsmm.MultipleTimeScaleIntegrator(2*fs, [2, 1, 1], bath=_nh(dof), nres=2),
+    'respa-memory': lambda dof: atomsmm.RespaPropagator([2, 2, 1], has_memory=True).integrator(2*fs),
+    'nhl-r-massive': lambda dof: atomsmm.NHL_R_Integrator(2*fs, [2, 1, 1], 300*K, 50*fs, 10/ps),
+}
+
+
+@pytest.mark.parametrize('case', sorted(CASES))
+def test_reference_integrators_lower_faithfully(case):
+    system, pos = water_cluster(24)
+    respa = atomsmm.RESPASystem(system, 7*unit.angstroms, 5*unit.angstroms)
+    dof = atomsmm.countDegreesOfFreedom(respa)
+    compare(respa, lambda: CASES[case](dof), pos, velocities(respa, 6), 2, group_mask=0b111 | (1 << 31))
