@@ -36,6 +36,13 @@ def force_record(force):
         rec['n_bonds'] = force.getNumBonds()
     if hasattr(force, 'getNumExceptions'):
         rec['n_exceptions'] = force.getNumExceptions()
+    if hasattr(force, 'getNumInteractionGroups') and force.getNumInteractionGroups():
+        rec['interaction_groups'] = [[sorted(int(i) for i in s1)[:8], len(s1), len(s2)]
+                                     for s1, s2 in (force.getInteractionGroupParameters(k)
+                                                    for k in range(force.getNumInteractionGroups()))]
+    if hasattr(force, 'getNumEnergyParameterDerivatives') and force.getNumEnergyParameterDerivatives():
+        rec['derivatives'] = [force.getEnergyParameterDerivativeName(k)
+                              for k in range(force.getNumEnergyParameterDerivatives())]
     return rec
 
 
@@ -130,6 +137,17 @@ def build_cases(atomsmm, unit, app, loader):
         out['systems']['respa_slowexc_' + case] = [force_record(f) for f in respa_slow.getForces()]
         computing = atomsmm.ComputingSystem(system)
         out['systems']['computing_' + case] = [force_record(f) for f in computing.getForces()]
+    # AlchemicalSystem of the (disabled) AFED test of the reference, tests/test_afed.py:21-35
+    pdb, ff = loader('methane-in-water')
+    system = ff.createSystem(pdb.topology, nonbondedMethod=app.PME, constraints=None, rigidWater=False,
+                             removeCMMotion=False)
+    solute = set(i for i, atom in enumerate(pdb.topology.atoms()) if atom.residue.name == 'C1')
+    alchemical = atomsmm.systems.AlchemicalSystem(system, solute)
+    records = [force_record(f) for f in alchemical.getForces()]
+    nb = alchemical.getForce(atomsmm.findNonbondedForce(alchemical))
+    records.append(dict(solute=sorted(solute), solute_parameters=[
+        [float(getattr(v, 'value_in_md_units', lambda: v)()) for v in nb.getParticleParameters(i)] for i in sorted(solute)]))
+    out['systems']['alchemical_methane'] = records
     return out
 
 
