@@ -755,6 +755,7 @@ static int run_one_step(b2_context* ctx) {
 
 int program_release(b2_context* ctx) {
     if (ctx->graph_exec) {
+        cudaStreamSynchronize(ctx->stream);      // b2_run is asynchronous: the graph may still be in flight
         cudaGraphExecDestroy(ctx->graph_exec);
         ctx->graph_exec = nullptr;
     }
