@@ -139,51 +139,50 @@ def broadcast_bytes(payload, src=0, group=None):
 
 
 def _molecules(system):
-    """Connected components of the bond/constraint graph (Context.getMolecules)."""
+    """Connected components of the bond/constraint graph (Context.getMolecules),
+    numbered by their lowest atom index.  -> (molecule id per atom, list of atom-index arrays)"""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
     n = system.getNumParticles()
-    parent = list(range(n))
-
-    def find(a):
-        while parent[a] != a:
-            parent[a] = parent[parent[a]]
-            a = parent[a]
-        return a
-
-    def union(a, b):
-        ra, rb = find(a), find(b)
-        if ra != rb:
-            parent[max(ra, rb)] = min(ra, rb)
+    edges = []
     for force in system.getForces():
-        if isinstance(force, mm.HarmonicBondForce):
-            for i, j, _, _ in force._bonds:
-                union(i, j)
-        elif isinstance(force, mm.CustomBondForce):
-            for i, j, _ in force._bonds:
-                union(i, j)
-        elif isinstance(force, mm.HarmonicAngleForce):
-            for i, j, k, _, _ in force._angles:
-                union(i, j)
-                union(j, k)
-        elif isinstance(force, mm.CustomAngleForce):
-            for i, j, k, _ in force._angles:
-                union(i, j)
-                union(j, k)
+        if isinstance(force, (mm.HarmonicBondForce, mm.CustomBondForce)):
+            if len(force._bonds):
+                edges.append(mm.index_columns(force._bonds, 2))
+        elif isinstance(force, (mm.HarmonicAngleForce, mm.CustomAngleForce)):
+            if len(force._angles):
+                a = mm.index_columns(force._angles, 3)
+                edges += [a[:, :2], a[:, 1:3]]
         elif isinstance(force, mm.PeriodicTorsionForce):
-            for t in force._torsions:
-                union(t[0], t[1])
-                union(t[1], t[2])
-                union(t[2], t[3])
-    for i, j, _ in system._constraints:
-        union(i, j)
-    roots = {}
-    molecule = np.empty(n, dtype=np.int32)
-    for i in range(n):
-        r = find(i)
-        molecule[i] = roots.setdefault(r, len(roots))
-    groups = [[] for _ in range(len(roots))]
-    for i in range(n):
-        groups[molecule[i]].append(i)
+            if len(force._torsions):
+                t = mm.index_columns(force._torsions, 4)
+                edges += [t[:, :2], t[:, 1:3], t[:, 2:4]]
+    if system._constraints:
+        edges.append(np.array([[c[0], c[1]] for c in system._constraints], dtype=np.int32))
+    if edges:
+        e = np.concatenate(edges, axis=0).astype(np.int64)
+        graph = coo_matrix((np.ones(len(e), dtype=np.int8), (e[:, 0], e[:, 1])), shape=(n, n))
+        _, labels = connected_components(graph, directed=False)
+    else:
+        labels = np.arange(n)
+    # number the components in order of their first atom
+    _, first = np.unique(labels, return_index=True)
+    rank = np.empty(len(first), dtype=np.int64)
+    rank[np.argsort(first, kind='stable')] = np.arange(len(first))
+    molecule = rank[labels].astype(np.int32)
+    order = np.argsort(molecule, kind='stable')
+    counts = np.bincount(molecule, minlength=len(first))
+    groups = np.split(order, np.cumsum(counts)[:-1]) if n else []
     return molecule, groups
+
+
+def _pair_keys(pairs, n):
+    """Sorted unique int64 keys min*n+max of an [m, 2] index array (exclusion sets are compared and
+    merged as arrays: config 5 has 4.2 M exclusions)."""
+    if len(pairs) == 0:
+        return np.zeros(0, dtype=np.int64)
+    p = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+    return np.unique(np.minimum(p[:, 0], p[:, 1])*n + np.maximum(p[:, 0], p[:, 1]))
 
 
 class State(object):
@@ -274,7 +273,7 @@ class Context(object):
                 for k in range(force.getNumGlobalParameters()):
                     self._parameters.setdefault(force.getGlobalParameterName(k), force.getGlobalParameterDefaultValue(k))
         self._molecule, self._molecule_groups = _molecules(system)
-        self._masses = np.array([_md(system.getParticleMass(i)) for i in range(n)], dtype=np.float64)
+        self._masses = np.array(system._masses, dtype=np.float64)
         self._x = torch.zeros((n, 3), dtype=torch.float64, device=self._device)
         self._buffer = torch.zeros((n, 3), dtype=torch.float64, device=self._device)
         self._have_positions = False
@@ -350,7 +349,7 @@ class Context(object):
                 if force.getNumParticles() != n:
                     raise mm.OpenMMException('CustomNonbondedForce must have exactly as many particles as the System')
                 family, cutoff, params, info = lowering.classify_pair_force(force, self._parameters)
-                table = np.array(force._particles, dtype=np.float64).reshape(n, -1)
+                table = mm.value_columns(force._particles, 0).reshape(n, -1)
                 if table.shape[1] == 2:
                     # (sigma, epsilon) only; with an interaction group the charge column carries the
                     # +1/-1 set labels the soft-core kernel uses to keep only unlike pairs
@@ -359,8 +358,7 @@ class Context(object):
                         labels[:] = -1.0
                         labels[info['partition']] = 1.0
                     table = np.concatenate([labels[:, None], table], axis=1)
-                pairs = frozenset((min(i, j), max(i, j)) for i, j in force._exclusions)
-                exclusions = self._merge_exclusions(exclusions, pairs)
+                exclusions = self._merge_exclusions(exclusions, _pair_keys(mm.index_columns(force._exclusions, 2), n))
                 set_id = self._param_set(table[:, 0], table[:, 1], table[:, 2])
                 econst = 0.0
                 if force.getUseLongRangeCorrection():
@@ -378,23 +376,23 @@ class Context(object):
                 exclusions = self._describe_nonbonded(force, exclusions, volume)
             elif isinstance(force, mm.HarmonicBondForce):
                 if force.getNumBonds():
-                    atoms = np.array([[b[0], b[1]] for b in force._bonds], dtype=np.int32)
-                    params = np.array([[b[2], b[3]] for b in force._bonds], dtype=np.float64)
+                    atoms = mm.index_columns(force._bonds, 2)
+                    params = mm.value_columns(force._bonds, 2)
                     self._add_bonded(lowering.BOND_HARMONIC, group, atoms, params, force.usesPeriodicBoundaryConditions())
             elif isinstance(force, mm.HarmonicAngleForce):
                 if force.getNumAngles():
-                    atoms = np.array([a[:3] for a in force._angles], dtype=np.int32)
-                    params = np.array([a[3:5] for a in force._angles], dtype=np.float64)
+                    atoms = mm.index_columns(force._angles, 3)
+                    params = mm.value_columns(force._angles, 3)
                     self._add_bonded(lowering.ANGLE_HARMONIC, group, atoms, params, force.usesPeriodicBoundaryConditions())
             elif isinstance(force, mm.PeriodicTorsionForce):
                 if force.getNumTorsions():
-                    atoms = np.array([t[:4] for t in force._torsions], dtype=np.int32)
-                    params = np.array([[t[4], t[5], t[6]] for t in force._torsions], dtype=np.float64)
+                    atoms = mm.index_columns(force._torsions, 4)
+                    params = mm.value_columns(force._torsions, 4)
                     self._add_bonded(lowering.TORSION_PERIODIC, group, atoms, params, force.usesPeriodicBoundaryConditions())
             elif isinstance(force, mm.CustomBondForce):
                 if force.getNumBonds():
-                    atoms = np.array([[b[0], b[1]] for b in force._bonds], dtype=np.int32)
-                    params = np.array([b[2] for b in force._bonds], dtype=np.float64).reshape(len(atoms), -1)
+                    atoms = mm.index_columns(force._bonds, 2)
+                    params = mm.value_columns(force._bonds, 2).reshape(len(atoms), -1)
                     family, gparams, code = lowering.classify_bond_force(force, self._parameters)
                     periodic = force.usesPeriodicBoundaryConditions()
                     if family == lowering.BOND_LJC:
@@ -409,8 +407,8 @@ class Context(object):
             elif isinstance(force, mm.CustomAngleForce):
                 if force.getNumAngles():
                     from . import expr as X
-                    atoms = np.array([a[:3] for a in force._angles], dtype=np.int32)
-                    params = np.array([a[3] for a in force._angles], dtype=np.float64).reshape(len(atoms), -1)
+                    atoms = mm.index_columns(force._angles, 3)
+                    params = mm.value_columns(force._angles, 3).reshape(len(atoms), -1)
                     names = [force.getPerAngleParameterName(k) for k in range(force.getNumPerAngleParameters())]
                     globals_ = {force.getGlobalParameterName(k): self._parameters[force.getGlobalParameterName(k)]
                                 for k in range(force.getNumGlobalParameters())}
@@ -419,12 +417,12 @@ class Context(object):
             else:
                 raise lowering.UnsupportedDescription('force class %s is not supported' % type(force).__name__)
         if exclusions is not None:
-            pairs = np.array(sorted(exclusions), dtype=np.int32).reshape(-1, 2)
+            pairs = np.stack([exclusions//n, exclusions % n], axis=1).astype(np.int32)
             self._call('b2_set_exclusions', len(pairs), _iptr(pairs))
 
     @staticmethod
     def _merge_exclusions(current, new):
-        if current is not None and current != new:
+        if current is not None and not np.array_equal(current, new):
             raise lowering.UnsupportedDescription('all pair forces of a System must share one exclusion list')
         return new
 
@@ -471,7 +469,7 @@ class Context(object):
         method = force.getNonbondedMethod()
         n = self._n
         group = force.getForceGroup()
-        table = np.array(force._particles, dtype=np.float64).reshape(n, 3)
+        table = mm.value_columns(force._particles, 0).reshape(n, 3)
         kc = 138.935456
         cutoff = force.getCutoffDistance().value_in_md_units()
         use_switch = force.getUseSwitchingFunction()
@@ -498,8 +496,9 @@ class Context(object):
             params = [kc, 3.0, 0.0, 0.0, alpha, float(use_switch), rswitch, cutoff]
             rgroup = force.getReciprocalSpaceForceGroup()
             self._pme_request = (group if rgroup < 0 else rgroup, alpha, grid)
-        pairs = frozenset((min(e[0], e[1]), max(e[0], e[1])) for e in force._exceptions)
-        exclusions = self._merge_exclusions(exclusions, pairs)
+        exc_atoms = mm.index_columns(force._exceptions, 2)
+        exc_values = mm.value_columns(force._exceptions, 2).reshape(len(exc_atoms), 3)
+        exclusions = self._merge_exclusions(exclusions, _pair_keys(exc_atoms, n))
         set_id = self._param_set(table[:, 0], table[:, 1], table[:, 2])
         if alpha > 0:
             rgroup, _, grid = self._pme_request
@@ -519,11 +518,11 @@ class Context(object):
                    ctypes.byref(handle))
         self._pair_handles[id(force)] = (handle.value, dict(name='nonbonded'), force)
         # exceptions: own LJ + bare Coulomb, and under Ewald the erf correction with particle charges
-        exc = [e for e in force._exceptions if alpha > 0 or e[2] != 0.0 or e[4] != 0.0]
-        if exc:
-            atoms = np.array([[e[0], e[1]] for e in exc], dtype=np.int32)
+        live = np.ones(len(exc_atoms), dtype=bool) if alpha > 0 else (exc_values[:, 0] != 0.0) | (exc_values[:, 2] != 0.0)
+        if live.any():
+            atoms = np.ascontiguousarray(exc_atoms[live])
             q = table[:, 0]
-            params = np.array([[e[2], e[3], e[4], q[e[0]]*q[e[1]]] for e in exc], dtype=np.float64)
+            params = np.concatenate([exc_values[live], (q[atoms[:, 0]]*q[atoms[:, 1]])[:, None]], axis=1)
             self._add_bonded(lowering.BOND_LJC, group, atoms, params, True, [kc, alpha])
         return exclusions
 
@@ -635,7 +634,7 @@ class Context(object):
         return mm.Platform('B200')
 
     def getMolecules(self):
-        return [tuple(g) for g in self._molecule_groups]
+        return [tuple(g.tolist()) for g in self._molecule_groups]
 
     def getParameter(self, name):
         if name in getattr(self, '_device_parameters', ()):

@@ -58,6 +58,68 @@ class Vec3(tuple):
         return Vec3(-self[0], -self[1], -self[2])
 
 
+class PackedRows(object):
+    """Columnar, read-mostly storage of per-particle / per-term records: ``indices`` (int32 [n, k],
+    k may be 0) followed by ``values`` (float64 [n, m]).  Behaves like the list of rows the
+    description classes keep (``len``, indexing, iteration, item assignment), so getters work
+    unchanged, while consumers that need whole tables (engine.Context, replication of a box to
+    millions of atoms) take the arrays directly through ``index_columns`` / ``value_columns``.
+    ``nested``: the values of a row form ONE trailing tuple (CustomBondForce / CustomAngleForce rows)."""
+
+    def __init__(self, indices, values, nested=False):
+        n = len(values) if values is not None else len(indices)
+        self.indices = np.ascontiguousarray(indices if indices is not None else np.zeros((n, 0)), dtype=np.int32)
+        self.values = np.ascontiguousarray(values if values is not None else np.zeros((n, 0)), dtype=np.float64)
+        self.indices = self.indices.reshape(n, -1)
+        self.values = self.values.reshape(n, -1)
+        self.nested = bool(nested)
+
+    def __len__(self):
+        return self.values.shape[0]
+
+    def _row(self, k):
+        head = [int(i) for i in self.indices[k]]
+        tail = [float(v) for v in self.values[k]]
+        return head + ([tail] if self.nested else tail)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self._row(j) for j in range(*k.indices(len(self)))]
+        return self._row(k)
+
+    def __setitem__(self, k, row):
+        ni = self.indices.shape[1]
+        self.indices[k] = [int(i) for i in row[:ni]]
+        tail = row[ni] if self.nested else row[ni:]
+        self.values[k] = [float(v) for v in tail]
+
+    def __iter__(self):
+        for k in range(len(self)):
+            yield self._row(k)
+
+    def append(self, row):
+        raise OpenMMException('this force holds a packed (replicated) table: rows cannot be appended')
+
+
+def index_columns(rows, count):
+    """int32 [n, count]: the leading index columns of a list of rows or a PackedRows."""
+    if isinstance(rows, PackedRows):
+        return rows.indices[:, :count]
+    return np.array([r[:count] for r in rows], dtype=np.int32).reshape(len(rows), count)
+
+
+def value_columns(rows, first):
+    """float64 [n, m]: the values after ``first`` index columns (a nested trailing tuple is flattened)."""
+    if isinstance(rows, PackedRows):
+        return rows.values
+    if len(rows) == 0:
+        return np.zeros((0, 0), dtype=np.float64)
+    if len(rows[0]) == first + 1 and isinstance(rows[0][first], (list, tuple)):
+        return np.array([r[first] for r in rows], dtype=np.float64).reshape(len(rows), -1)
+    return np.array([r[first:] for r in rows], dtype=np.float64).reshape(len(rows), -1)
+
+
+
 _nm = unit.nanometer
 _kj = unit.kilojoule_per_mole
 _e = unit.elementary_charge

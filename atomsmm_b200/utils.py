@@ -6,6 +6,8 @@ reference: src/atomsmm/utils.py:16-228).
 from collections import OrderedDict
 from copy import deepcopy
 
+import numpy as np
+
 from . import mm
 from . import unit
 
@@ -20,8 +22,12 @@ class InputError(Exception):
 
 def countDegreesOfFreedom(system):
     """3 x (number of massive particles) - 3 - (number of constraints)  (utils.py:24-40)."""
-    massive = sum(1 for i in range(system.getNumParticles())
-                  if unit.md_value(system.getParticleMass(i)) > 0)
+    masses = getattr(system, '_masses', None)
+    if masses is not None:          # this package's System: one pass over the stored floats
+        massive = int(np.count_nonzero(np.asarray(masses, dtype=float) > 0))
+    else:
+        massive = sum(1 for i in range(system.getNumParticles())
+                      if unit.md_value(system.getParticleMass(i)) > 0)
     return 3*massive - 3 - system.getNumConstraints()
 
 

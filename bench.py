@@ -2,25 +2,29 @@
 """
 Benchmark of the hot path (BASELINE.json metric: atom-steps/s and ns/day; pair-kernel HBM GB/s).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c5|c2|c3|c4] [--replicas]
 
-Workload (config.workload): BASELINE config 2 -- the q-SPC-FW water box replicated 4x4x4
-(98 304 atoms, L = 10 nm, +-0.002 nm jitter, seed 1), RESPASystem (near force-switch 0.7/0.5 nm in
-group 1, full LJ + reaction-field Coulomb rc 1.0 nm in group 2, bonded terms in group 0),
-integrator TrotterSuzuki(Respa([4,2,1]), SuzukiYoshida(NoseHoover(300 K, dof, 100 fs), 3)) at 4 fs.
+Default workload (config.workload) = BASELINE config 5, the configuration the metric's multi-GPU half
+is quoted on and the largest one: the q-SPC-FW water cell replicated 14x14x14 (4 214 784 atoms,
+L = 35 nm, +-0.002 nm jitter, seed 1), RESPASystem (near force-switch 0.7/0.5 nm in group 1, full
+LJ + reaction-field Coulomb rc 1.0 nm in group 2, bonded terms in group 0), integrator
+TrotterSuzuki(Respa([4,2,1]), SuzukiYoshida(NoseHoover(300 K, dof, 100 fs), 3)) at 4 fs.  It fits one
+B200 (N = 1) and is the one configuration that shards: with N > 1 ranks ONE system is integrated by
+all ranks under spatial domain decomposition ("scaling": "strong"; halo positions are pulled over
+NVLink peer memory before every pair-force evaluation, csrc/dist.cu).  `--workload c2` is BASELINE
+config 2 (98 304 atoms, same forces and integrator), c3 the ionic liquid, c4 the AFED replica;
+`--replicas` runs N independent replicas instead of one decomposed system ("scaling": "weak").
 
-A bench "step" is one call integrator.step(MD_STEPS_PER_CALL) (default 100 outer MD steps): one
-pass of the hot path over one batch.  `value` times K such calls with state resident in HBM;
-`e2e` times the same through the public API with HOST buffers: upload of positions+velocities from
-pinned host memory, the MD steps, download of positions+velocities+energies, every step.
+A bench "step" is one call integrator.step(md_steps_per_step) (default 100 outer MD steps; every MD
+step is 8 inner iterations, 3 pair-force evaluations and 2 thermostat chains): one pass of the hot
+path over one batch.  `value` times K such calls with state resident in HBM; `e2e` times the same
+through the public API with HOST buffers: upload of positions+velocities from pinned host memory, the
+MD steps, download of positions+velocities+energies, every step.
 
-N > 1 (default): N independent replicas of the workload, one per GPU, no data-path collective
-("scaling": "weak") -- ensembles are how configs 1-4 shard.
-N > 1 with --dd: ONE system integrated by all ranks with spatial domain decomposition (NCCL position
-exchange before every pair-force evaluation); "scaling": "strong".  `--workload c5` selects BASELINE
-config 5 (the cell replicated 14x14x14 = 4 214 784 atoms, L = 35 nm), the configuration the
-decomposition is meant for:
-    torchrun --nproc-per-node 8 bench.py --gpus 8 --workload c5 --dd --steps 3 --md-steps 20
+Before anything is timed the first frame is checked against the oracle (`parity` in the line): forces
+of every force group within 1e-5 relative RMS, energies within 1e-6 relative, and the interacting
+pair sets of both neighbour lists equal (count and checksum) to those of the float64 C restatement
+(oracle/cport.py).  A failed gate makes the run exit non-zero after printing the line.
 """
 
 import argparse
@@ -55,7 +59,7 @@ def build_workload(reps):
     else:
         big, pos = respa, base_pos
     n = big.getNumParticles()
-    mass = np.array([big.getParticleMass(i).value_in_md_units() for i in range(n)])
+    mass = np.array(big._masses, dtype=np.float64)
     rng = np.random.Generator(np.random.Philox(1234))
     vel = rng.standard_normal((n, 3))*np.sqrt(8.314472471220217e-3*300.0/mass)[:, None]
     vel -= (mass[:, None]*vel).sum(0)/mass.sum()
@@ -86,7 +90,7 @@ def build_c3(reps):
     pos = systems.positions_of(pdb)
     big, pos = systems.replicate(system, pos, box, reps) if reps > 1 else (system, pos)
     n = big.getNumParticles()
-    mass = np.array([big.getParticleMass(i).value_in_md_units() for i in range(n)])
+    mass = np.array(big._masses, dtype=np.float64)
     rng = np.random.Generator(np.random.Philox(1234))
     vel = rng.standard_normal((n, 3))*np.sqrt(8.314472471220217e-3*300.0/mass)[:, None]
     vel -= (mass[:, None]*vel).sum(0)/mass.sum()
@@ -115,7 +119,7 @@ def build_c4():
     variable = atomsmm.ExtendedSystemVariable('lambda_vdw', 1000, 5, 40*fs)
     integrator = atomsmm.AdiabaticDynamicsIntegrator(nvt, 2, [variable])
     n = alchemical.getNumParticles()
-    mass = np.array([alchemical.getParticleMass(i).value_in_md_units() for i in range(n)])
+    mass = np.array(alchemical._masses, dtype=np.float64)
     rng = np.random.Generator(np.random.Philox(1234))
     vel = rng.standard_normal((n, 3))*np.sqrt(8.314472471220217e-3*300.0/mass)[:, None]
     return alchemical, systems.positions_of(pdb), vel, integrator
@@ -200,13 +204,37 @@ def measured_peak():
     return 6650.0, 'fallback'
 
 
+def workload_text(args, n):
+    if args.workload in ('c2', 'c5'):
+        return ('%s: q-SPC-FW water x%d^3, %d atoms, RESPASystem near 0.7/0.5 nm force-switch + LJ/reaction-field '
+                '1.0 nm, RESPA [4,2,1] + NoseHoover SY3, dt 4 fs' % (args.workload, args.reps, n))
+    if args.workload == 'c3':
+        return ('c3: emim/B(CN)4 ionic liquid x%d^3, %d atoms, DampedSmoothedForce + NonbondedExceptionsForce, '
+                'RESPA [4,1] + Bussi, dt 2 fs' % (args.reps, n))
+    return 'c4: AFED, methane in water, %d atoms, soft-core lambda_vdw extended variable, outer step 4 x 1 fs' % n
+
+
+def workload_config(args, n, dt_fs=DT_FS):
+    """Identical for both arms: names the workload, nothing about how it is executed."""
+    return dict(workload=workload_text(args, n), atoms=n, dt_fs=dt_fs,
+                loops=LOOPS if args.workload in ('c2', 'c5') else ([4, 1] if args.workload == 'c3' else None),
+                l2_policy='no flush needed: a bench step is consecutive MD steps of ONE trajectory (positions, lists and '
+                          'forces change every step), and at the default workload the per-step working set (state '
+                          '0.4 GB + neighbour lists ~3 GB) is 25x the 126 MB L2')
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the float64 C/OpenMP restatement of the reference algorithm (oracle/c/oracle.c) on
-    all host cores; each step is a bounded sample (a few outer MD steps) of the same workload."""
+    """CPU arm: the float64 C/OpenMP restatement of the reference algorithm (oracle/c/oracle.c; OpenMM
+    itself is not installable offline) on all host cores.  Each step is a bounded
+    sample of the same workload: `--cpu-md-steps` outer MD steps (default 1)."""
     if rank != 0:
         return
     import numpy as np
     from oracle import cport
+    if args.workload not in ('c2', 'c5'):
+        print(json.dumps(dict(impl='reference', unavailable='the CPU restatement drives RESPA [n0,n1,1] + Nose-Hoover '
+                                                            'only (workloads c2, c5)')))
+        return
     system, pos, vel = build_workload(args.reps)
     n = system.getNumParticles()
     integrator, dof = make_integrator(system)
@@ -224,52 +252,91 @@ def run_reference(args, rank, world):
     elapsed = time.perf_counter() - t0
     value = n*sample*args.steps/elapsed
     line = dict(metric='atom-steps/s', value=value, unit='atom-steps/s', n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1e3*elapsed/args.steps, higher_is_better=True, scaling='weak',
+                warmup=args.warmup, ms_per_step=1e3*elapsed/args.steps, higher_is_better=True,
+                scaling='strong' if (args.gpus > 1 and not args.replicas) else 'weak',
                 vs_baseline=None, dtype='f64', data='synthetic', impl='reference',
-                config=workload_config(args, n, sample),
+                config=workload_config(args, n), md_steps_per_step=sample,
                 ns_per_day=sample*args.steps*DT_FS*1e-6*86400/elapsed,
                 cpu_baseline=dict(value=value, unit='atom-steps/s', cores=cores, kind='port',
-                                  sample='%d outer MD steps per step of the %d-atom workload, C/OpenMP float64 '
-                                         'restatement of the reference algorithm (OpenMM itself is not installable '
-                                         'offline)' % (sample, n)),
+                                  sample='%d outer MD step(s) per step of the %d-atom workload (throughput is per '
+                                         'atom-step, so the sample length does not bias it), C/OpenMP float64 '
+                                         'restatement of the reference algorithm; NOT OpenMM-CPU, which is not '
+                                         'installable offline' % (sample, n)),
                 e2e=dict(value=value, unit='atom-steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
 
-def workload_config(args, n, md_steps, what=None):
-    dd = getattr(args, 'dd', False) and args.gpus > 1
-    text = what % n if what else ('%s: q-SPC-FW water x%d^3, %d atoms, RESPASystem near 0.7/0.5 nm force-switch + '
-                                  'LJ/reaction-field 1.0 nm, RESPA [4,2,1] + NoseHoover SY3, dt 4 fs'
-                                  % (getattr(args, 'workload', 'c2'), args.reps, n))
-    return dict(workload=text,
-                atoms=n, md_steps_per_step=md_steps, dt_fs=DT_FS, loops=LOOPS,
-                replicas=1 if dd else args.gpus,
-                parallelism=('domain decomposition over %d ranks' % args.gpus) if dd else
-                            ('%d independent replicas' % args.gpus),
-                l2_policy='no flush: a bench step is %d CONSECUTIVE MD steps of one trajectory (positions, lists and '
-                          'forces change every step), not a repeated identical input; at 98 304 atoms the working set '
-                          '(state ~10 MB + neighbour lists ~65 MB) is L2-resident exactly as in a production run of this '
-                          'size; the same engine on a working set far beyond L2 (--workload c5, 4.2 M atoms, ~3 GB of '
-                          'lists) runs at a HIGHER per-atom rate (profiles/round1_c5_n1.json), so the number does not '
-                          'come from cache warmth' % md_steps)
+def parity_gate(args, context, system, pos, rank):
+    """First-frame parity against the oracle (SURVEY 8d "parity gates run with every benchmark").  Every
+    rank takes part in the engine calls (collective under domain decomposition); rank 0 runs the oracle."""
+    import numpy as np
+    from atomsmm_b200 import mm
+    groups = sorted(set(f.getForceGroup() for f in system.getForces() if not isinstance(f, mm.CMMotionRemover)))
+    groups = [g for g in groups if g != 31]          # RESPASystem's group 31 is a report-only duplicate
+    engine = {}
+    for g in groups:
+        state = context.getState(getForces=True, getEnergy=True, groups={g})
+        engine[g] = (state._forces, state._potential)
+    pair_forces = [f for f in system.getForces()
+                   if isinstance(f, (mm.CustomNonbondedForce, mm.NonbondedForce)) and f.getForceGroup() != 31
+                   and f.getNumParticles() > 0]
+    sets = {}
+    if context._nranks == 1:
+        for f in pair_forces:
+            sets[f.getForceGroup()] = context.pair_set(f)
+    if rank != 0:
+        return None
+    from oracle import cport
+    t0 = time.perf_counter()
+    port = cport.CPort(system, threads=os.cpu_count(), verify=system.getNumParticles() <= 200000)
+    result = dict(oracle='oracle/cport.py: float64 C/OpenMP restatement, pinned on the reference goldens '
+                         '(tests/test_oracle_c.py, tests/test_oracle_goldens.py)',
+                  atoms=system.getNumParticles(), force_rel_rms={}, energy_rel={}, pair_sets={},
+                  tolerance=dict(force_rel_rms=1e-5, energy_rel=1e-6, pair_sets='equal count and checksum'))
+    ok = True
+    for g in groups:
+        f_ref, e_ref, _ = port.evaluate(pos, groups={g})
+        f, e = engine[g]
+        rms = float(np.sqrt(np.sum((f - f_ref)**2)/max(np.sum(f_ref**2), 1e-300)))
+        rel = abs(e - e_ref)/max(abs(e_ref), 1e-300)
+        result['force_rel_rms'][str(g)] = rms
+        result['energy_rel'][str(g)] = rel
+        ok = ok and rms <= 1e-5 and rel <= 1e-6 and bool(np.isfinite(rms))
+    for f in pair_forces:
+        g = f.getForceGroup()
+        if g in sets:
+            expect = port.pair_set(pos, f)
+            same = tuple(sets[g]) == tuple(expect)
+            result['pair_sets'][str(g)] = dict(pairs=int(expect[0]), equal=bool(same))
+            ok = ok and same
+    if not sets:
+        result['pair_sets'] = 'single-GPU diagnostic (checked at N=1 and in tests/test_gpu_scale.py)'
+    result['ok'] = bool(ok)
+    result['seconds'] = round(time.perf_counter() - t0, 1)
+    return result
 
 
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument('--gpus', type=int, default=1)
-    parser.add_argument('--steps', type=int, default=10)
+    parser.add_argument('--steps', type=int, default=5)
     parser.add_argument('--warmup', type=int, default=3)
     parser.add_argument('--impl', default='b200')
-    parser.add_argument('--reps', type=int, default=4, help='replication of the 1 536-atom cell per axis')
+    parser.add_argument('--reps', type=int, default=None, help='replication of the 1 536-atom cell per axis')
     parser.add_argument('--md-steps', type=int, default=MD_STEPS_PER_CALL)
-    parser.add_argument('--cpu-md-steps', type=int, default=2)
+    parser.add_argument('--cpu-md-steps', type=int, default=1)
     parser.add_argument('--no-cpu-baseline', action='store_true')
-    parser.add_argument('--workload', default='c2', choices=['c2', 'c3', 'c4', 'c5'])
-    parser.add_argument('--dd', action='store_true', help='one system over all ranks (domain decomposition)')
+    parser.add_argument('--no-parity', action='store_true', help='skip the first-frame parity gate (profiling runs)')
+    parser.add_argument('--workload', default='c5', choices=['c2', 'c3', 'c4', 'c5'])
+    parser.add_argument('--replicas', action='store_true', help='N independent replicas instead of one decomposed system')
+    parser.add_argument('--dd', action='store_true', help='(default for N > 1; kept for older command lines)')
     parser.add_argument('--no-e2e', action='store_true', help='skip the host-buffer end-to-end leg')
+    parser.add_argument('--no-profile', action='store_true', help='skip the per-launch pair-kernel timing pass')
     args = parser.parse_args()
-    if args.workload == 'c5':
-        args.reps = 14
+    if args.reps is None:
+        args.reps = {'c5': 14, 'c2': 4, 'c3': 4, 'c4': 1}[args.workload]
+    if args.workload == 'c4':
+        args.replicas = True            # AFED shards as independent replicas (SURVEY 8e)
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else max(args.warmup, 1)
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -288,19 +355,17 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 
-    dt_fs, what = DT_FS, None
+    dt_fs = DT_FS
     if args.workload == 'c3':
         system, pos, vel, integrator = build_c3(args.reps)
-        dt_fs, what = 2.0, ('c3: emim/B(CN)4 ionic liquid x%d^3, %%d atoms, DampedSmoothedForce + NonbondedExceptionsForce, '
-                            'RESPA [4,1] + Bussi, dt 2 fs' % args.reps)
+        dt_fs = 2.0
     elif args.workload == 'c4':
         system, pos, vel, integrator = build_c4()
-        dt_fs, what = 4.0, 'c4: AFED, methane in water, %d atoms, soft-core lambda_vdw extended variable, outer step 4 x 1 fs'
     else:
         system, pos, vel = build_workload(args.reps)
         integrator, dof = make_integrator(system)
     n = system.getNumParticles()
-    dd = args.dd and world > 1
+    dd = world > 1 and not args.replicas
     integrator.setRandomNumberSeed(1 if dd else 1 + rank)
     properties = {'DeviceIndex': local}
     if dd:
@@ -316,6 +381,11 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    parity = None
+    if not args.no_parity and args.workload in ('c2', 'c5'):
+        parity = parity_gate(args, context, system, pos, rank)
+        barrier()
 
     # ---- resident-state timing ---------------------------------------------------------------------
     sampler = ClockSampler(local)
@@ -345,13 +415,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed = float(t.item())
     value = replicas*n*md*args.steps/elapsed
+    comm = context.comm_info()
 
     # ---- end to end through the public API with host buffers --------------------------------------
     host_x = torch.from_numpy(pos.copy()).pin_memory()
     host_v = torch.from_numpy(vel.copy()).pin_memory()
     state = context.getState(getPositions=True, getVelocities=True)
-    host_x.copy_(torch.from_numpy(state.getPositions(asNumpy=True).value_in_unit(unit.nanometer)))
-    host_v.copy_(torch.from_numpy(state.getVelocities(asNumpy=True).value_in_unit(unit.nanometer/unit.picosecond)))
+    host_x.copy_(torch.from_numpy(state._positions))
+    host_v.copy_(torch.from_numpy(state._velocities))
     e2e_steps = max(3, args.steps//2)
 
     def e2e_step():
@@ -381,47 +452,61 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_value = replicas*n*md*e2e_steps/float(t.item())
+        if energy is None or not np.isfinite(energy):
+            raise SystemExit('bench.py: the trajectory produced a non-finite energy')
     state_bytes = 2*n*3*8
 
     # ---- roofline of the dominant kernel: CUDA events around every pair launch, eager pass --------
-    context.set_profiling(True)
-    integrator.step(8)
-    profile = context.pair_profile()
-    context.set_profiling(False)
-    peak, peak_kind = measured_peak()
-    used = [p for p in profile if p['launches'] > 0]
-    dominant = max(used, key=lambda p: p['total_ms'])
-    avg_s = dominant['total_ms']*1e-3/dominant['launches']
-    bytes_per_launch = n*(24 + 16 + 16) + 4*dominant['entries']
-    achieved = bytes_per_launch/avg_s/1e9
-    pair_ms_per_md_step = sum(p['total_ms'] for p in used)/8.0
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as handle:
-            if args.workload == 'c2' and args.reps == 4:
-                traffic = json.load(handle).get(dominant['name'])
-    except (OSError, ValueError):
-        pass
-    roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved/peak, traffic=traffic,
-                    peak_kind=peak_kind, kernel='k_pair_force<%s> group %d' % (dominant['name'], dominant['group']),
-                    avg_launch_us=avg_s*1e6, algorithmic_bytes_per_launch=bytes_per_launch,
-                    list_entries=dominant['entries'],
-                    pair_kernels_share_of_step=pair_ms_per_md_step/(1e3*elapsed/(args.steps*md)),
-                    note='pair tiles are fp32-issue bound, not HBM bound (SURVEY 8d): algorithmic bytes = N*(24 B x + '
-                         '16 B params + 16 B force) + 4 B per neighbour-list entry; timed in a separate eager pass '
-                         'of the same step program with CUDA events on the launch stream')
+    roofline = None
+    if not args.no_profile:
+        context.set_profiling(True)
+        integrator.step(8)
+        profile = context.pair_profile()
+        context.set_profiling(False)
+        peak, peak_kind = measured_peak()
+        used = [p for p in profile if p['launches'] > 0]
+        dominant = max(used, key=lambda p: p['total_ms'])
+        avg_s = dominant['total_ms']*1e-3/dominant['launches']
+        owned = comm['hi'] - comm['lo']
+        bytes_per_launch = owned*(24 + 16 + 16) + 4*dominant['entries']
+        achieved = bytes_per_launch/avg_s/1e9
+        pair_ms_per_md_step = sum(p['total_ms'] for p in used)/8.0
+        traffic, traffic_source = None, None
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as handle:
+                entry = json.load(handle).get('%s/%s' % (args.workload, dominant['name']))
+                if entry and world == 1:
+                    traffic, traffic_source = entry['dram_bytes_per_launch'], entry['source']
+        except (OSError, ValueError, KeyError):
+            pass
+        step_bytes = 1176.0 if args.workload in ('c2', 'c5') else None      # [4,2,1] + SY3-NH
+        roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved/peak, traffic=traffic,
+                        traffic_source=traffic_source, peak_kind=peak_kind,
+                        kernel='k_pair_force<%s> group %d' % (dominant['name'], dominant['group']),
+                        avg_launch_us=avg_s*1e6, algorithmic_bytes_per_launch=bytes_per_launch,
+                        list_entries=dominant['entries'],
+                        pair_kernels_share_of_step=pair_ms_per_md_step/(1e3*elapsed/(args.steps*md)),
+                        whole_step=(dict(bytes_per_atom_step=step_bytes, achieved=step_bytes*value/world/1e9,
+                                         frac=step_bytes*value/world/1e9/peak) if step_bytes else None),
+                        note='pair tiles are fp32-issue bound, not HBM bound (SURVEY 8d): algorithmic bytes = owned atoms*(24 B x '
+                             '+ 16 B params + 16 B force) + 4 B per neighbour-list entry; timed in a separate eager pass '
+                             'of the same step program with CUDA events on the launch stream; whole_step = SURVEY 8d '
+                             'compulsory bytes per atom-step x measured rate, per GPU')
 
     line = dict(metric='atom-steps/s', value=value, unit='atom-steps/s', n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3*elapsed/args.steps, higher_is_better=True,
                 scaling='strong' if dd else 'weak',
                 vs_baseline=None, dtype='f32 pair forces / f64 state', data='synthetic',
-                config=workload_config(args, n, md, what), ns_per_day=md*args.steps*dt_fs*1e-6*86400/elapsed,
-                clocks=clocks, gpu_launches=int(launches),
+                config=workload_config(args, n, dt_fs), md_steps_per_step=md,
+                parallelism=(('domain decomposition over %d ranks (%s)' % (world, comm.get('exchange', 'nccl'))) if dd
+                             else ('%d independent replicas' % world)),
+                ns_per_day=md*args.steps*dt_fs*1e-6*86400/elapsed,
+                clocks=clocks, gpu_launches=int(launches), parity=parity,
                 e2e=(dict(value=e2e_value, unit='atom-steps/s', h2d_bytes_per_step=state_bytes,
                           d2h_bytes_per_step=state_bytes + 16, final_energy=energy) if e2e_value is not None else None),
                 roofline=roofline, engine=dict(kernels_per_md_step=after['kernels_per_step'],
                                                list_rebuilds=after['rebuilds'], list_capacity=after['list_capacity'],
-                                               list_stats=context.list_stats()))
+                                               list_stats=context.list_stats(), comm=comm))
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload in ('c2', 'c5'):
         from oracle import cport
         cores = os.cpu_count()
@@ -429,17 +514,20 @@ def main():
         g = dict(zip([integrator.getGlobalVariableName(k) for k in range(integrator.getNumGlobalVariables())],
                      integrator._global_values))
         x, v, p_eta = port.respa(pos, vel, 1, DT_FS*1e-3, LOOPS[0], LOOPS[1], (1, g['LkT'], g['Q'], 0.0))
-        sample = 4
+        sample = 2 if n > 1000000 else 4
         t0 = time.perf_counter()
         port.respa(x, v, sample, DT_FS*1e-3, LOOPS[0], LOOPS[1], (1, g['LkT'], g['Q'], p_eta))
         cpu_elapsed = time.perf_counter() - t0
         line['cpu_baseline'] = dict(value=n*sample/cpu_elapsed, unit='atom-steps/s', cores=cores, kind='port',
                                     sample='%d outer MD steps of the same %d-atom workload (after 1 warm-up step), '
-                                           'C/OpenMP float64 restatement of the reference algorithm' % (sample, n))
+                                           'C/OpenMP float64 restatement of the reference algorithm (not OpenMM-CPU)'
+                                           % (sample, n))
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity['ok']:
+        raise SystemExit('bench.py: first-frame parity gate FAILED: %s' % json.dumps(parity))
 
 
 if __name__ == '__main__':

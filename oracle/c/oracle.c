@@ -413,6 +413,36 @@ int orc_eval(orc_sys* s, const double* x, unsigned mask, double* f, double* ener
     return 0;
 }
 
+/* Exact interacting pair set of pair force `which`: i < j, r^2 < rc^2 (float64, sum order x,y,z), not
+ * excluded -> number of pairs and an order-independent checksum (sum of a 64-bit mix of (i<<32|j)), the same
+ * definition as the engine's k_pair_set: "neighbour lists bit-exact" is checked as equality of both. */
+static unsigned long long mix64(unsigned long long z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30))*0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27))*0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+int orc_pair_set(orc_sys* s, const double* x, int which, long long* count, unsigned long long* checksum) {
+    if (which < 0 || which >= s->npair) return -1;
+    ensure_list(s, x);
+    const double rc = pair_range(&s->pair[which]), rc2 = rc*rc;
+    long long c = 0;
+    unsigned long long h = 0;
+#pragma omp parallel for schedule(dynamic, 128) num_threads(s->threads) reduction(+:c, h)
+    for (int i = 0; i < s->n; i++) {
+        for (int m = s->nl_ptr[i]; m < s->nl_ptr[i+1]; m++) {
+            int j = s->nl_idx[m];
+            double r2 = 0;
+            for (int k = 0; k < 3; k++) { double d = x[3*j+k] - x[3*i+k]; d -= s->box[k]*rint(d/s->box[k]); r2 += d*d; }
+            if (r2 < rc2) { c++; h += mix64(((unsigned long long)i << 32) | (unsigned)j); }
+        }
+    }
+    *count = c;
+    *checksum = h;
+    return 0;
+}
+
 static void kick(int n, double* v, const double* f, const double* g, const double* mass, double c) {
     for (int i = 0; i < n; i++) if (mass[i] > 0) for (int k = 0; k < 3; k++) v[3*i+k] += c*(f[3*i+k] - (g ? g[3*i+k] : 0.0))/mass[i];
 }

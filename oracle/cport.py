@@ -28,8 +28,8 @@ c_int_p = ctypes.POINTER(ctypes.c_int)
 def library():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            subprocess.run(['make', '-s', '-C', os.path.join(HERE, 'c')], check=True)
+        # make decides whether the library is stale (a no-op when it is up to date)
+        subprocess.run(['make', '-s', '-C', os.path.join(HERE, 'c')], check=True)
         lib = ctypes.CDLL(LIB_PATH)
         lib.orc_create.argtypes = [ctypes.c_int, c_double_p, c_double_p, ctypes.POINTER(ctypes.c_void_p)]
         lib.orc_destroy.argtypes = [ctypes.c_void_p]
@@ -42,6 +42,8 @@ def library():
         lib.orc_eval.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_uint, c_double_p, c_double_p, c_double_p]
         lib.orc_respa.argtypes = [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_int, ctypes.c_double, ctypes.c_int,
                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, c_double_p]
+        lib.orc_pair_set.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong),
+                                     ctypes.POINTER(ctypes.c_ulonglong)]
         lib.orc_counter.argtypes = [ctypes.c_void_p, ctypes.c_int]
         lib.orc_counter.restype = ctypes.c_long
         _lib = lib
@@ -54,6 +56,14 @@ def _dp(a):
 
 def _ip(a):
     return a.ctypes.data_as(c_int_p)
+
+
+def _columns(force, attribute, nindex):
+    """(int32 index columns, float64 value columns) of a description table, read in bulk (the
+    description classes keep them as lists of rows or as columnar mm.PackedRows; values are in MD units)."""
+    from atomsmm_b200 import mm
+    rows = getattr(force, attribute)
+    return mm.index_columns(rows, nindex), mm.value_columns(rows, nindex)
 
 
 F_NEAR, F_DAMPED, F_LJC, F_LJ_VIRIAL = 1, 2, 3, 4
@@ -93,36 +103,39 @@ class CPort(object):
         self.system = system
         n = self.n = system.getNumParticles()
         self.box = refmath.system_box(system)
-        self.mass = np.array([system.getParticleMass(i).value_in_md_units() for i in range(n)], dtype=np.float64)
+        self.mass = np.array(system._masses, dtype=np.float64)
         self.handle = ctypes.c_void_p()
         lib.orc_create(n, _dp(self.mass), _dp(self.box), ctypes.byref(self.handle))
         if threads:
             lib.orc_set_threads(self.handle, threads)
         self.threads = threads or os.cpu_count()
         params_set = False
+        self._pair_index = {}      # id(force) -> index among the pair forces of the C system
         self.econst = {}      # position-independent energies (long-range corrections) per group
         for force in system.getForces():
             kind = refmath._kind(force)
             group = force.getForceGroup()
             if kind == 'CustomNonbondedForce':
-                table = np.array([force.getParticleParameters(k) for k in range(n)], dtype=np.float64)
+                table = _columns(force, '_particles', 0)[1].reshape(n, -1)
                 self._set_params(table[:, 0], table[:, 1], table[:, 2], params_set)
                 params_set = True
-                excl = np.array([force.getExclusionParticles(k) for k in range(force.getNumExclusions())], dtype=np.int32)
+                excl = np.ascontiguousarray(_columns(force, '_exclusions', 2)[0])
                 lib.orc_set_exclusions(self.handle, len(excl), _ip(np.ascontiguousarray(excl.reshape(-1))))
                 family, cutoff, p = _custom_pair_params(force)
                 p = np.array(p, dtype=np.float64)
                 if verify:
                     self._verify(force, family, cutoff, p)
+                self._pair_index[id(force)] = len(self._pair_index)
                 lib.orc_add_pair(self.handle, family, group, cutoff, _dp(p), len(p))
             elif kind == 'NonbondedForce':
                 if force.getNumParticles() == 0:
                     continue
-                table = np.array([[v.value_in_md_units() for v in force.getParticleParameters(k)] for k in range(n)])
+                table = _columns(force, '_particles', 0)[1].reshape(n, 3)
                 self._set_params(table[:, 0], table[:, 1], table[:, 2], params_set)
                 params_set = True
-                exc = [force.getExceptionParameters(k) for k in range(force.getNumExceptions())]
-                excl = np.array([[e[0], e[1]] for e in exc], dtype=np.int32)
+                excl, exc_values = _columns(force, '_exceptions', 2)
+                excl = np.ascontiguousarray(excl)
+                exc_values = exc_values.reshape(len(excl), 3)
                 lib.orc_set_exclusions(self.handle, len(excl), _ip(np.ascontiguousarray(excl.reshape(-1))))
                 method = force.getNonbondedMethod()
                 cutoff = force.getCutoffDistance().value_in_md_units()
@@ -138,31 +151,25 @@ class CPort(object):
                 else:
                     raise ValueError('C port needs a periodic cutoff method')
                 p = np.array(p, dtype=np.float64)
+                self._pair_index[id(force)] = len(self._pair_index)
                 lib.orc_add_pair(self.handle, F_LJC, group, cutoff, _dp(p), len(p))
                 if force.getUseDispersionCorrection():
                     self.econst[group] = self.econst.get(group, 0.0) + refmath.nonbonded_lrc(force, self.box)
-                keep = [e for e in exc if alpha > 0 or e[2].value_in_md_units() != 0 or e[4].value_in_md_units() != 0]
-                if keep:
-                    atoms = np.array([[e[0], e[1]] for e in keep], dtype=np.int32)
+                keep = np.ones(len(excl), dtype=bool) if alpha > 0 else (exc_values[:, 0] != 0) | (exc_values[:, 2] != 0)
+                if keep.any():
+                    atoms = np.ascontiguousarray(excl[keep])
                     q = table[:, 0]
-                    prm = np.array([[e[2].value_in_md_units(), e[3].value_in_md_units(), e[4].value_in_md_units(),
-                                     q[e[0]]*q[e[1]]] for e in keep], dtype=np.float64)
+                    prm = np.concatenate([exc_values[keep], (q[atoms[:, 0]]*q[atoms[:, 1]])[:, None]], axis=1)
                     self._add_bonded(B_LJC, group, atoms, prm, [refmath.ONE_4PI_EPS0, alpha])
             elif kind == 'HarmonicBondForce':
-                b = [force.getBondParameters(k) for k in range(force.getNumBonds())]
-                if b:
-                    self._add_bonded(B_BOND, group, np.array([[x[0], x[1]] for x in b], dtype=np.int32),
-                                     np.array([[x[2].value_in_md_units(), x[3].value_in_md_units()] for x in b]))
+                if force.getNumBonds():
+                    self._add_bonded(B_BOND, group, *_columns(force, '_bonds', 2))
             elif kind == 'HarmonicAngleForce':
-                a = [force.getAngleParameters(k) for k in range(force.getNumAngles())]
-                if a:
-                    self._add_bonded(B_ANGLE, group, np.array([x[:3] for x in a], dtype=np.int32),
-                                     np.array([[x[3].value_in_md_units(), x[4].value_in_md_units()] for x in a]))
+                if force.getNumAngles():
+                    self._add_bonded(B_ANGLE, group, *_columns(force, '_angles', 3))
             elif kind == 'PeriodicTorsionForce':
-                t = [force.getTorsionParameters(k) for k in range(force.getNumTorsions())]
-                if t:
-                    self._add_bonded(B_TORSION, group, np.array([x[:4] for x in t], dtype=np.int32),
-                                     np.array([[float(x[4]), x[5].value_in_md_units(), x[6].value_in_md_units()] for x in t]))
+                if force.getNumTorsions():
+                    self._add_bonded(B_TORSION, group, *_columns(force, '_torsions', 4))
             elif kind == 'CustomBondForce':
                 text = force.getEnergyFunction().replace(' ', '')
                 names = [force.getPerBondParameterName(k) for k in range(force.getNumPerBondParameters())]
@@ -171,9 +178,8 @@ class CPort(object):
                 import re
                 m = re.search(r'Kc=([0-9.]+)', text)
                 kc = float(m.group(1)) if m else force.getGlobalParameterDefaultValue(0)
-                b = [force.getBondParameters(k) for k in range(force.getNumBonds())]
-                atoms = np.array([[x[0], x[1]] for x in b], dtype=np.int32)
-                prm = np.array([list(x[2]) + [0.0] for x in b], dtype=np.float64)
+                atoms, prm = _columns(force, '_bonds', 2)
+                prm = np.concatenate([prm.reshape(len(atoms), 3), np.zeros((len(atoms), 1))], axis=1)
                 self._add_bonded(B_LJC, group, atoms, prm, [kc, 0.0])
             elif kind == 'CMMotionRemover':
                 continue
@@ -189,7 +195,8 @@ class CPort(object):
     def _set_params(self, q, sigma, eps, already):
         q, sigma, eps = (np.ascontiguousarray(a, dtype=np.float64) for a in (q, sigma, eps))
         if already:
-            assert np.array_equal(q, self._q) and np.array_equal(sigma, self._sigma) and np.array_equal(eps, self._eps)
+            # one parameter table for all pair forces; tables imported through unit conversions may differ in the last bit
+            assert all(np.allclose(a, b, rtol=1e-14, atol=0) for a, b in ((q, self._q), (sigma, self._sigma), (eps, self._eps)))
             return
         self._q, self._sigma, self._eps = q, sigma, eps
         self.lib.orc_set_params(self.handle, _dp(q), _dp(sigma), _dp(eps))
@@ -247,6 +254,16 @@ class CPort(object):
         self.lib.orc_eval(self.handle, _dp(x), self._mask(groups), _dp(f), ctypes.byref(energy), ctypes.byref(virial))
         constant = sum(v for g, v in self.econst.items() if groups is None or g in groups)
         return f, energy.value + constant, virial.value
+
+    def pair_set(self, positions, force):
+        """(count, checksum) of the exact interacting pair set of a pair force of the system: i < j,
+        r^2 < rc^2 in float64, not excluded (the definition of the engine's Context.pair_set)."""
+        which = self._pair_index[id(force)]
+        x = np.ascontiguousarray(positions, dtype=np.float64)
+        count, checksum = ctypes.c_longlong(), ctypes.c_ulonglong()
+        code = self.lib.orc_pair_set(self.handle, _dp(x), which, ctypes.byref(count), ctypes.byref(checksum))
+        assert code == 0
+        return count.value, checksum.value
 
     def respa(self, positions, velocities, nsteps, dt, n0, n1, nose_hoover=None):
         """Advance (copies of) x, v by nsteps of RespaPropagator([n0, n1, 1]); nose_hoover =

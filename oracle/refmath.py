@@ -490,7 +490,13 @@ def pme_reciprocal(pos, q, box, alpha, grid, order=5, kc=ONE_4PI_EPS0):
 
 def nonbonded_lrc(force, box):
     n = force.getNumParticles()
-    table = np.array([[p.value_in_md_units() for p in force.getParticleParameters(k)[1:]] for k in range(n)])
+    rows = getattr(force, '_particles', None)
+    if rows is not None and n > 100000:
+        # this repository's description classes keep MD-unit floats: read the table in bulk
+        from atomsmm_b200 import mm
+        table = mm.value_columns(rows, 0).reshape(n, 3)[:, 1:]
+    else:
+        table = np.array([[p.value_in_md_units() for p in force.getParticleParameters(k)[1:]] for k in range(n)])
     classes, counts = np.unique(table, axis=0, return_counts=True)
     rc = float(force.getCutoffDistance().value_in_md_units())
     use_switch = force.getUseSwitchingFunction()

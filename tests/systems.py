@@ -57,36 +57,56 @@ def respa_water(method=app.CutoffPeriodic, rcut_in=7*A, rswitch_in=5*A, **kwargs
 
 def replicate(system, positions, box, reps, jitter=0.002, seed=1):
     """Tile a periodic system reps^3 times (BASELINE configs 2, 3, 5): new System with the same
-    forces on shifted copies, every atom displaced by uniform(-jitter, jitter) nm."""
+    forces on shifted copies, every atom displaced by uniform(-jitter, jitter) nm.  Tables are tiled
+    with numpy and kept columnar (mm.PackedRows): config 5 has 4.2 M atoms."""
     import copy
     n = system.getNumParticles()
     copies = reps**3
     big = mm.System()
-    for _ in range(copies):
-        for i in range(n):
-            big.addParticle(system.getParticleMass(i))
+    big._masses = np.tile(np.asarray(system._masses, dtype=np.float64), copies).tolist()
     b = np.asarray(box, dtype=float)
     big.setDefaultPeriodicBoxVectors(mm.Vec3(b[0]*reps, 0, 0), mm.Vec3(0, b[1]*reps, 0), mm.Vec3(0, 0, b[2]*reps))
-    shifts = [(ix, iy, iz) for ix in range(reps) for iy in range(reps) for iz in range(reps)]
-    pos = np.concatenate([positions + np.array(s)*b for s in shifts], axis=0)
+    shifts = np.array([(ix, iy, iz) for ix in range(reps) for iy in range(reps) for iz in range(reps)], dtype=float)
+    pos = (np.asarray(positions)[None, :, :] + (shifts*b)[:, None, :]).reshape(-1, 3)
     rng = np.random.default_rng(seed)
     pos = pos + rng.uniform(-jitter, jitter, size=pos.shape)
+    offsets = (np.arange(copies, dtype=np.int64)*n)[:, None, None]
+
+    def tile(rows, nindex, nested=False):
+        if len(rows) == 0:
+            return []
+        idx = mm.index_columns(rows, nindex).astype(np.int64)
+        val = mm.value_columns(rows, nindex)
+        idx = (idx[None, :, :] + offsets).reshape(-1, nindex) if nindex else None
+        return mm.PackedRows(idx, np.tile(val, (copies, 1)), nested=nested)
+
     for force in system.getForces():
-        new = copy.deepcopy(force)
+        tables = {}
         if isinstance(force, mm.NonbondedForce):
-            new._particles = [list(p) for _ in range(copies) for p in force._particles]
-            new._exceptions = [[e[0] + c*n, e[1] + c*n] + list(e[2:]) for c in range(copies) for e in force._exceptions]
-            new._exception_index = {(min(e[0], e[1]), max(e[0], e[1])): k for k, e in enumerate(new._exceptions)}
+            tables = dict(_particles=(0, False), _exceptions=(2, False))
         elif isinstance(force, mm.CustomNonbondedForce):
-            new._particles = [list(p) for _ in range(copies) for p in force._particles]
-            new._exclusions = [(i + c*n, j + c*n) for c in range(copies) for i, j in force._exclusions]
-        elif isinstance(force, (mm.HarmonicBondForce, mm.CustomBondForce)):
-            new._bonds = [[bd[0] + c*n, bd[1] + c*n] + list(bd[2:]) for c in range(copies) for bd in force._bonds]
-        elif isinstance(force, (mm.HarmonicAngleForce, mm.CustomAngleForce)):
-            new._angles = [[a[0] + c*n, a[1] + c*n, a[2] + c*n] + list(a[3:]) for c in range(copies) for a in force._angles]
+            tables = dict(_particles=(0, False), _exclusions=(2, False))
+        elif isinstance(force, mm.HarmonicBondForce):
+            tables = dict(_bonds=(2, False))
+        elif isinstance(force, mm.CustomBondForce):
+            tables = dict(_bonds=(2, True))
+        elif isinstance(force, mm.HarmonicAngleForce):
+            tables = dict(_angles=(3, False))
+        elif isinstance(force, mm.CustomAngleForce):
+            tables = dict(_angles=(3, True))
         elif isinstance(force, mm.PeriodicTorsionForce):
-            new._torsions = [[t[0] + c*n, t[1] + c*n, t[2] + c*n, t[3] + c*n] + list(t[4:]) for c in range(copies)
-                             for t in force._torsions]
+            tables = dict(_torsions=(4, False))
+        saved = {name: force.__dict__[name] for name in tables}
+        for name in tables:
+            force.__dict__[name] = []          # do not deep-copy what is about to be replaced
+        try:
+            new = copy.deepcopy(force)
+        finally:
+            force.__dict__.update(saved)
+        for name, (nindex, nested) in tables.items():
+            new.__dict__[name] = tile(saved[name], nindex, nested)
+        if isinstance(force, mm.NonbondedForce):
+            new._exception_index = {}
         big.addForce(new)
     return big, pos
 

@@ -13,7 +13,7 @@ def run(extra_env=None):
     env = dict(os.environ)
     env.update(extra_env or {})
     return subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
-                           '--warmup', '1', '--cpu-md-steps', '1'], capture_output=True, text=True, env=env,
+                           '--warmup', '1', '--cpu-md-steps', '1', '--workload', 'c2'], capture_output=True, text=True, env=env,
                           timeout=600)
 
 
