@@ -113,8 +113,8 @@ extern "C" int b2_create(int device, b2_context** out) {
         cudaMalloc(&ctx->sum_partial, sizeof(double)*1024) != cudaSuccess ||
         cudaMalloc(&ctx->ticket, sizeof(unsigned)*4) != cudaSuccess ||
         cudaMalloc(&ctx->nl_flags, sizeof(int)*16) != cudaSuccess ||
-        cudaMalloc(&ctx->band_pairs, sizeof(int)*4*ctx->band_capacity) != cudaSuccess ||
-        cudaMalloc(&ctx->band_count, sizeof(unsigned)*2) != cudaSuccess) {
+        cudaMalloc(&ctx->band_count, sizeof(unsigned)*2) != cudaSuccess ||
+        cudaMalloc(&ctx->band_ticket, sizeof(unsigned)*2) != cudaSuccess) {
         delete ctx;
         return b2_fail(nullptr, B2_ERR_CUDA, "device allocation failed");
     }
@@ -123,6 +123,7 @@ extern "C" int b2_create(int device, b2_context** out) {
     cudaMemset(ctx->ticket, 0, sizeof(unsigned)*4);
     cudaMemset(ctx->nl_flags, 0, sizeof(int)*16);
     cudaMemset(ctx->band_count, 0, sizeof(unsigned)*2);
+    cudaMemset(ctx->band_ticket, 0, sizeof(unsigned)*2);
     ctx->sum_partial_size = 1024;
     *out = ctx;
     return B2_OK;
@@ -150,6 +151,7 @@ extern "C" int b2_destroy(b2_context* ctx) {
     cudaFree(ctx->nl_flags); cudaFree(ctx->d_energy); cudaFree(ctx->code); cudaFree(ctx->consts);
     cudaFree(ctx->globals); cudaFree(ctx->sum_partial); cudaFree(ctx->rng_state);
     cudaFree(ctx->band_pairs); cudaFree(ctx->band_count); cudaFree(ctx->ticket);
+    cudaFree(ctx->band_slot); cudaFree(ctx->band_acc); cudaFree(ctx->band_ticket);
     cudaFree(ctx->chunk_start); cudaFree(ctx->chunk_term_ptr); cudaFree(ctx->chunk_terms);
     for (double* p : ctx->carry_tmp) cudaFree(p);
     cudaFree(ctx->order_tmp);
@@ -175,6 +177,13 @@ extern "C" int b2_set_stream(b2_context* ctx, void* cuda_stream) {
 extern "C" int b2_synchronize(b2_context* ctx) {
     if (!ctx) return B2_ERR_ARG;
     B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->dd_state) {
+        unsigned long long state[4];
+        B2_CUDA(cudaMemcpy(state, ctx->dd_state, sizeof(state), cudaMemcpyDeviceToHost));
+        if (state[2])
+            return b2_fail(ctx, B2_ERR_STATE, "domain decomposition: a peer did not answer within the time-out "
+                           "(exchange %llu); results since then are invalid", state[0]);
+    }
     if (ctx->nl_flags) {
         int flags[11];
         B2_CUDA(cudaMemcpy(flags, ctx->nl_flags, sizeof(flags), cudaMemcpyDeviceToHost));
@@ -230,6 +239,15 @@ extern "C" int b2_set_particles(b2_context* ctx, int n, const double* mass, cons
     B2_CUDA(cudaMalloc(&ctx->exmask, sizeof(unsigned long long)*n));
     B2_CUDA(cudaMemsetAsync(ctx->v, 0, sizeof(double)*3*n, ctx->stream));
     B2_CUDA(cudaMemsetAsync(ctx->exmask, 0, sizeof(unsigned long long)*n, ctx->stream));
+    // cutoff-band buffers, per lane: a pair falls into the fp32 rounding band of the cutoff with probability
+    // ~1e-5, i.e. ~2e-3 band pairs per atom at liquid densities; sized 16x above that
+    if (ctx->band_capacity < (unsigned)(n/32)) ctx->band_capacity = (unsigned)(n/32);
+    if (getenv("B2_BAND_CAPACITY")) ctx->band_capacity = (unsigned)std::max(1, atoi(getenv("B2_BAND_CAPACITY")));
+    B2_CUDA(cudaMalloc(&ctx->band_pairs, sizeof(int)*4*(size_t)ctx->band_capacity));
+    B2_CUDA(cudaMalloc(&ctx->band_acc, sizeof(long long)*6*(size_t)ctx->band_capacity));
+    B2_CUDA(cudaMalloc(&ctx->band_slot, sizeof(int)*2*(size_t)n));
+    B2_CUDA(cudaMemsetAsync(ctx->band_acc, 0, sizeof(long long)*6*(size_t)ctx->band_capacity, ctx->stream));
+    B2_CUDA(cudaMemsetAsync(ctx->band_slot, 0xff, sizeof(int)*2*(size_t)n, ctx->stream));
     return B2_OK;
 }
 
@@ -278,6 +296,8 @@ extern "C" int b2_set_exclusions(b2_context* ctx, int npairs, const int* pairs) 
     return B2_OK;
 }
 
+static int upload_param_set(b2_context* ctx, int k);
+
 static int find_list(b2_context* ctx, double cutoff) {
     for (int k = 0; k < ctx->nlists; k++)
         if (fabs(ctx->lists[k].cutoff - cutoff) < 1e-12) return k;
@@ -320,6 +340,42 @@ extern "C" int b2_update_pair_force(b2_context* ctx, int handle, const double* p
     if (nparams != pf.nparams) return b2_fail(ctx, B2_ERR_ARG, "parameter count mismatch");
     for (int k = 0; k < nparams; k++) pf.params[k] = params[k];
     pf.econst = energy_constant;
+    for (int g = 0; g < B2_FSLOTS; g++) ctx->fvalid[g] = -1;
+    ctx->deriv_version = -1;
+    program_release(ctx);
+    return B2_OK;
+}
+
+// Replaces the per-particle parameters of ONE pair force (updateParametersInContext after
+// setParticleParameters; reference: utils.py reset_coulomb_scaling_factor-style rescaling).  A
+// parameter set shared with other pair forces is split first, so that they keep their values.
+extern "C" int b2_update_pair_particles(b2_context* ctx, int handle, const double* charge, const double* sigma,
+                                        const double* epsilon) {
+    if (!ctx || handle < 0 || handle >= (int)ctx->pair_forces.size()) return b2_fail(ctx, B2_ERR_ARG, "bad pair force handle");
+    if (!charge || !sigma || !epsilon) return b2_fail(ctx, B2_ERR_ARG, "null parameter table");
+    PairForce& pf = ctx->pair_forces[handle];
+    const int n = ctx->n;
+    std::vector<double> s(3*(size_t)n);
+    for (int i = 0; i < n; i++) { s[3*i] = charge[i]; s[3*i+1] = sigma[i]; s[3*i+2] = epsilon[i]; }
+    if (ctx->h_sets[pf.set] == s) return B2_OK;
+    bool shared = false;
+    for (size_t k = 0; k < ctx->pair_forces.size(); k++)
+        if ((int)k != handle && ctx->pair_forces[k].set == pf.set) shared = true;
+    for (const PmeForce& pm : ctx->pme_forces)
+        if (pm.set == pf.set) shared = true;
+    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    int target = pf.set;
+    if (shared) {
+        if ((int)ctx->h_sets.size() >= B2_MAX_SETS) return b2_fail(ctx, B2_ERR_UNSUPPORTED, "too many parameter sets");
+        target = (int)ctx->h_sets.size();
+        ctx->h_sets.push_back(s);
+        B2_CUDA(cudaMalloc(&ctx->par[target], sizeof(float4)*n));
+        B2_CUDA(cudaMalloc(&ctx->pard[target], sizeof(double)*3*n));
+        pf.set = target;
+    } else {
+        ctx->h_sets[target] = s;
+    }
+    if (ctx->have_order) B2_TRY(upload_param_set(ctx, target));
     for (int g = 0; g < B2_FSLOTS; g++) ctx->fvalid[g] = -1;
     ctx->deriv_version = -1;
     program_release(ctx);
@@ -408,6 +464,7 @@ extern "C" int b2_add_pme(b2_context* ctx, int group, int param_set, double alph
     if (nx < PME_MIN_GRID || ny < PME_MIN_GRID || nz < PME_MIN_GRID || !(alpha > 0))
         return b2_fail(ctx, B2_ERR_ARG, "bad PME parameters");
     if (!ctx->periodic) return b2_fail(ctx, B2_ERR_UNSUPPORTED, "PME needs a periodic box");
+    if (ctx->nranks > 1) return b2_fail(ctx, B2_ERR_UNSUPPORTED, "PME is not available with domain decomposition yet");
     PmeForce pf;
     pf.group = group; pf.set = param_set; pf.alpha = alpha; pf.kc = kc; pf.eself = self_energy;
     pf.K[0] = nx; pf.K[1] = ny; pf.K[2] = nz;
@@ -500,6 +557,21 @@ static int compute_order(b2_context* ctx, const std::vector<double>& hx) {
     return B2_OK;
 }
 
+// parameter set k in the engine's order: fp32 {q, sigma/2, sqrt(eps)} for the force tiles, fp64 {q, sigma, eps}
+static int upload_param_set(b2_context* ctx, int k) {
+    const int n = ctx->n;
+    std::vector<float4> p(n);
+    std::vector<double> pd(3*(size_t)n);
+    for (int s = 0; s < n; s++) {
+        const double* src = &ctx->h_sets[k][3*(size_t)ctx->h_orig[s]];
+        p[s] = make_float4((float)src[0], (float)(0.5*src[1]), (float)sqrt(src[2]), 0.f);
+        pd[3*s] = src[0]; pd[3*s+1] = src[1]; pd[3*s+2] = src[2];
+    }
+    B2_CUDA(cudaMemcpy(ctx->par[k], p.data(), sizeof(float4)*n, cudaMemcpyHostToDevice));
+    B2_CUDA(cudaMemcpy(ctx->pard[k], pd.data(), sizeof(double)*3*n, cudaMemcpyHostToDevice));
+    return B2_OK;
+}
+
 static int upload_static(b2_context* ctx) {
     const int n = ctx->n;
     std::vector<int> inv(n);
@@ -515,17 +587,7 @@ static int upload_static(b2_context* ctx) {
     }
     B2_CUDA(cudaMemcpy(ctx->massd, md.data(), sizeof(double)*n, cudaMemcpyHostToDevice));
     B2_CUDA(cudaMemcpy(ctx->invm, im.data(), sizeof(float)*n, cudaMemcpyHostToDevice));
-    for (size_t k = 0; k < ctx->h_sets.size(); k++) {
-        std::vector<float4> p(n);
-        std::vector<double> pd(3*(size_t)n);
-        for (int s = 0; s < n; s++) {
-            const double* src = &ctx->h_sets[k][3*(size_t)ctx->h_orig[s]];
-            p[s] = make_float4((float)src[0], (float)(0.5*src[1]), (float)sqrt(src[2]), 0.f);
-            pd[3*s] = src[0]; pd[3*s+1] = src[1]; pd[3*s+2] = src[2];
-        }
-        B2_CUDA(cudaMemcpy(ctx->par[k], p.data(), sizeof(float4)*n, cudaMemcpyHostToDevice));
-        B2_CUDA(cudaMemcpy(ctx->pard[k], pd.data(), sizeof(double)*3*n, cudaMemcpyHostToDevice));
-    }
+    for (size_t k = 0; k < ctx->h_sets.size(); k++) B2_TRY(upload_param_set(ctx, (int)k));
     std::vector<unsigned long long> mask(n, 0ull);   // indexed by caller index first
     ctx->excl_span = 0;
     for (size_t k = 0; k + 1 < ctx->h_excl.size(); k += 2) {
@@ -544,6 +606,7 @@ static int upload_static(b2_context* ctx) {
 extern "C" int b2_set_positions(b2_context* ctx, const double* x_dev) {
     if (!ctx || ctx->n == 0 || !x_dev) return b2_fail(ctx, B2_ERR_STATE, "set particles first");
     const int n = ctx->n, T = 256;
+    B2_TRY(dist_before_move(ctx));
     bool resort = !ctx->have_order || ctx->force_resort;
     ctx->force_resort = false;
     if (!resort) {
@@ -692,7 +755,7 @@ extern "C" int b2_eval(b2_context* ctx, uint32_t group_mask, int flags, double* 
         for (const PairForce& pf : ctx->pair_forces)
             if (group_mask & (1u << pf.group)) any_pair = true;
         if (any_pair) {
-            B2_TRY(dist_sync_positions(ctx));
+            if (!ctx->p2p) B2_TRY(dist_sync_positions(ctx));
             B2_TRY(nl_prepare(ctx, false));
         }
         for (const PairForce& pf : ctx->pair_forces) {
@@ -716,6 +779,7 @@ extern "C" int b2_eval(b2_context* ctx, uint32_t group_mask, int flags, double* 
             k_fold_energy<<<1, 1, 0, ctx->stream>>>(ctx->d_energy, pm.group, pm.eself, 0);
             B2_LAUNCH_CHECK();
         }
+        B2_TRY(dist_before_move(ctx));
         double h[66];
         B2_CUDA(cudaMemcpyAsync(h, ctx->d_energy, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         B2_TRY(b2_synchronize(ctx));

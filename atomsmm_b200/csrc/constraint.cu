@@ -201,7 +201,12 @@ int con_snapshot(b2_context* ctx) {
 }
 
 int con_positions(b2_context* ctx) {
-    if (ctx->nclusters == 0) return B2_OK;
+    // the position version advances on EVERY rank whenever the system has constraints, also on a rank that
+    // owns no cluster: versions drive the exchange protocol and must stay identical across ranks
+    if (ctx->nclusters == 0) {
+        if (!ctx->h_con_dist.empty()) ctx->pos_version++;
+        return B2_OK;
+    }
     const int T = 128;
     k_shake<<<(ctx->nclusters + T - 1)/T, T, 0, ctx->stream>>>(ctx->nclusters, ctx->con_ptr, ctx->con_pairs, ctx->con_d2,
                                                                  ctx->massd, ctx->x, ctx->xcon, ctx->con_tol, ctx->nl_flags);

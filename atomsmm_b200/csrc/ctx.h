@@ -30,6 +30,7 @@
 #define B2_MAX_PAIR_PARAMS 16
 #define B2_CHUNK 128           // atoms per molecule chunk of the fused inner-loop kernel
 #define B2_INNER_MAX_FORCES 16
+#define B2_MAX_RANKS 16
 
 struct PairParams {           // passed by value to kernels
     int family;
@@ -140,7 +141,17 @@ struct b2_context {
     void* comm = nullptr;                         // ncclComm_t
     std::vector<int> range;                       // ownership boundaries in sorted order, size nranks+1
     int a_lo = 0, a_hi = 0, g_lo = 0, g_hi = 0;   // owned atoms [a_lo, a_hi), i-groups [g_lo, g_hi)
-    long long x_synced = 0;                       // pos_version for which x is consistent on all ranks
+    long long x_synced = 0;                       // pos_version for which x is complete and consistent on all ranks
+    // peer-memory halo exchange over NVLink (dist.cu): readers PULL the owners' positions
+    bool p2p = false;                             // peers' x and signal blocks are mapped into this process
+    double* peer_x[B2_MAX_RANKS] = {nullptr};     // peer r's position array (own entry: ctx->x)
+    unsigned long long* peer_sig[B2_MAX_RANKS] = {nullptr};   // peer r's signal block (own entry: ctx->sig)
+    unsigned long long* sig = nullptr;            // this rank's signal block: written by the peers
+    unsigned long long* dd_state = nullptr;       // [0] exchange epoch [1] reduction epoch [2] time-out flag [3] ticket
+    unsigned char* halo_mark = nullptr;           // [ngroups] j-group seen by the list build and not (entirely) owned
+    int* halo_groups = nullptr;                   // compacted marks: the groups whose atoms are pulled
+    int* halo_count = nullptr;                    // device counter of halo_groups
+    bool acks_pending = false;                    // peers may still be reading x: wait before the next move
 
     // ---- fused RESPA inner loop (integrate.cu) ----------------------------------------------
     bool inner_built = false, inner_ok = false;
@@ -160,9 +171,12 @@ struct b2_context {
     double* xcon = nullptr;                       // [n][3] last constrained configuration
 
     // ---- cutoff-band pairs settled in float64 (pair.cu) -----------------------------------
-    int* band_pairs = nullptr;
-    unsigned* band_count = nullptr;
-    unsigned band_capacity = 1u << 16;
+    int* band_pairs = nullptr;                    // [2 lanes][capacity] int2
+    unsigned* band_count = nullptr;               // [2 lanes]
+    unsigned band_capacity = 1u << 16;            // per lane; sized from n by b2_set_particles
+    int* band_slot = nullptr;                     // [2 lanes][n] owner entry of every atom's accumulator (-1: none)
+    long long* band_acc = nullptr;                // [2 lanes][capacity][3] fixed-point accumulators
+    unsigned* band_ticket = nullptr;              // [2 lanes]
 
     // ---- profiling (eager mode only): CUDA-event pairs around every pair-force launch -------
     bool profiling = false;
@@ -238,7 +252,12 @@ int pme_setup(b2_context* ctx, PmeForce& pf);
 int pme_eval(b2_context* ctx, PmeForce& pf, float4* out, double* acc);
 void pme_release(PmeForce& pf);
 int dist_partition(b2_context* ctx);
-int dist_sync_positions(b2_context* ctx);
+int dist_sync_positions(b2_context* ctx);           // every rank ends up with the complete position array
+int dist_exchange_halo(b2_context* ctx);            // peer-memory mode: post + pull (halo, or everything on a rebuild)
+int dist_before_move(b2_context* ctx);              // peer-memory mode: wait until the peers have finished reading x
+int dist_halo_compact(b2_context* ctx);             // after a list build: marks -> halo_groups
+int dist_reduce_value(b2_context* ctx, double* value);   // sum of one device double over the ranks, on the stream
+void dd_fill_peers(const b2_context* ctx, void* peers_out);   // DDPeers record for kernels outside dist.cu
 int dist_gather3(b2_context* ctx, double* array);
 int dist_gather_forces(b2_context* ctx, float4* array);
 int dist_allreduce(b2_context* ctx, double* values, int count);

@@ -2,19 +2,27 @@
 // order (whole molecules, Morton-contiguous => spatially compact domains), NCCL over NVLink.
 //
 // The reference is single-process; this is the engine's own decomposition:
-//   * every rank keeps a full copy of the positions; before each pair-force evaluation the owned
-//     segments are exchanged (grouped ncclBroadcast = all-gather with uneven segments).  With the
-//     full (both-directions) neighbour list there is NO force return;
 //   * velocities, forces, thermostat variables, neighbour lists and all integration work exist
-//     only for the owned range; bonded terms are intramolecular and need no communication;
-//   * global sums (mvv, energies) are ncclAllReduce'd; the skin test runs on the replicated
-//     positions, so every rank takes the same rebuild decision without communication;
-//   * all NCCL calls are enqueued on the context stream and are captured into the per-step graph.
+//     only for the owned range; bonded terms are intramolecular and need no communication; with the
+//     full (both-directions) neighbour list there is NO force return;
+//   * HALO EXCHANGE over peer memory (default): every rank maps its peers' position arrays
+//     (cudaIpc, NVLink).  Before a pair-force evaluation each rank tests the skin criterion on its
+//     OWN atoms, posts "positions final + rebuild wanted?" to all peers, and pulls the positions of
+//     its halo -- the j-groups its last list build saw and does not own, ~5 MB instead of the
+//     100 MB of a full replica at 4.2 M atoms -- straight out of the owners' memory; if any rank
+//     wants a rebuild, everybody pulls everything and rebuilds (same decision everywhere, taken on
+//     the device, so the whole step stays one CUDA graph).  Sums are pushed into the peers'
+//     signal blocks and added in rank order (dd.cuh);
+//   * fall-back (B2_DD_EXCHANGE=nccl or no peer access): every rank keeps a full replica, owned
+//     segments are all-gathered with grouped ncclBroadcast before each pair-force evaluation and
+//     sums are ncclAllReduce'd;
+//   * host-initiated gathers of the complete state (getters, re-ordering) always use NCCL.
 #include <dlfcn.h>
 #include <nccl.h>
 #include <string.h>
 
 #include "ctx.h"
+#include "dd.cuh"
 
 struct NcclApi {
     void* handle = nullptr;
@@ -86,6 +94,16 @@ extern "C" int b2_comm_init(b2_context* ctx, int nranks, int rank, const char* i
 }
 
 void dist_release(b2_context* ctx) {
+    if (ctx->p2p) {
+        for (int r = 0; r < ctx->nranks; r++) {
+            if (r == ctx->rank) continue;
+            if (ctx->peer_x[r]) cudaIpcCloseMemHandle(ctx->peer_x[r]);
+            if (ctx->peer_sig[r]) cudaIpcCloseMemHandle(ctx->peer_sig[r]);
+        }
+        ctx->p2p = false;
+    }
+    cudaFree(ctx->sig); cudaFree(ctx->dd_state); cudaFree(ctx->halo_mark); cudaFree(ctx->halo_groups); cudaFree(ctx->halo_count);
+    ctx->sig = nullptr; ctx->dd_state = nullptr; ctx->halo_mark = nullptr; ctx->halo_groups = nullptr; ctx->halo_count = nullptr;
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->comm);
     ctx->comm = nullptr;
 }
@@ -147,8 +165,10 @@ static int allgather_segments(b2_context* ctx, void* base, size_t elem_bytes) {
     return B2_OK;
 }
 
+// every rank ends up with the complete, current position array (NCCL all-gather of the owned segments)
 int dist_sync_positions(b2_context* ctx) {
     if (ctx->nranks == 1 || ctx->x_synced == ctx->pos_version) return B2_OK;
+    B2_TRY(dist_before_move(ctx));        // x is about to be overwritten outside the owned range: no reader may be active
     B2_TRY(allgather_segments(ctx, ctx->x, 3*sizeof(double)));
     ctx->x_synced = ctx->pos_version;
     return B2_OK;
@@ -160,5 +180,233 @@ int dist_gather_forces(b2_context* ctx, float4* array) { return allgather_segmen
 int dist_allreduce(b2_context* ctx, double* values, int count) {
     if (ctx->nranks == 1) return B2_OK;
     B2_NCCL(g_nccl.AllReduce(values, values, count, ncclDouble, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
+    return B2_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// peer-memory exchange (see dd.cuh)
+// ---------------------------------------------------------------------------------------------
+static DDPeers make_peers(const b2_context* ctx) {
+    DDPeers P;
+    memset(&P, 0, sizeof(P));
+    P.rank = ctx->rank; P.nranks = ctx->nranks;
+    for (int r = 0; r <= ctx->nranks && r <= B2_MAX_RANKS; r++) P.range[r] = r < (int)ctx->range.size() ? ctx->range[r] : ctx->n;
+    for (int r = 0; r < ctx->nranks; r++) { P.x[r] = ctx->peer_x[r]; P.sig[r] = ctx->peer_sig[r]; }
+    return P;
+}
+
+void dd_fill_peers(const b2_context* ctx, void* out) { *(DDPeers*)out = make_peers(ctx); }
+
+// "my owned positions of this exchange are final", plus this rank's verdict of the skin test
+__global__ void k_dd_post(DDPeers P, unsigned long long* state, const int* __restrict__ nl_flags) {
+    __shared__ unsigned long long epoch;
+    if (threadIdx.x == 0) { epoch = state[0] + 1ull; state[0] = epoch; }
+    __syncthreads();
+    const int r = threadIdx.x;
+    if (r < P.nranks && r != P.rank) {
+        const unsigned long long flag = nl_flags[0] != 0 ? 1ull : 0ull;
+        __threadfence_system();
+        dd_st_release(&P.sig[r][DD_POST + P.rank], (epoch << 1) | flag);
+    }
+}
+
+// wait for every peer's post, then copy the halo (or, when anybody wants a rebuild, all foreign
+// atoms) out of the owners' memory; the last block to finish publishes the common rebuild
+// decision, resets the halo counter for the coming rebuild and acknowledges to the owners
+__global__ void __launch_bounds__(256) k_dd_pull(DDPeers P, unsigned long long* state, int* nl_flags, double* __restrict__ x,
+                                                 int n, const int* __restrict__ halo_groups, int* halo_count) {
+    __shared__ int s_flag;
+    __shared__ unsigned long long s_epoch;
+    __shared__ bool last;
+    if (threadIdx.x == 0) { s_flag = nl_flags[0] != 0 ? 1 : 0; s_epoch = state[0]; }
+    __syncthreads();
+    const unsigned long long e = s_epoch;
+    if ((int)threadIdx.x < P.nranks && (int)threadIdx.x != P.rank) {
+        const unsigned long long v = dd_wait(&P.sig[P.rank][DD_POST + threadIdx.x], 1, e, state);
+        if (v & 1ull) atomicOr(&s_flag, 1);
+    }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x*blockDim.x;
+    const long long first = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (s_flag) {
+        for (long long d = first; d < 3ll*n; d += stride) {
+            const int o = dd_owner(P, (int)(d/3));
+            if (o != P.rank) x[d] = __ldcg(P.x[o] + d);
+        }
+    } else {
+        const long long total = 3ll*B2_GROUP*(*halo_count);
+        for (long long t = first; t < total; t += stride) {
+            const int g = halo_groups[t/(3*B2_GROUP)];
+            const long long d = 3ll*B2_GROUP*g + t % (3*B2_GROUP);
+            if (d < 3ll*n) {
+                const int o = dd_owner(P, (int)(d/3));
+                if (o != P.rank) x[d] = __ldcg(P.x[o] + d);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd((unsigned*)(state + 3), 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) {
+        *(unsigned*)(state + 3) = 0u;
+        nl_flags[0] = s_flag;
+        if (s_flag) *halo_count = 0;
+    }
+    if ((int)threadIdx.x < P.nranks && (int)threadIdx.x != P.rank) {
+        __threadfence_system();
+        dd_st_release(&P.sig[threadIdx.x][DD_ACK + P.rank], e);
+    }
+}
+
+// an owner may move its atoms again only after every peer has finished reading them
+__global__ void k_dd_wait_acks(DDPeers P, unsigned long long* state) {
+    const unsigned long long e = state[0];
+    if ((int)threadIdx.x < P.nranks && (int)threadIdx.x != P.rank) dd_wait(&P.sig[P.rank][DD_ACK + threadIdx.x], 0, e, state);
+}
+
+__global__ void k_halo_compact(int ngroups, unsigned char* __restrict__ mark, int* __restrict__ halo_groups, int* halo_count,
+                               const int* __restrict__ flags) {
+    if (!flags[0]) return;
+    const int g = blockIdx.x*blockDim.x + threadIdx.x;
+    if (g >= ngroups || !mark[g]) return;
+    mark[g] = 0;
+    halo_groups[atomicAdd(halo_count, 1)] = g;
+}
+
+// globals[target] <- sum over ranks of globals[target]
+__global__ void k_dd_reduce(DDPeers P, unsigned long long* state, double* value) {
+    __shared__ double part[B2_MAX_RANKS];
+    __shared__ unsigned long long epoch;
+    const double total = dd_allreduce_sum(P, state, *value, threadIdx.x, part, &epoch);
+    __syncthreads();
+    if (threadIdx.x == 0) *value = total;
+}
+
+int dist_exchange_halo(b2_context* ctx) {
+    if (!ctx->p2p) return B2_OK;
+    DDPeers P = make_peers(ctx);
+    k_dd_post<<<1, 32, 0, ctx->stream>>>(P, ctx->dd_state, ctx->nl_flags);
+    B2_LAUNCH_CHECK();
+    k_dd_pull<<<296, 256, 0, ctx->stream>>>(P, ctx->dd_state, ctx->nl_flags, ctx->x, ctx->n, ctx->halo_groups, ctx->halo_count);
+    B2_LAUNCH_CHECK();
+    ctx->acks_pending = true;
+    ctx->counters[7]++;
+    return B2_OK;
+}
+
+int dist_before_move(b2_context* ctx) {
+    if (!ctx->p2p || !ctx->acks_pending) return B2_OK;
+    DDPeers P = make_peers(ctx);
+    k_dd_wait_acks<<<1, 32, 0, ctx->stream>>>(P, ctx->dd_state);
+    B2_LAUNCH_CHECK();
+    ctx->acks_pending = false;
+    return B2_OK;
+}
+
+int dist_halo_compact(b2_context* ctx) {
+    if (!ctx->p2p) return B2_OK;
+    const int T = 256;
+    k_halo_compact<<<(ctx->ngroups + T - 1)/T, T, 0, ctx->stream>>>(ctx->ngroups, ctx->halo_mark, ctx->halo_groups,
+                                                                    ctx->halo_count, ctx->nl_flags);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+// sum of one device double over the ranks, on the context stream
+int dist_reduce_value(b2_context* ctx, double* value) {
+    if (ctx->nranks == 1) return B2_OK;
+    if (!ctx->p2p) return dist_allreduce(ctx, value, 1);
+    DDPeers P = make_peers(ctx);
+    k_dd_reduce<<<1, 32, 0, ctx->stream>>>(P, ctx->dd_state, value);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+// ---- set-up: exchange of cudaIpc handles (host side does the all-gather, e.g. torch.distributed) ---
+struct DDHandles {
+    cudaIpcMemHandle_t x, sig;
+    int device, n;
+};
+static_assert(sizeof(DDHandles) <= 256, "handle record must fit the ABI's 256 bytes");
+
+extern "C" int b2_comm_export(b2_context* ctx, char* out256) {
+    if (!ctx || !out256 || ctx->n == 0) return b2_fail(ctx, B2_ERR_STATE, "set particles before exporting the peer handles");
+    B2_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->sig == nullptr) {
+        // 2 MB: an allocation of its own (small cudaMalloc blocks share a slab, and a slab can be opened only
+        // once per peer -- the position array of a small system may live in one)
+        B2_CUDA(cudaMalloc(&ctx->sig, 2u << 20));
+        B2_CUDA(cudaMemset(ctx->sig, 0, 2u << 20));
+    }
+    DDHandles h;
+    memset(&h, 0, sizeof(h));
+    B2_CUDA(cudaIpcGetMemHandle(&h.x, ctx->x));
+    B2_CUDA(cudaIpcGetMemHandle(&h.sig, ctx->sig));
+    h.device = ctx->device; h.n = ctx->n;
+    memset(out256, 0, 256);
+    memcpy(out256, &h, sizeof(h));
+    return B2_OK;
+}
+
+// all256: nranks records as written by b2_comm_export, in rank order.  On failure (no peer access, IPC not
+// permitted) the context stays in the NCCL all-gather mode and the reason is in b2_last_error.
+extern "C" int b2_comm_import(b2_context* ctx, int nranks, const char* all256) {
+    if (ctx && nranks == -1) {                       // "not every rank could map its peers": back to the NCCL mode
+        ctx->p2p = false;
+        program_release(ctx);
+        return B2_OK;
+    }
+    if (!ctx || !all256 || nranks != ctx->nranks) return b2_fail(ctx, B2_ERR_ARG, "bad peer handle table");
+    if (nranks == 1) return B2_OK;
+    if (nranks > B2_MAX_RANKS) return b2_fail(ctx, B2_ERR_UNSUPPORTED, "at most %d ranks in peer-memory mode", B2_MAX_RANKS);
+    B2_CUDA(cudaSetDevice(ctx->device));
+    for (int r = 0; r < nranks; r++) {
+        DDHandles h;
+        memcpy(&h, all256 + 256*(size_t)r, sizeof(h));
+        if (h.n != ctx->n) return b2_fail(ctx, B2_ERR_ARG, "rank %d describes %d atoms, this rank %d", r, h.n, ctx->n);
+        if (r == ctx->rank) { ctx->peer_x[r] = ctx->x; ctx->peer_sig[r] = ctx->sig; continue; }
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, ctx->device, h.device);
+        if (!can) return b2_fail(ctx, B2_ERR_UNSUPPORTED, "device %d cannot access device %d", ctx->device, h.device);
+        void *px = nullptr, *ps = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&px, h.x, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&ps, h.sig, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return b2_fail(ctx, B2_ERR_UNSUPPORTED, "cudaIpcOpenMemHandle for rank %d failed: %s", r, cudaGetErrorString(e));
+        }
+        ctx->peer_x[r] = (double*)px;
+        ctx->peer_sig[r] = (unsigned long long*)ps;
+    }
+    if (ctx->dd_state == nullptr) {
+        B2_CUDA(cudaMalloc(&ctx->dd_state, sizeof(unsigned long long)*8));
+        B2_CUDA(cudaMemset(ctx->dd_state, 0, sizeof(unsigned long long)*8));
+        B2_CUDA(cudaMalloc(&ctx->halo_mark, ctx->ngroups));
+        B2_CUDA(cudaMemset(ctx->halo_mark, 0, ctx->ngroups));
+        B2_CUDA(cudaMalloc(&ctx->halo_groups, sizeof(int)*ctx->ngroups));
+        B2_CUDA(cudaMalloc(&ctx->halo_count, sizeof(int)));
+        B2_CUDA(cudaMemset(ctx->halo_count, 0, sizeof(int)));
+    }
+    ctx->p2p = true;
+    program_release(ctx);
+    return B2_OK;
+}
+
+extern "C" int b2_comm_mode(b2_context* ctx, int* peer_memory, long long* halo_atoms) {
+    if (!ctx) return B2_ERR_ARG;
+    if (peer_memory) *peer_memory = ctx->p2p ? 1 : 0;
+    if (halo_atoms) {
+        *halo_atoms = 0;
+        if (ctx->p2p && ctx->halo_count) {
+            int c = 0;
+            B2_CUDA(cudaStreamSynchronize(ctx->stream));
+            B2_CUDA(cudaMemcpy(&c, ctx->halo_count, sizeof(int), cudaMemcpyDeviceToHost));
+            *halo_atoms = (long long)c*B2_GROUP;
+        }
+    }
     return B2_OK;
 }

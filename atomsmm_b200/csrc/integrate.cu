@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "bonded.cuh"
+#include "dd.cuh"
 
 #define FULL 0xffffffffu
 
@@ -146,6 +147,22 @@ __global__ void k_global(const int* __restrict__ code, int len, const double* __
     __shared__ ScalarStage stage;
     if (begin_step && threadIdx.x == 0) rng_state[2] += 1ull;      // MD step counter of the RNG streams
     run_scalar_program_staged(stage, code, len, consts, nconsts, globals, nglobals, rng_state, energies);
+}
+
+// Domain decomposition, peer-memory mode: the all-reduce of a thermostat's sum(m v.v) and the scalar
+// program that consumes it are ONE single-block kernel -- partials are pushed into the peers' signal
+// blocks over NVLink and added in rank order (dd.cuh), no library collective in the step graph.
+__global__ void k_global_reduce(DDPeers P, unsigned long long* dd_state, int target, const int* __restrict__ code, int len,
+                                const double* __restrict__ consts, int nconsts, double* globals, int nglobals,
+                                unsigned long long* rng_state, const double* energies) {
+    __shared__ ScalarStage stage;
+    __shared__ double part[B2_MAX_RANKS];
+    __shared__ unsigned long long epoch;
+    const double total = dd_allreduce_sum(P, dd_state, __ldcg(&globals[target]), threadIdx.x, part, &epoch);
+    __syncthreads();
+    if (threadIdx.x == 0) { globals[target] = total; __threadfence(); }
+    __syncthreads();
+    if (len > 0) run_scalar_program_staged(stage, code, len, consts, nconsts, globals, nglobals, rng_state, energies);
 }
 
 // The velocity kernel: v <- s*v + sum_k s_k c_k f_k/m ; [x += c_d v] ; [mvv <- sum(m v.v) ; scalar
@@ -424,7 +441,7 @@ int forces_ensure(b2_context* ctx, uint32_t mask, int slot) {
     for (const PairForce& pf : ctx->pair_forces)
         if (mask & (1u << pf.group)) any_pair = true;
     if (any_pair) {
-        B2_TRY(dist_sync_positions(ctx));
+        if (!ctx->p2p) B2_TRY(dist_sync_positions(ctx));     // peer-memory mode: the halo arrives inside nl_prepare
         B2_TRY(nl_prepare(ctx, false));
     }
     bool written = false;
@@ -433,6 +450,7 @@ int forces_ensure(b2_context* ctx, uint32_t mask, int slot) {
         B2_TRY(pair_eval_forces(ctx, pf, ctx->fbuf[slot], written));
         written = true;
     }
+    B2_TRY(dist_before_move(ctx));      // by now the peers have long finished reading: the wait costs nothing here
     if (!written) B2_CUDA(cudaMemsetAsync(ctx->fbuf[slot], 0, sizeof(float4)*ctx->n, ctx->stream));
     B2_TRY(bonded_eval_forces(ctx, mask, ctx->fbuf[slot]));
     for (PmeForce& pm : ctx->pme_forces)
@@ -452,7 +470,7 @@ static bool has_pair_force(const b2_context* ctx, uint32_t mask) {
 // lists, different outputs -- and run concurrently on two streams, which become two branches of
 // the step's CUDA graph.  Each kernel alone leaves ~30 % of the issue slots idle and has its own tail.
 static int forces_ensure_dual(b2_context* ctx, uint32_t mask_a, int slot_a, uint32_t mask_b, int slot_b) {
-    B2_TRY(dist_sync_positions(ctx));
+    if (!ctx->p2p) B2_TRY(dist_sync_positions(ctx));
     B2_TRY(nl_prepare(ctx, false));
     B2_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
     B2_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
@@ -469,6 +487,7 @@ static int forces_ensure_dual(b2_context* ctx, uint32_t mask_a, int slot_a, uint
     }
     B2_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
     B2_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    B2_TRY(dist_before_move(ctx));
     const uint32_t masks[2] = {mask_a, mask_b};
     const int slots[2] = {slot_a, slot_b};
     for (int k = 0; k < 2; k++) {
@@ -525,6 +544,7 @@ static int launch_vel(b2_context* ctx, const b2_op& op) {
     const int blocks = std::max(1, (hi - lo + T - 1)/T);
     KickArgs ka;
     B2_TRY(fill_kick(ctx, op, ka));
+    if (op.c >= 0) B2_TRY(dist_before_move(ctx));
     cudaStream_t s = ctx->stream;
     // with several ranks the sum must be all-reduced before the scalar program may consume it
     const bool split = ctx->nranks > 1 && ka.mvv >= 0;
@@ -539,7 +559,13 @@ static int launch_vel(b2_context* ctx, const b2_op& op) {
                                           ctx->rng_state, ctx->d_energy);
     }
     B2_LAUNCH_CHECK();
-    if (split) {
+    if (split && ctx->p2p) {
+        DDPeers P;
+        dd_fill_peers(ctx, &P);
+        k_global_reduce<<<1, 64, 0, s>>>(P, ctx->dd_state, ka.mvv, ctx->code + op.f, op.g, ctx->consts, ctx->nconsts,
+                                         ctx->globals, ctx->nglobals, ctx->rng_state, ctx->d_energy);
+        B2_LAUNCH_CHECK();
+    } else if (split) {
         B2_TRY(dist_allreduce(ctx, ctx->globals + ka.mvv, 1));
         if (op.g > 0) {
             k_global<<<1, 64, 0, s>>>(ctx->code + op.f, op.g, ctx->consts, ctx->nconsts, ctx->globals,
@@ -618,6 +644,7 @@ static int try_fused_run(b2_context* ctx, size_t k, int* consumed) {
     }
     for (int g = 0; g < B2_FSLOTS; g++) A.f[g] = ctx->fbuf[g];
     A.write_force = local_valid == version ? 1 : 0;
+    B2_TRY(dist_before_move(ctx));
     k_inner<<<ctx->nchunks, B2_CHUNK, 0, ctx->stream>>>(ctx->chunk_start, ctx->chunk_term_ptr, ctx->chunk_terms,
                                                         ctx->x, ctx->v, ctx->massd, ctx->globals,
                                                         ctx->fbuf[A.local_slot], A);
@@ -671,7 +698,8 @@ static int run_one_step(b2_context* ctx) {
         }
         case B2_OP_PERDOF: {
             PerDofTable tab = make_table(ctx);
-            k_perdof<<<(ndof + T - 1)/T, T, 0, s>>>(3*lo, 3*hi, tab, op.a, ctx->code + op.b, op.c, ctx->consts,
+            if (op.a == 0) B2_TRY(dist_before_move(ctx));
+            k_perdof<<<std::max(1, (ndof + T - 1)/T), T, 0, s>>>(3*lo, 3*hi, tab, op.a, ctx->code + op.b, op.c, ctx->consts,
                                                       ctx->globals, ctx->rng_state, op.e, 0);
             B2_LAUNCH_CHECK();
             if (op.a == 0) ctx->pos_version++;
@@ -689,7 +717,7 @@ static int run_one_step(b2_context* ctx) {
             B2_LAUNCH_CHECK();
             k_sum_final<<<1, 256, 0, s>>>(blocks, ctx->sum_partial, ctx->globals, op.a);
             B2_LAUNCH_CHECK();
-            B2_TRY(dist_allreduce(ctx, ctx->globals + op.a, 1));
+            B2_TRY(dist_reduce_value(ctx, ctx->globals + op.a));
             break;
         }
         case B2_OP_GLOBAL:
@@ -707,17 +735,19 @@ static int run_one_step(b2_context* ctx) {
             break;
         }
         case B2_OP_DRIFT:
-            k_drift<<<(ndof + T - 1)/T, T, 0, s>>>(3*lo, 3*hi, ctx->x, ctx->v, ctx->massd, ctx->globals, op.a);
+            B2_TRY(dist_before_move(ctx));
+            k_drift<<<std::max(1, (ndof + T - 1)/T), T, 0, s>>>(3*lo, 3*hi, ctx->x, ctx->v, ctx->massd, ctx->globals, op.a);
             B2_LAUNCH_CHECK();
             ctx->pos_version++;
             break;
         case B2_OP_SCALE:
-            k_scale<<<(ndof + T - 1)/T, T, 0, s>>>(3*lo, 3*hi, ctx->v, ctx->globals, op.a);
+            k_scale<<<std::max(1, (ndof + T - 1)/T), T, 0, s>>>(3*lo, 3*hi, ctx->v, ctx->globals, op.a);
             B2_LAUNCH_CHECK();
             break;
         case B2_OP_UPDATE_STATE:
             break;
         case B2_OP_CONSTRAIN_X:
+            B2_TRY(dist_before_move(ctx));
             B2_TRY(con_positions(ctx));
             break;
         case B2_OP_CONSTRAIN_V:
@@ -735,7 +765,7 @@ static int run_one_step(b2_context* ctx) {
             for (const PairForce& pf : ctx->pair_forces) {
                 if (pf.family != B2_PAIR_SOFTCORE) continue;
                 if (!prepared) {
-                    B2_TRY(dist_sync_positions(ctx));
+                    if (!ctx->p2p) B2_TRY(dist_sync_positions(ctx));
                     B2_TRY(nl_prepare(ctx, false));
                     prepared = true;
                 }
@@ -750,6 +780,7 @@ static int run_one_step(b2_context* ctx) {
             return b2_fail(ctx, B2_ERR_UNSUPPORTED, "unknown program op %d", op.kind);
         }
     }
+    B2_TRY(dist_before_move(ctx));      // a step leaves no acknowledgement outstanding (graph replays are self-contained)
     return B2_OK;
 }
 
@@ -792,6 +823,7 @@ int program_run(b2_context* ctx, int nsteps) {
             B2_TRY(inner_prepare(ctx));
             B2_TRY(con_prepare(ctx));
         }
+        B2_TRY(dist_before_move(ctx));
         const unsigned long long entry = valid_mask(ctx);
         const bool synced = ctx->x_synced == ctx->pos_version;
         if (use_graph && ctx->graph_ready && (entry & ctx->graph_entry_mask) == ctx->graph_entry_mask &&

@@ -57,9 +57,9 @@ __device__ __forceinline__ bool is_excluded(int oi, int oj, unsigned long long m
 }
 
 // K8: skin test, one pass over x and xref (48 B/atom), before every pair-force evaluation.
-__global__ void k_skin_check(int n, const double* __restrict__ x, const double* __restrict__ xref, double limit2,
+__global__ void k_skin_check(int lo, int n, const double* __restrict__ x, const double* __restrict__ xref, double limit2,
                              int* flags, int have_ref) {
-    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    int i = lo + blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (have_ref) {
         double dx = x[3*i] - xref[3*i], dy = x[3*i+1] - xref[3*i+1], dz = x[3*i+2] - xref[3*i+2];
@@ -266,7 +266,8 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
                                                              const unsigned long long* __restrict__ exmask,
                                                              const int* __restrict__ excl_ptr,
                                                              const int* __restrict__ excl_idx, int excl_span,
-                                                             BuildArgs a, int* flags) {
+                                                             BuildArgs a, int* flags,
+                                                             unsigned char* __restrict__ halo_mark, int own_lo, int own_hi) {
     if (!flags[0]) return;
     const int warp = g_lo + ((blockIdx.x*blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -432,6 +433,11 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
                         const float gzz = fmaxf(fabsf(dz) - (hi[2] + hj.z), 0.f);
                         pass = gx*gx + gyy*gyy + gzz*gzz < rmax2;
                         e = make_float4(dx, dy, dz, cj.w);
+                        // domain decomposition: a candidate group that this rank does not own entirely is halo
+                        if (halo_mark && pass) {
+                            const int jg = __float_as_int(cj.w);
+                            if (jg*B2_GROUP < own_lo || (jg + 1)*B2_GROUP > own_hi) halo_mark[jg] = 1;
+                        }
                     }
                     const unsigned ballot = __ballot_sync(FULL, pass);
                     if (pass) queue[wib][qn + __popc(ballot & lt)] = e;
@@ -476,6 +482,7 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
                 const float gzz = fmaxf(fabsf(dz) - (hi[2] + hj.z), 0.f);
                 pass = gx*gx + gyy*gyy + gzz*gzz < rmax2;
                 e = make_float4(dx, dy, dz, __int_as_float(jg));
+                if (halo_mark && pass && (jg*B2_GROUP < own_lo || (jg + 1)*B2_GROUP > own_hi)) halo_mark[jg] = 1;
             }
             const unsigned ballot = __ballot_sync(FULL, pass);
             if (pass) queue[wib][qn + __popc(ballot & lt)] = e;
@@ -505,9 +512,9 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
 }
 
 // reference positions for the next skin test; the last block to finish closes the rebuild
-__global__ void k_save_ref(int n3, const double* __restrict__ x, double* __restrict__ xref, int* flags, int* hmax_bits) {
+__global__ void k_save_ref(int lo3, int n3, const double* __restrict__ x, double* __restrict__ xref, int* flags, int* hmax_bits) {
     if (!flags[0]) return;
-    int i = blockIdx.x*blockDim.x + threadIdx.x;
+    int i = lo3 + blockIdx.x*blockDim.x + threadIdx.x;
     if (i < n3) xref[i] = x[i];
     __shared__ bool last;
     __syncthreads();
@@ -546,9 +553,10 @@ int nl_setup(b2_context* ctx) {
     double rmax = 0;
     for (int k = 0; k < ctx->nlists; k++) rmax = std::max(rmax, ctx->lists[k].cutoff + ctx->skin);
     for (int d = 0; d < 3; d++) {
-        if (ctx->lists[0].cutoff > 0.5*ctx->box[d] + 1e-9)
-            return b2_fail(ctx, B2_ERR_ARG, "cutoff %g nm exceeds half the box length %g nm", rmax - ctx->skin,
-                           ctx->box[d]);
+        for (int k = 0; k < ctx->nlists; k++)
+            if (ctx->lists[k].cutoff > 0.5*ctx->box[d] + 1e-9)
+                return b2_fail(ctx, B2_ERR_ARG, "cutoff %g nm exceeds half the box length %g nm (minimum image)",
+                               ctx->lists[k].cutoff, ctx->box[d]);
         // cells are short along x (the contiguous direction of the cell-ordered arrays: the list build
         // walks rows of cells along x) and as long as the list radius along y and z, so that a row is
         // one long contiguous run of candidates instead of many short ones
@@ -614,9 +622,18 @@ int nl_prepare(b2_context* ctx, bool force) {
     cudaStream_t s = ctx->stream;
     double limit = 0.5*ctx->skin;
     int* hmax = ctx->nl_flags + 5;
-    k_skin_check<<<(n + T - 1)/T, T, 0, s>>>(n, ctx->x, ctx->xref, limit*limit, ctx->nl_flags,
-                                               (ctx->lists_built && !force) ? 1 : 0);
+    // Peer-memory domain decomposition: every atom is tested by its owner, the verdicts are OR-ed over the
+    // ranks inside the halo exchange, which also brings in the positions the pair kernels (or, when the
+    // verdict is "rebuild", the list build) are about to read.  Otherwise the test runs over all atoms
+    // (single GPU; NCCL mode, where the caller has all-gathered the positions before).
+    const int t_lo = ctx->p2p ? ctx->a_lo : 0, t_hi = ctx->p2p ? ctx->a_hi : n;
+    k_skin_check<<<std::max(1, (t_hi - t_lo + T - 1)/T), T, 0, s>>>(t_lo, t_hi, ctx->x, ctx->xref, limit*limit, ctx->nl_flags,
+                                                                  (ctx->lists_built && !force) ? 1 : 0);
     B2_LAUNCH_CHECK();
+    if (ctx->p2p) {
+        if (!force) B2_TRY(dist_exchange_halo(ctx));     // forced builds follow b2_set_positions: x is complete everywhere
+        else B2_CUDA(cudaMemsetAsync(ctx->halo_count, 0, sizeof(int), s));
+    }
     k_group_geom<<<(8*ng + T - 1)/T, T, 0, s>>>(n, ng, ctx->x, g, ctx->prel, ctx->gcen, ctx->ghalf, ctx->gcell,
                                                  ctx->cell_count, hmax, (float)(fat_factor*ctx->cellsize[0]),
                                                  ctx->fat_list, ng, ctx->nl_flags);
@@ -641,9 +658,11 @@ int nl_prepare(b2_context* ctx, bool force) {
     }
     k_build_lists<<<std::max(1, (ctx->g_hi - ctx->g_lo + NL_WARPS - 1)/NL_WARPS), 32*NL_WARPS, 0, s>>>(
         n, ctx->g_lo, ctx->g_hi, g, ctx->cell_start, ctx->cgc, ctx->cgh, ctx->gcen, ctx->ghalf, ctx->prel, hmax,
-        ctx->fat_list, ctx->orig, ctx->exmask, ctx->excl_far ? ctx->excl_ptr : nullptr, ctx->excl_idx, ctx->excl_span, a, ctx->nl_flags);
+        ctx->fat_list, ctx->orig, ctx->exmask, ctx->excl_far ? ctx->excl_ptr : nullptr, ctx->excl_idx, ctx->excl_span, a, ctx->nl_flags,
+        ctx->p2p ? ctx->halo_mark : nullptr, ctx->a_lo, ctx->a_hi);
     B2_LAUNCH_CHECK();
-    k_save_ref<<<(3*n + T - 1)/T, T, 0, s>>>(3*n, ctx->x, ctx->xref, ctx->nl_flags, hmax);
+    B2_TRY(dist_halo_compact(ctx));
+    k_save_ref<<<std::max(1, (3*(t_hi - t_lo) + T - 1)/T), T, 0, s>>>(3*t_lo, 3*t_hi, ctx->x, ctx->xref, ctx->nl_flags, hmax);
     B2_LAUNCH_CHECK();
     ctx->lists_built = true;
     return B2_OK;

@@ -103,6 +103,10 @@ struct BandBuffer {
     int* pairs;          // int2 (sorted i, sorted j)
     unsigned* count;
     unsigned capacity;
+    int* slot;           // [n] per atom: index of the band entry that owns the atom's accumulator, or -1
+    long long* acc;      // [capacity][3] fixed-point accumulators (2^-32 kJ/mol/nm)
+    unsigned* ticket;    // last-block-done counter of k_pair_band
+    int* flags;          // nl_flags: [10] = band overflow
 };
 
 template <class POT, bool MINIMG>
@@ -127,8 +131,10 @@ __device__ __forceinline__ void sweep_chunk(const POT& pot, const float4* __rest
         const unsigned en = (unsigned)__float_as_int(pj.w);      // full list entry: mask<<24 | j
         if (r2 < rc2 && !((en >> (24 + il)) & 1u)) {      // rc2 here is the OUTER edge of the band
             if (r2 >= rc2_lo) {
-                const unsigned slot = atomicAdd(bb.count, 1u);
-                if (slot < bb.capacity && i >= 0) { bb.pairs[2*slot] = i; bb.pairs[2*slot+1] = (int)(en & 0xffffffu); }
+                if (i >= 0) {                     // padding lanes of the last group own no atom
+                    const unsigned slot = atomicAdd(bb.count, 1u);
+                    if (slot < bb.capacity) { bb.pairs[2*slot] = i; bb.pairs[2*slot+1] = (int)(en & 0xffffffu); }
+                }
                 continue;
             }
             float rF, e, rinv2;
@@ -215,10 +221,19 @@ __global__ void __launch_bounds__(32*WPB, 8) k_pair_force(int n, int g_lo, int n
     }
 }
 
+// Settlement of the band pairs in float64.  The append order of the band buffer depends on warp
+// scheduling, so the contributions are NOT added to the fp32 force buffer one by one (float addition
+// does not commute with re-ordering): every touched atom gets ONE fixed-point accumulator (claimed
+// by the first entry that reaches it; which entry wins only names the accumulator), all entries add
+// into it with 64-bit integer atomics -- associative, hence independent of the order -- and the last
+// block to finish adds every accumulator to the atom's force exactly once and cleans up.
+#define B2_BAND_SCALE 4294967296.0
 template <class POTD>
 __global__ void k_pair_band(const double* __restrict__ x, const double* __restrict__ pard, BandBuffer bb, POTD pot,
                             double rc2d, double bx, double by, double bz, float4* __restrict__ out) {
-    const unsigned total = min(*bb.count, bb.capacity);
+    const unsigned found = *bb.count;
+    const unsigned total = min(found, bb.capacity);
+    if (found > bb.capacity && blockIdx.x == 0 && threadIdx.x == 0) bb.flags[10] = 1;   // reported by b2_synchronize
     for (unsigned k = blockIdx.x*blockDim.x + threadIdx.x; k < total; k += gridDim.x*blockDim.x) {
         const int i = bb.pairs[2*k], j = bb.pairs[2*k+1];
         double dx = x[3*j] - x[3*i], dy = x[3*j+1] - x[3*i+1], dz = x[3*j+2] - x[3*i+2];
@@ -229,11 +244,36 @@ __global__ void k_pair_band(const double* __restrict__ x, const double* __restri
             pot.template operator()<false>(r2, pard[3*i]*pard[3*j], 0.5*(pard[3*i+1] + pard[3*j+1]),
                                            sqrt(pard[3*i+2]*pard[3*j+2]), rF, e, rinv2);
             const double fr = -rF*rinv2;        // d points from i to j
-            atomicAdd(&out[i].x, (float)(fr*dx));
-            atomicAdd(&out[i].y, (float)(fr*dy));
-            atomicAdd(&out[i].z, (float)(fr*dz));
+            const int prev = atomicCAS(&bb.slot[i], -1, (int)k);
+            const int owner = prev < 0 ? (int)k : prev;
+            unsigned long long* a = reinterpret_cast<unsigned long long*>(bb.acc + 3*(size_t)owner);
+            atomicAdd(a, (unsigned long long)__double2ll_rn(fr*dx*B2_BAND_SCALE));
+            atomicAdd(a + 1, (unsigned long long)__double2ll_rn(fr*dy*B2_BAND_SCALE));
+            atomicAdd(a + 2, (unsigned long long)__double2ll_rn(fr*dz*B2_BAND_SCALE));
         }
     }
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(bb.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (unsigned k = threadIdx.x; k < total; k += blockDim.x) {
+        const int i = bb.pairs[2*k];
+        if (__ldcg(&bb.slot[i]) != (int)k) continue;          // not the entry that owns atom i's accumulator
+        long long* a = bb.acc + 3*(size_t)k;
+        const double fx = (double)__ldcg(&a[0])*(1.0/B2_BAND_SCALE), fy = (double)__ldcg(&a[1])*(1.0/B2_BAND_SCALE),
+                     fz = (double)__ldcg(&a[2])*(1.0/B2_BAND_SCALE);
+        float4 f = out[i];
+        f.x += (float)fx; f.y += (float)fy; f.z += (float)fz;
+        out[i] = f;
+        a[0] = 0; a[1] = 0; a[2] = 0;
+        bb.slot[i] = -1;
+    }
+    if (threadIdx.x == 0) *bb.ticket = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -359,7 +399,9 @@ static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, POTD potd
     const double rcd = effective_cutoff(pf);
     // lane 1 = the side stream, with its own half of the band buffer
     cudaStream_t stream = lane ? ctx->side_stream : ctx->stream;
-    BandBuffer bb{ctx->band_pairs + (lane ? 2*(size_t)ctx->band_capacity : 0), ctx->band_count + lane, ctx->band_capacity};
+    BandBuffer bb{ctx->band_pairs + (lane ? 2*(size_t)ctx->band_capacity : 0), ctx->band_count + lane, ctx->band_capacity,
+                  ctx->band_slot + (lane ? (size_t)ctx->n : 0), ctx->band_acc + (lane ? 3*(size_t)ctx->band_capacity : 0),
+                  ctx->band_ticket + lane, ctx->nl_flags};
     B2_CUDA(cudaMemsetAsync(bb.count, 0, sizeof(unsigned), stream));
     const NList& L = ctx->lists[pf.list];
     const int blocks = (ctx->g_hi - ctx->g_lo + WPB - 1)/WPB;
@@ -419,7 +461,9 @@ static int launch_energy(b2_context* ctx, const PairForce& pf, POT pot, double r
         else if (ck == 3 && !sw) { LJCPot<COUL_ERFC, LJ_STD, SW_NONE, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; } \
         else if (ck == 2) { LJCPot<COUL_RF, LJ_STD, SW_LJ, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; }      \
         else if (ck == 3) { LJCPot<COUL_ERFC, LJ_STD, SW_LJ, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; }    \
-        else { LJCPot<COUL_PLAIN, LJ_STD, SW_LJ, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; }                \
+        /* ck == 1 is a CustomNonbondedForce: OpenMM's switch multiplies its WHOLE energy, Coulomb included */ \
+        else if (sw) { LJCPot<COUL_PLAIN, LJ_STD, SW_ALL, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; }      \
+        else { LJCPot<COUL_PLAIN, LJ_STD, SW_NONE, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; }             \
         break;                                                                                              \
     }                                                                                                       \
     case B2_PAIR_LJ_VIRIAL: { LJCPot<COUL_NONE, LJ_VIRIAL, SW_ALL, SWF_LINEAR, VAR_NONE, T> pot{p}; CALL_LJC; break; } \

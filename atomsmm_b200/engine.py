@@ -39,6 +39,7 @@ _SIGNATURES = {
     'b2_add_pair_force': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_double_p,
                           ctypes.c_int, ctypes.c_double, c_int_p],
     'b2_update_pair_force': [c_void, ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_double],
+    'b2_update_pair_particles': [c_void, ctypes.c_int, c_double_p, c_double_p, c_double_p],
     'b2_bind_pair_parameter': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int],
     'b2_add_bonded_force': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p, c_double_p, ctypes.c_int,
                             ctypes.c_int, c_double_p, ctypes.c_int, c_int_p],
@@ -72,6 +73,9 @@ _SIGNATURES = {
                        ctypes.POINTER(ctypes.c_longlong)],
     'b2_comm_unique_id': [ctypes.c_char_p],
     'b2_comm_init': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_char_p],
+    'b2_comm_export': [c_void, ctypes.c_char_p],
+    'b2_comm_import': [c_void, ctypes.c_int, ctypes.c_char_p],
+    'b2_comm_mode': [c_void, c_int_p, ctypes.POINTER(ctypes.c_longlong)],
     'b2_partition_ranges': [ctypes.c_int, c_int_p, ctypes.c_int, c_int_p],
     'b2_hilbert_index': [c_double_p, c_double_p, ctypes.POINTER(ctypes.c_ulonglong)],
     'b2_comm_info': [c_void, c_int_p, c_int_p, c_int_p, c_int_p, ctypes.POINTER(ctypes.c_longlong)],
@@ -320,13 +324,36 @@ class Context(object):
             self._check(self._lib.b2_comm_unique_id(ident), None)
         payload = broadcast_bytes(ident.raw if self._rank == 0 else None)
         self._call('b2_comm_init', self._nranks, self._rank, ctypes.create_string_buffer(payload, 128))
+        # peer-memory halo exchange: every rank maps its peers' position arrays (cudaIpc over NVLink)
+        self._exchange = 'nccl all-gather'
+        if os.environ.get('B2_DD_EXCHANGE', 'p2p').lower() != 'nccl':
+            record = ctypes.create_string_buffer(256)
+            self._call('b2_comm_export', record)
+            table = [None]*self._nranks
+            dist.all_gather_object(table, record.raw)
+            code = self._lib.b2_comm_import(self._handle, self._nranks, ctypes.create_string_buffer(b''.join(table), 256*self._nranks))
+            # all ranks must agree on the mode: one failure sends everybody to the NCCL path
+            verdicts = [None]*self._nranks
+            dist.all_gather_object(verdicts, int(code))
+            if all(v == 0 for v in verdicts):
+                self._exchange = 'peer-memory halo pull over NVLink'
+            else:
+                import warnings
+                message = self._lib.b2_last_error(self._handle) if code != 0 else None
+                self._call('b2_comm_import', -1, None)
+                warnings.warn('peer-memory exchange unavailable on some rank (%s, codes %r): using the NCCL all-gather path'
+                              % (message.decode() if message else 'ok here', verdicts))
 
     def comm_info(self):
         rank, nranks, lo, hi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         exchanges = ctypes.c_longlong()
         self._call('b2_comm_info', ctypes.byref(rank), ctypes.byref(nranks), ctypes.byref(lo), ctypes.byref(hi),
                    ctypes.byref(exchanges))
-        return dict(rank=rank.value, nranks=nranks.value, lo=lo.value, hi=hi.value, exchanges=exchanges.value)
+        p2p, halo = ctypes.c_int(), ctypes.c_longlong()
+        self._call('b2_comm_mode', ctypes.byref(p2p), ctypes.byref(halo))
+        return dict(rank=rank.value, nranks=nranks.value, lo=lo.value, hi=hi.value, exchanges=exchanges.value,
+                    exchange=getattr(self, '_exchange', 'none') if nranks.value > 1 else 'none',
+                    halo_atoms=halo.value)
 
     # -- description -> C ABI ----------------------------------------------------------------------
     def _describe(self):
@@ -349,15 +376,7 @@ class Context(object):
                 if force.getNumParticles() != n:
                     raise mm.OpenMMException('CustomNonbondedForce must have exactly as many particles as the System')
                 family, cutoff, params, info = lowering.classify_pair_force(force, self._parameters)
-                table = mm.value_columns(force._particles, 0).reshape(n, -1)
-                if table.shape[1] == 2:
-                    # (sigma, epsilon) only; with an interaction group the charge column carries the
-                    # +1/-1 set labels the soft-core kernel uses to keep only unlike pairs
-                    labels = np.zeros(n)
-                    if info.get('partition') is not None:
-                        labels[:] = -1.0
-                        labels[info['partition']] = 1.0
-                    table = np.concatenate([labels[:, None], table], axis=1)
+                table = self._custom_table(force, info)
                 exclusions = self._merge_exclusions(exclusions, _pair_keys(mm.index_columns(force._exclusions, 2), n))
                 set_id = self._param_set(table[:, 0], table[:, 1], table[:, 2])
                 econst = 0.0
@@ -463,10 +482,37 @@ class Context(object):
         return lowering.long_range_correction(classes, counts,
                                               lambda r, s, e: 24*e*(2*(s/r)**12 - (s/r)**6), cutoff, rs, volume)
 
-    def _describe_nonbonded(self, force, exclusions, volume):
-        """openmm.NonbondedForce: pair part + exception pairs (+ reciprocal space: not yet)."""
+    def _nonbonded_params(self, force):
+        """(kernel parameter block, PME request or None) of an openmm.NonbondedForce."""
         NB = mm.NonbondedForce
         method = force.getNonbondedMethod()
+        kc = 138.935456
+        cutoff = force.getCutoffDistance().value_in_md_units()
+        use_switch = force.getUseSwitchingFunction()
+        rswitch = force.getSwitchingDistance().value_in_md_units()
+        if method in (NB.NoCutoff, NB.CutoffNonPeriodic):
+            raise lowering.UnsupportedDescription('NonbondedForce needs a periodic cutoff method on this engine')
+        if method == NB.CutoffPeriodic:
+            es = force.getReactionFieldDielectric()
+            krf = (es - 1)/((2*es + 1)*cutoff**3)
+            crf = 3*es/((2*es + 1)*cutoff)
+            return [kc, 2.0, krf, crf, 0.0, float(use_switch), rswitch, cutoff], None
+        if method != NB.PME:
+            raise lowering.UnsupportedDescription('only PME is implemented for reciprocal space (not Ewald / LJPME)')
+        a, nx, ny, nz = force._pme
+        tol = force.getEwaldErrorTolerance()
+        if a != 0.0:
+            alpha, grid = a, [nx, ny, nz]
+        else:
+            # OpenMM's rule (SURVEY A8); no rounding to FFT-friendly sizes, like the Reference platform
+            alpha = math.sqrt(-math.log(2*tol))/cutoff
+            grid = [max(6, int(math.ceil(2*alpha*L/(3*tol**0.2)))) for L in self._box]
+        rgroup = force.getReciprocalSpaceForceGroup()
+        return [kc, 3.0, 0.0, 0.0, alpha, float(use_switch), rswitch, cutoff], \
+            (force.getForceGroup() if rgroup < 0 else rgroup, alpha, grid)
+
+    def _describe_nonbonded(self, force, exclusions, volume):
+        """openmm.NonbondedForce: pair part + exception pairs + reciprocal space (PME)."""
         n = self._n
         group = force.getForceGroup()
         table = mm.value_columns(force._particles, 0).reshape(n, 3)
@@ -474,28 +520,10 @@ class Context(object):
         cutoff = force.getCutoffDistance().value_in_md_units()
         use_switch = force.getUseSwitchingFunction()
         rswitch = force.getSwitchingDistance().value_in_md_units()
-        alpha = 0.0
-        if method in (NB.NoCutoff, NB.CutoffNonPeriodic):
-            raise lowering.UnsupportedDescription('NonbondedForce needs a periodic cutoff method on this engine')
-        if method == NB.CutoffPeriodic:
-            es = force.getReactionFieldDielectric()
-            krf = (es - 1)/((2*es + 1)*cutoff**3)
-            crf = 3*es/((2*es + 1)*cutoff)
-            params = [kc, 2.0, krf, crf, 0.0, float(use_switch), rswitch, cutoff]
-        else:
-            if method != NB.PME:
-                raise lowering.UnsupportedDescription('only PME is implemented for reciprocal space (not Ewald / LJPME)')
-            a, nx, ny, nz = force._pme
-            tol = force.getEwaldErrorTolerance()
-            if a != 0.0:
-                alpha, grid = a, [nx, ny, nz]
-            else:
-                # OpenMM's rule; no rounding to FFT-friendly sizes, like the Reference platform
-                alpha = math.sqrt(-math.log(2*tol))/cutoff
-                grid = [max(6, int(math.ceil(2*alpha*L/(3*tol**0.2)))) for L in self._box]
-            params = [kc, 3.0, 0.0, 0.0, alpha, float(use_switch), rswitch, cutoff]
-            rgroup = force.getReciprocalSpaceForceGroup()
-            self._pme_request = (group if rgroup < 0 else rgroup, alpha, grid)
+        params, pme = self._nonbonded_params(force)
+        alpha = params[4]
+        if pme is not None:
+            self._pme_request = pme
         exc_atoms = mm.index_columns(force._exceptions, 2)
         exc_values = mm.value_columns(force._exceptions, 2).reshape(len(exc_atoms), 3)
         exclusions = self._merge_exclusions(exclusions, _pair_keys(exc_atoms, n))
@@ -614,14 +642,54 @@ class Context(object):
         self._call('b2_run', steps)
         self._time += steps*self._integrator._dt
 
+    def _custom_table(self, force, info):
+        """Per-particle (charge, sigma, epsilon) table of a CustomNonbondedForce as the engine stores it."""
+        n = self._n
+        table = mm.value_columns(force._particles, 0).reshape(n, -1)
+        if table.shape[1] == 2:
+            # (sigma, epsilon) only; with an interaction group the charge column carries the
+            # +1/-1 set labels the soft-core kernel uses to keep only unlike pairs
+            labels = np.zeros(n)
+            if info.get('partition') is not None:
+                labels[:] = -1.0
+                labels[info['partition']] = 1.0
+            table = np.concatenate([labels[:, None], table], axis=1)
+        return table
+
+    def _pair_description(self, force):
+        """(params, energy constant, particle table) of a pair force from its CURRENT description."""
+        volume = float(np.prod(self._box))
+        if isinstance(force, mm.NonbondedForce):
+            params, pme = self._nonbonded_params(force)
+            if pme is not None:
+                raise lowering.UnsupportedDescription('updateParametersInContext of a PME NonbondedForce is not supported '
+                                                      '(self energy and exception corrections depend on the charges)')
+            table = mm.value_columns(force._particles, 0).reshape(self._n, 3)
+            econst = 0.0
+            if force.getUseDispersionCorrection():
+                cutoff = force.getCutoffDistance().value_in_md_units()
+                rs = force.getSwitchingDistance().value_in_md_units() if force.getUseSwitchingFunction() else None
+                classes, counts = self._classes(table[:, 1], table[:, 2])
+                econst = lowering.long_range_correction(
+                    classes, counts, lambda r, s, e: 4*e*((s/r)**12 - (s/r)**6), cutoff, rs, volume)
+            return params, econst, table
+        family, cutoff, params, info = lowering.classify_pair_force(force, self._parameters)
+        table = self._custom_table(force, info)
+        econst = self._custom_lrc(force, family, params, table, cutoff, volume) if force.getUseLongRangeCorrection() else 0.0
+        return params, econst, table
+
     def _parameters_changed(self, force):
+        """Force.updateParametersInContext: global parameters, the long-range correction and the
+        per-particle table of a pair force are re-read from the description (NonbondedForce
+        exceptions and explicit-list forces cannot be updated in a live context)."""
         entry = self._pair_handles.get(id(force))
         if entry is None:
             raise lowering.UnsupportedDescription('updateParametersInContext is only supported for pair forces')
-        handle, info, _ = entry
-        family, cutoff, params, _ = lowering.classify_pair_force(force, self._parameters)
+        handle = entry[0]
+        params, econst, table = self._pair_description(force)
         p = np.array(params, dtype=np.float64)
-        self._call('b2_update_pair_force', handle, _dptr(p), len(p), 0.0)
+        self._call('b2_update_pair_force', handle, _dptr(p), len(p), float(econst))
+        self._call('b2_update_pair_particles', handle, _dptr(table[:, 0]), _dptr(table[:, 1]), _dptr(table[:, 2]))
 
     # -- public API --------------------------------------------------------------------------------
     def getSystem(self):
@@ -653,9 +721,9 @@ class Context(object):
         for handle, info, force in self._pair_handles.values():
             if hasattr(force, 'getNumGlobalParameters') and any(
                     force.getGlobalParameterName(k) == name for k in range(force.getNumGlobalParameters())):
-                family, cutoff, params, _ = lowering.classify_pair_force(force, self._parameters)
+                params, econst, _ = self._pair_description(force)
                 p = np.array(params, dtype=np.float64)
-                self._call('b2_update_pair_force', handle, _dptr(p), len(p), 0.0)
+                self._call('b2_update_pair_force', handle, _dptr(p), len(p), float(econst))
         if self._program is not None and name in self._program.global_names:
             self._set_global(name, self._parameters[name])
 

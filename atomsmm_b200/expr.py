@@ -311,8 +311,31 @@ class Bytecode(object):
             return len(self.consts) - 1
 
 
-def compile_ast(node, resolve, bc):
-    """Append RPN code for ``node`` to ``bc``.  ``resolve(name)`` -> (op, arg) for a variable."""
+VM_STACK = 24      # B2_VM_STACK of csrc/program.h: evaluation stack of the device VM
+
+
+def stack_depth(node):
+    """Largest number of values the RPN code of ``node`` keeps on the VM stack."""
+    kind = node[0]
+    if kind in ('num', 'var'):
+        return 1
+    if kind in ('add', 'sub', 'mul', 'div'):
+        return max(stack_depth(node[1]), 1 + stack_depth(node[2]))
+    if kind == 'neg':
+        return stack_depth(node[1])
+    if kind == 'pow':
+        return max(stack_depth(node[1]), 1 + stack_depth(node[2]))
+    if kind == 'call':
+        return max([1] + [k + stack_depth(a) for k, a in enumerate(node[2])])
+    raise ParseError('bad node %r' % (node,))
+
+
+def compile_ast(node, resolve, bc, _root=True):
+    """Append RPN code for ``node`` to ``bc``.  ``resolve(name)`` -> (op, arg) for a variable.
+    An expression deeper than the device VM's stack is refused here (never a silent overflow)."""
+    if _root and stack_depth(node) > VM_STACK:
+        raise ParseError('expression needs an evaluation stack of %d values; the device VM has %d'
+                         % (stack_depth(node), VM_STACK))
     kind = node[0]
     if kind == 'num':
         bc.emit('PUSHC', bc.const(node[1]))
@@ -320,25 +343,25 @@ def compile_ast(node, resolve, bc):
         op, arg = resolve(node[1])
         bc.emit(op, arg)
     elif kind in ('add', 'sub', 'mul', 'div'):
-        compile_ast(node[1], resolve, bc)
-        compile_ast(node[2], resolve, bc)
+        compile_ast(node[1], resolve, bc, False)
+        compile_ast(node[2], resolve, bc, False)
         bc.emit(kind.upper())
     elif kind == 'neg':
-        compile_ast(node[1], resolve, bc)
+        compile_ast(node[1], resolve, bc, False)
         bc.emit('NEG')
     elif kind == 'pow':
-        compile_ast(node[1], resolve, bc)
+        compile_ast(node[1], resolve, bc, False)
         exponent = node[2]
         if exponent[0] == 'neg' and exponent[1][0] == 'num':
             exponent = ('num', -exponent[1][1])
         if exponent[0] == 'num' and float(exponent[1]).is_integer() and abs(exponent[1]) <= 64:
             bc.emit('POWI', int(exponent[1]))
         else:
-            compile_ast(exponent, resolve, bc)
+            compile_ast(exponent, resolve, bc, False)
             bc.emit('POW')
     elif kind == 'call':
         for a in node[2]:
-            compile_ast(a, resolve, bc)
+            compile_ast(a, resolve, bc, False)
         bc.emit(_CALL_OPS[node[1]])
     else:
         raise ParseError('bad node %r' % (node,))

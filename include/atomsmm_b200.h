@@ -115,6 +115,12 @@ B2_API int b2_add_pair_force(b2_context* ctx, int family, int group, int param_s
 /* updateParametersInContext / Context.setParameter for a pair force */
 B2_API int b2_update_pair_force(b2_context* ctx, int handle, const double* params, int nparams,
                          double energy_constant);
+/* Force.updateParametersInContext after setParticleParameters (openmm API used by the reference at
+ * systems.py reset_coulomb_scaling_factor-style rescaling and by user scripts): replaces the
+ * per-particle (charge, sigma, epsilon) table of ONE pair force; host arrays of n values each, caller's
+ * atom order.  A parameter set shared with other forces is split so that they keep their values. */
+B2_API int b2_update_pair_particles(b2_context* ctx, int handle, const double* charge, const double* sigma,
+                             const double* epsilon);
 /* A context parameter that the integrator itself moves (AFED extended variables,
  * integrators.py:670-744: `lambda <- lambda + 0.5*dt*v_lambda` is a ComputeGlobal on a context
  * parameter): from now on parameter `param` of pair force `handle` (1 = lambda_vdw, 2 = lambda_coul of
@@ -219,6 +225,20 @@ B2_API int b2_partition_ranges(int n, const int* molecule_sorted, int nranks, in
  * orders molecules; consecutive indices are face-adjacent cells, so runs of consecutive atoms -- the
  * 8-atom i-groups, the molecule chunks, the ranks' ownership ranges -- are spatially compact. */
 B2_API int b2_hilbert_index(const double position[3], const double box[3], unsigned long long* out_key);
+/* Peer-memory halo exchange over NVLink / NVSwitch (the default when the GPUs of the node can map each
+ * other's memory).  After b2_comm_init every rank exports a 256-byte record (cudaIpc handles of its
+ * position array and of its signal block), the host side all-gathers the records (rank order) and every
+ * rank imports the table.  From then on the ranks keep only their HALO current: before each pair-force
+ * evaluation a rank tests the skin criterion on its own atoms, posts the verdict to its peers and pulls
+ * the positions of the groups its last neighbour-list build saw (or of everybody, when any rank wants a
+ * rebuild) directly out of the owners' memory; sums go through the peers' signal blocks.  No library
+ * collective is left in the step graph.  If b2_comm_import fails (no peer access), the context stays in
+ * the NCCL mode: full replicas, grouped ncclBroadcast all-gather, ncclAllReduce; b2_comm_import(ctx, -1, NULL)
+ * puts a rank back into that mode (all ranks must run the same mode).
+ * b2_comm_mode: peer_memory = 1 in the peer-memory mode; halo_atoms = atoms pulled per exchange. */
+B2_API int b2_comm_export(b2_context* ctx, char out256[256]);
+B2_API int b2_comm_import(b2_context* ctx, int nranks, const char* all256);
+B2_API int b2_comm_mode(b2_context* ctx, int* peer_memory, long long* halo_atoms);
 /* ownership range [lo, hi) of this rank in the engine's spatial order, and the number of
  * position exchanges performed so far */
 B2_API int b2_comm_info(b2_context* ctx, int* rank, int* nranks, int* lo, int* hi, long long* exchanges);

@@ -299,3 +299,55 @@ class DistributedExecutor(Executor):
 
     def full_state(self):
         return self.gather(self.x.copy()), self.gather(self.v.copy())
+
+
+class HaloExecutor(DistributedExecutor):
+    """The PEER-MEMORY protocol of csrc/dist.cu + csrc/dd.cuh (halo pull): before a pair-force evaluation
+    every rank tests the skin criterion on its OWN atoms, the verdicts are OR-ed over the ranks, and then
+    either everybody refreshes every foreign atom and rebuilds (new reference positions, new halo = the
+    foreign atoms within list radius of an owned atom), or each rank refreshes ONLY its halo; all other
+    foreign atoms keep whatever stale position they had.  The trajectories must still equal the
+    single-process ones: a needed atom left stale would show up as a force error."""
+
+    def __init__(self, *args, rlist=1.1, skin=0.1, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.rlist, self.skin = rlist, skin
+        self.xref = None
+        self.halo = np.zeros(self.n, bool)
+        self.rebuilds = 0
+        self.halo_sizes = []
+
+    def _build(self):
+        own = np.arange(self.lo, self.hi)
+        self.xref = self.x[own].copy()
+        d = self.x[:, None, :] - self.x[None, own, :]
+        d -= self.box*np.rint(d/self.box)
+        near = (np.sum(d*d, axis=2) < self.rlist**2).any(axis=1)
+        near[own] = False
+        self.halo = near
+        self.rebuilds += 1
+        self.halo_sizes.append(int(near.sum()))
+
+    def ensure(self, mask, slot):
+        cached = self.forces.get(slot)
+        if cached is not None and cached[0] == self.version:
+            return
+        if (mask & self.pair_mask) and self.synced != self.version:
+            own = slice(self.lo, self.hi)
+            moved = 1.0 if self.xref is None else float(
+                (np.sum((self.x[own] - self.xref)**2, axis=1) > (0.5*self.skin)**2).any())
+            verdict = self.torch.tensor([moved], dtype=self.torch.float64)
+            self.dist.all_reduce(verdict, op=self.dist.ReduceOp.MAX)
+            fresh = self.gather(self.x.copy())            # what the owners hold; this rank may read only parts of it
+            if float(verdict) > 0:
+                self.x = fresh
+                self._build()
+            else:
+                self.x[self.halo] = fresh[self.halo]
+            self.synced = self.version
+            self.exchanges += 1
+        Executor.ensure(self, mask, slot)
+
+    def full_state(self):
+        self.synced = -1
+        return super().full_state()

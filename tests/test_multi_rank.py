@@ -115,6 +115,83 @@ def _protocol_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
+def _halo_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    dist = _init(rank, world, port, 'gloo')
+    try:
+        import atomsmm_b200 as atomsmm
+        from atomsmm_b200 import mm, unit
+        from lowered_executor import Executor, HaloExecutor
+        import systems
+        import test_lowered_programs as T
+        # the 1 536-atom water box doubled along x (5 x 2.5 x 2.5 nm): each rank owns one copy, and with
+        # a list radius of 1.1 nm a slab of the other copy is NOT in its halo and goes stale
+        respa, pdb = systems.respa_water()
+        base = systems.positions_of(pdb)
+        n = respa.getNumParticles()
+        double = mm.System()
+        double._masses = list(respa._masses)*2
+        double.setDefaultPeriodicBoxVectors(mm.Vec3(5.0, 0, 0), mm.Vec3(0, 2.5, 0), mm.Vec3(0, 0, 2.5))
+        import copy
+        for force in respa.getForces():
+            new = copy.deepcopy(force)
+            for name, nindex in (('_particles', 0), ('_exceptions', 2), ('_exclusions', 2), ('_bonds', 2), ('_angles', 3),
+                                 ('_torsions', 4)):
+                rows = getattr(force, name, None)
+                if rows is None or len(rows) == 0:
+                    continue
+                nested = isinstance(force, (mm.CustomBondForce, mm.CustomAngleForce))
+                idx = mm.index_columns(rows, nindex).astype(np.int64)
+                val = mm.value_columns(rows, nindex)
+                idx2 = np.concatenate([idx, idx + n]) if nindex else None
+                setattr(new, name, mm.PackedRows(idx2, np.concatenate([val, val]), nested=nested))
+            double.addForce(new)
+        rng = np.random.default_rng(3)
+        pos = np.concatenate([base, base + np.array([2.5, 0, 0])]) + rng.uniform(-0.002, 0.002, size=(2*n, 3))
+        mass = np.array(double._masses)
+        vel = rng.standard_normal((2*n, 3))*np.sqrt(8.314472471220217e-3*300/mass)[:, None]
+        dof = atomsmm.countDegreesOfFreedom(double)
+
+        def factory():
+            nh = atomsmm.NoseHooverPropagator(300*T.K, dof, 100*T.fs)
+            return atomsmm.TrotterSuzukiPropagator(atomsmm.RespaPropagator([2, 2, 1]),
+                                                   atomsmm.SuzukiYoshidaPropagator(nh, 3)).integrator(4*T.fs)
+        mask = 0b111
+        # a tight skin so that the three steps contain both kinds of exchange (halo-only and rebuild)
+        shared = HaloExecutor(double, factory(), pos, vel, dist, pair_mask=0b110, group_mask=mask, rlist=1.04, skin=0.04)
+        single = Executor(double, factory(), pos, vel, group_mask=mask)
+        shared.step(3)
+        single.step(3)
+        x, v = shared.full_state()
+        assert shared.hi - shared.lo == n
+        assert np.max(np.abs(x - single.x)) < 1e-12 and np.max(np.abs(v - single.v)) < 1e-10
+        assert shared.exchanges == 2*3 and 1 <= shared.rebuilds < shared.exchanges, (shared.exchanges, shared.rebuilds)
+        assert all(0 < h < n for h in shared.halo_sizes), shared.halo_sizes      # a strict subset of the other copy
+        out.put((rank, 'ok'))
+    except Exception as error:    # pragma: no cover
+        import traceback
+        out.put((rank, traceback.format_exc() + repr(error)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_exchange_protocol_world_size_2_gloo():
+    """The peer-memory protocol (owned-only skin test, OR-ed verdict, halo-only refresh between rebuilds, stale
+    positions everywhere else) on two gloo ranks reproduces the single-process trajectory."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_halo_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, 'ok'), (1, 'ok')], results
+
+
 def test_domain_decomposition_protocol_world_size_2_gloo():
     """The exchange / ownership / all-reduce protocol of csrc/dist.cu, executed on the CPU by two gloo
     ranks on the lowered RESPA + Nose-Hoover program, reproduces the single-process result."""
