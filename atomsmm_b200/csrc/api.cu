@@ -737,7 +737,26 @@ extern "C" int b2_eval(b2_context* ctx, uint32_t group_mask, int flags, double* 
                        double* virial_host) {
     if (!ctx || !ctx->have_positions) return b2_fail(ctx, B2_ERR_STATE, "positions have not been set");
     const int n = ctx->n, T = 256;
-    if ((flags & B2_EVAL_FORCES) && forces_dev) {
+    if ((flags & B2_EVAL_FORCES) && (flags & B2_EVAL_DOUBLE) && forces_dev) {
+        // report cadence: every contribution evaluated and accumulated in float64 (engine order in scratch3)
+        double* f64 = ctx->scratch3;
+        B2_CUDA(cudaMemsetAsync(f64, 0, sizeof(double)*3*n, ctx->stream));
+        bool any_pair = false;
+        for (const PairForce& pf : ctx->pair_forces)
+            if (group_mask & (1u << pf.group)) any_pair = true;
+        if (any_pair) {
+            if (!ctx->p2p) B2_TRY(dist_sync_positions(ctx));
+            B2_TRY(nl_prepare(ctx, false));
+        }
+        for (const PairForce& pf : ctx->pair_forces)
+            if (group_mask & (1u << pf.group)) B2_TRY(pair_eval_forces64(ctx, pf, f64));
+        B2_TRY(dist_before_move(ctx));
+        B2_TRY(bonded_eval_forces64(ctx, group_mask, f64));
+        for (PmeForce& pm : ctx->pme_forces)
+            if (group_mask & (1u << pm.group)) B2_TRY(pme_eval(ctx, pm, nullptr, nullptr, f64));
+        B2_TRY(dist_gather3(ctx, f64));
+        B2_TRY(state_permute_to_user(ctx, f64, forces_dev));
+    } else if ((flags & B2_EVAL_FORCES) && forces_dev) {
         int slot = 32;
         bool scratch = true;
         if (group_mask == 0xffffffffu) scratch = false;

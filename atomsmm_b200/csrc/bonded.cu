@@ -25,6 +25,16 @@ __global__ void k_bonded(BondArgs a, int arity, const double* x, float4* out, do
     if (ENERGY) block_accumulate(e, w, acc);
 }
 
+__global__ void k_bonded64(BondArgs a, int arity, const double* x, double* out) {
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= a.nterms) return;
+    double e = 0, w = 0;
+    const GlobalGeo64 geo{x, out};
+    if (arity == 2) term_bond2<true, false>(a, t, geo, e, w);
+    else if (arity == 3) term_angle<true, false>(a, t, geo, e);
+    else term_torsion<true, false>(a, t, geo, e);
+}
+
 __global__ void k_bonded_batch(BondBatch b, const double* x, float4* out) {
     const int t = blockIdx.x*blockDim.x + threadIdx.x;
     if (t >= b.first[b.count]) return;
@@ -92,4 +102,16 @@ int bonded_eval(b2_context* ctx, const BondedForce& bf, float4* out, bool want_f
     if (want_force && want_energy) return launch<true, true>(ctx, bf, a, out, acc);
     if (want_force) return launch<true, false>(ctx, bf, a, out, acc);
     return launch<false, true>(ctx, bf, a, out, acc);
+}
+
+// float64 forces of every explicit-list force whose group is in `mask`, accumulated into out[n][3]
+int bonded_eval_forces64(b2_context* ctx, uint32_t mask, double* out) {
+    for (const BondedForce& bf : ctx->bonded_forces) {
+        if (!(mask & (1u << bf.group)) || bf.nterms == 0) continue;
+        if ((bf.family == B2_BOND_CUSTOM || bf.family == B2_ANGLE_CUSTOM) && bf.ncode_de == 0) continue;
+        const int T = 128;
+        k_bonded64<<<(bf.nterms + T - 1)/T, T, 0, ctx->stream>>>(bonded_make_args(ctx, bf), bf.arity, ctx->x, out);
+        B2_LAUNCH_CHECK();
+    }
+    return B2_OK;
 }

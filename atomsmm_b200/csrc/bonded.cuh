@@ -35,6 +35,18 @@ struct GlobalGeo {
     }
 };
 
+// float64 force buffer [n][3] (report cadence)
+struct GlobalGeo64 {
+    const double* x;
+    double* out;
+    __device__ __forceinline__ double pos(int i, int k) const { return x[3*i+k]; }
+    __device__ __forceinline__ void add(int i, double fx, double fy, double fz) const {
+        atomicAdd(&out[3*i], fx);
+        atomicAdd(&out[3*i+1], fy);
+        atomicAdd(&out[3*i+2], fz);
+    }
+};
+
 // Forces are accumulated in 64-bit fixed point (2^-32 kJ/mol/nm resolution): integer addition is
 // associative, so the sum does not depend on the order in which threads arrive -- bit-reproducible.
 #define B2_FIXED_SCALE 4294967296.0

@@ -249,7 +249,9 @@ int pair_count_set(b2_context* ctx, const PairForce& pf, long long* count, unsig
 int bonded_eval(b2_context* ctx, const BondedForce& bf, float4* out, bool want_force, bool want_energy);
 int bonded_eval_forces(b2_context* ctx, uint32_t mask, float4* out);
 int pme_setup(b2_context* ctx, PmeForce& pf);
-int pme_eval(b2_context* ctx, PmeForce& pf, float4* out, double* acc);
+int pme_eval(b2_context* ctx, PmeForce& pf, float4* out, double* acc, double* out64 = nullptr);
+int pair_eval_forces64(b2_context* ctx, const PairForce& pf, double* out);
+int bonded_eval_forces64(b2_context* ctx, uint32_t mask, double* out);
 void pme_release(PmeForce& pf);
 int dist_partition(b2_context* ctx);
 int dist_sync_positions(b2_context* ctx);           // every rank ends up with the complete position array

@@ -337,6 +337,47 @@ __global__ void __launch_bounds__(32*WPB) k_pair_energy(int n, int g_lo, int ngr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp64 force kernel (report cadence: State forces with Precision=double, e.g. the molecular virial
+// of computers.py:211-240, which contracts forces with positions and needs more than fp32)
+// ---------------------------------------------------------------------------------------------
+template <class POT>
+__global__ void __launch_bounds__(32*WPB) k_pair_force64(int n, int g_lo, int ngroups, const double* __restrict__ x,
+                                                        const double* __restrict__ pard,
+                                                        const int* __restrict__ entries,
+                                                        const int* __restrict__ counts, int cap, POT pot,
+                                                        double rc2, double bx, double by, double bz,
+                                                        double* __restrict__ out /* [n][3], accumulated */) {
+    const int warp = g_lo + ((blockIdx.x*blockDim.x + threadIdx.x) >> 5);
+    if (warp >= ngroups) return;
+    const int lane = threadIdx.x & 31;
+    const int il = lane >> 2, jj = lane & 3;
+    const int i = warp*B2_GROUP + il;
+    const int ic = min(i, n - 1);
+    const double xi = x[3*ic], yi = x[3*ic+1], zi = x[3*ic+2];
+    const double qi = pard[3*ic], si = pard[3*ic+1], ei = pard[3*ic+2];
+    const int cnt = counts[warp];
+    const int* __restrict__ base = entries + (size_t)warp*cap;
+    double fx = 0, fy = 0, fz = 0;
+    for (int k = jj; k < cnt; k += 4) {
+        const int en = base[k];
+        const int j = en & 0xffffff;
+        if (((unsigned)en >> (24 + il)) & 1u) continue;
+        double dx = xi - x[3*j], dy = yi - x[3*j+1], dz = zi - x[3*j+2];
+        dx -= bx*rint(dx/bx); dy -= by*rint(dy/by); dz -= bz*rint(dz/bz);
+        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        if (r2 < rc2) {
+            double rF, e, rinv2;
+            pot.template operator()<false>(r2, qi*pard[3*j], 0.5*(si + pard[3*j+1]), sqrt(ei*pard[3*j+2]), rF, e, rinv2);
+            const double fr = rF*rinv2;
+            fx += fr*dx; fy += fr*dy; fz += fr*dz;
+        }
+    }
+    fx += __shfl_xor_sync(FULL, fx, 1); fy += __shfl_xor_sync(FULL, fy, 1); fz += __shfl_xor_sync(FULL, fz, 1);
+    fx += __shfl_xor_sync(FULL, fx, 2); fy += __shfl_xor_sync(FULL, fy, 2); fz += __shfl_xor_sync(FULL, fz, 2);
+    if (jj == 0 && i < n) { out[3*i] += fx; out[3*i+1] += fy; out[3*i+2] += fz; }
+}
+
 // exact interacting pair set: i<j (caller numbering), r^2 < rc^2 in float64, not excluded
 __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
     z += 0x9e3779b97f4a7c15ull;
@@ -501,6 +542,27 @@ int pair_eval_energy(b2_context* ctx, const PairForce& pf, int group) {
     DISPATCH(double, B2_TRY((launch_energy<decltype(pot), false>(ctx, pf, pot, rc2, acc))),
              B2_TRY((launch_energy<decltype(pot), true>(ctx, pf, pot, rc2, acc))));
     (void)group;
+    return B2_OK;
+}
+
+template <class POT>
+static int launch_force64(b2_context* ctx, const PairForce& pf, POT pot, double rc2, double* out) {
+    const NList& L = ctx->lists[pf.list];
+    const int blocks = (ctx->g_hi - ctx->g_lo + WPB - 1)/WPB;
+    if (blocks == 0) return B2_OK;
+    k_pair_force64<POT><<<blocks, 32*WPB, 0, ctx->stream>>>(ctx->n, ctx->g_lo, ctx->g_hi, ctx->x, ctx->pard[pf.set], L.entries,
+                                                          L.counts, L.cap, pot, rc2, ctx->box[0], ctx->box[1], ctx->box[2],
+                                                          out);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+// float64 forces of one pair force accumulated into out[n][3] (engine order)
+int pair_eval_forces64(b2_context* ctx, const PairForce& pf, double* out) {
+    float rc2f;
+    PotParams<double> p = make_params<double>(ctx, pf, &rc2f);
+    const double rc = effective_cutoff(pf);
+    DISPATCH(double, B2_TRY(launch_force64(ctx, pf, pot, rc*rc, out)), B2_TRY(launch_force64(ctx, pf, pot, rc*rc, out)));
     return B2_OK;
 }
 

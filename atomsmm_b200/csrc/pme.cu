@@ -108,7 +108,7 @@ __global__ void k_pme_convolve(size_t total, int nzh, int nz, cufftDoubleComplex
 }
 
 __global__ void k_pme_gather(int n, const double* __restrict__ x, const double* __restrict__ pard, PmeGrid g,
-                             const double* __restrict__ C, float4* __restrict__ out) {
+                             const double* __restrict__ C, float4* __restrict__ out, double* __restrict__ out64) {
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double q = pard[3*i];
@@ -132,6 +132,12 @@ __global__ void k_pme_gather(int n, const double* __restrict__ x, const double* 
                 fz += v*tx[a]*ty[b]*dz[c];
             }
         }
+    }
+    if (out64) {
+        out64[3*i] -= q*fx*g.K[0]/g.box[0];
+        out64[3*i+1] -= q*fy*g.K[1]/g.box[1];
+        out64[3*i+2] -= q*fz*g.K[2]/g.box[2];
+        return;
     }
     float4 f = out[i];
     f.x -= (float)(q*fx*g.K[0]/g.box[0]);
@@ -204,7 +210,7 @@ int pme_setup(b2_context* ctx, PmeForce& pf) {
 }
 
 // adds reciprocal-space forces into `out` (if not null) and the reciprocal energy into *acc
-int pme_eval(b2_context* ctx, PmeForce& pf, float4* out, double* acc) {
+int pme_eval(b2_context* ctx, PmeForce& pf, float4* out, double* acc, double* out64) {
     const int n = ctx->n, T = 128;
     PmeGrid g;
     for (int d = 0; d < 3; d++) { g.K[d] = pf.K[d]; g.box[d] = ctx->box[d]; }
@@ -222,11 +228,11 @@ int pme_eval(b2_context* ctx, PmeForce& pf, float4* out, double* acc) {
     k_pme_convolve<<<blocks, 256, 0, ctx->stream>>>(half, nzh, nz, (cufftDoubleComplex*)pf.spectrum, pf.eterm, acc,
                                                      acc != nullptr);
     B2_LAUNCH_CHECK();
-    if (out) {
+    if (out || out64) {
         if (cufftExecZ2D((cufftHandle)pf.plan_inv, (cufftDoubleComplex*)pf.spectrum, pf.grid) != CUFFT_SUCCESS)
             return b2_fail(ctx, B2_ERR_CUDA, "cufftExecZ2D failed");
         ctx->counters[0]++;
-        k_pme_gather<<<(n + T - 1)/T, T, 0, ctx->stream>>>(n, ctx->x, ctx->pard[pf.set], g, pf.grid, out);
+        k_pme_gather<<<(n + T - 1)/T, T, 0, ctx->stream>>>(n, ctx->x, ctx->pard[pf.set], g, pf.grid, out, out64);
         B2_LAUNCH_CHECK();
     }
     return B2_OK;

@@ -242,7 +242,9 @@ class State(object):
 class Context(object):
     """Execution context on one B200.  ``properties``: 'DeviceIndex' (default 0 or LOCAL_RANK),
     'Skin' (neighbour-list skin in nm, default 0.1), 'FastPaths' ('false' routes every per-DOF step
-    through the generic VM), 'DomainDecomposition' ('true': the ranks of the initialised
+    through the generic VM), 'Precision' ('mixed', the default: State forces are the fp32-tile forces the
+    integrator uses; 'double': getState evaluates and accumulates every force contribution in float64 --
+    report cadence only, time stepping is always mixed precision), 'DomainDecomposition' ('true': the ranks of the initialised
     torch.distributed world integrate ONE system together, each owning a spatial range of whole
     molecules; every rank must make the same calls with the same arguments)."""
 
@@ -267,6 +269,10 @@ class Context(object):
         self._call('b2_set_stream', c_void(self._stream.cuda_stream))
         self._skin = float(properties.get('Skin', 0.1))
         self._fast = str(properties.get('FastPaths', 'true')).lower() != 'false'
+        precision = str(properties.get('Precision', 'mixed')).lower()
+        if precision not in ('mixed', 'double'):
+            raise mm.OpenMMException("Precision must be 'mixed' or 'double' on this platform")
+        self._double_forces = precision == 'double'
         self._call('b2_set_skin', self._skin)
         box = _md(system.getDefaultPeriodicBoxVectors())
         self._box = np.array([box[0][0], box[1][1], box[2][2]], dtype=np.float64)
@@ -827,7 +833,8 @@ class Context(object):
                     fields['_velocities'] = vel
                 if getEnergy:
                     fields['_kinetic'] = 0.5*float(np.sum(self._masses[:, None]*vel*vel))
-            flags = (1 if getForces else 0) | (2 if (getEnergy or getParameterDerivatives) else 0)
+            flags = (1 if getForces else 0) | (2 if (getEnergy or getParameterDerivatives) else 0) | \
+                (4 if (getForces and self._double_forces) else 0)
             if flags:
                 energy, virial = ctypes.c_double(), ctypes.c_double()
                 self._call('b2_eval', ctypes.c_uint32(mask), flags,

@@ -83,7 +83,9 @@ enum {
 };
 
 /* flags for b2_eval */
-enum { B2_EVAL_FORCES = 1, B2_EVAL_ENERGY = 2 };
+enum { B2_EVAL_FORCES = 1, B2_EVAL_ENERGY = 2,
+       B2_EVAL_DOUBLE = 4   /* with B2_EVAL_FORCES: every contribution evaluated and accumulated in float64
+                               (OpenMM's Precision=double for State forces; report cadence only) */ };
 
 /* ---- life cycle ---------------------------------------------------------------------------- */
 /* replaces openmm.Context construction (computers.py:69, utils.py:155,226) */

@@ -33,17 +33,27 @@ def test_pressure_with_bath_temperature(cuda_platform, case, goldens):
     # reference: tests/test_computers.py:22-37 and 59-74
     system, pdb = read_system(case)
     computer = atomsmm.PressureComputer(system, pdb.topology, cuda_platform, temperature=300*unit.kelvin)
-    context = mm.Context(system, mm.CustomIntegrator(0), cuda_platform)
+    # the reference takes the forces from the Reference platform (float64): State forces at report cadence are
+    # evaluated in float64 with Precision=double (time stepping keeps its fp32 tiles)
+    context = mm.Context(system, mm.CustomIntegrator(0), cuda_platform, {'Precision': 'double'})
     context.setPositions(pdb.positions)
     state = context.getState(getPositions=True, getVelocities=True, getForces=True)
     computer.import_configuration(state)
     assert value(computer.get_atomic_virial()) == pytest.approx(goldens[0])
-    # small difference of large terms: 3e-6 instead of 1e-6
+    # P_atomic = (3NkT + W)/3V is a small difference of large terms (water: +11 493 - 11 662): the 2e-8
+    # deviation of W that OpenMM's own NUMERICAL long-range-correction quadrature leaves in the golden
+    # (the float64 oracle shows the same 1.5e-6) is amplified 75x.  Not a precision issue
+    # of the engine, hence the one relaxed tolerance here.
     assert value(computer.get_atomic_pressure()) == pytest.approx(goldens[1], rel=3e-6)
-    # the molecular virial contracts the fp32 forces of the simulated system with positions
-    assert value(computer.get_molecular_virial(state.getForces())) == pytest.approx(goldens[2], rel=2e-6)
-    # P_mol = (3 N_mol kT + W_mol)/3V amplifies the relative error of W_mol ~3.4x (water)
-    assert value(computer.get_molecular_pressure(state.getForces())) == pytest.approx(goldens[3], rel=1e-5)
+    # reference tolerances (tests/test_computers.py:34-37, 71-74: pytest.approx default 1e-6)
+    assert value(computer.get_molecular_virial(state.getForces())) == pytest.approx(goldens[2])
+    assert value(computer.get_molecular_pressure(state.getForces())) == pytest.approx(goldens[3])
+    # the mixed-precision State forces (what the integrator uses) agree with the float64 ones to fp32 accuracy
+    mixed = mm.Context(system, mm.CustomIntegrator(0), cuda_platform)
+    mixed.setPositions(pdb.positions)
+    f32 = mixed.getState(getForces=True).getForces(asNumpy=True).value_in_unit(unit.kilojoules_per_mole/unit.nanometer)
+    f64 = state.getForces(asNumpy=True).value_in_unit(unit.kilojoules_per_mole/unit.nanometer)
+    assert np.sqrt(np.sum((f32 - f64)**2)/np.sum(f64**2)) < 1e-5
 
 
 def test_pressure_with_kinetic_temperature(cuda_platform):
