@@ -139,7 +139,7 @@ extern "C" int b2_destroy(b2_context* ctx) {
     cudaStreamSynchronize(ctx->stream);
     program_release(ctx);
     dist_release(ctx);
-    cudaFree(ctx->x); cudaFree(ctx->v); cudaFree(ctx->xref); cudaFree(ctx->xsort);
+    cudaFree(ctx->x); cudaFree(ctx->v); cudaFree(ctx->xref); cudaFree(ctx->xsort); cudaFree(ctx->xq);
     for (int s = 0; s < B2_MAX_SETS; s++) { cudaFree(ctx->par[s]); cudaFree(ctx->pard[s]); }
     cudaFree(ctx->massd); cudaFree(ctx->invm); cudaFree(ctx->orig); cudaFree(ctx->inv); cudaFree(ctx->exmask);
     cudaFree(ctx->excl_ptr); cudaFree(ctx->excl_idx); cudaFree(ctx->scratch3);
@@ -152,6 +152,7 @@ extern "C" int b2_destroy(b2_context* ctx) {
     cudaFree(ctx->globals); cudaFree(ctx->sum_partial); cudaFree(ctx->rng_state);
     cudaFree(ctx->band_pairs); cudaFree(ctx->band_count); cudaFree(ctx->ticket);
     cudaFree(ctx->band_slot); cudaFree(ctx->band_acc); cudaFree(ctx->band_ticket);
+    cudaFree(ctx->mol_start); cudaFree(ctx->xbackup);
     cudaFree(ctx->chunk_start); cudaFree(ctx->chunk_term_ptr); cudaFree(ctx->chunk_terms);
     for (double* p : ctx->carry_tmp) cudaFree(p);
     cudaFree(ctx->order_tmp);
@@ -231,6 +232,7 @@ extern "C" int b2_set_particles(b2_context* ctx, int n, const double* mass, cons
     B2_CUDA(cudaMalloc(&ctx->v, sizeof(double)*3*n));
     B2_CUDA(cudaMalloc(&ctx->xref, sizeof(double)*3*n));
     B2_CUDA(cudaMalloc(&ctx->xsort, sizeof(double)*3*n));
+    B2_CUDA(cudaMalloc(&ctx->xq, sizeof(int4)*n));
     B2_CUDA(cudaMalloc(&ctx->scratch3, sizeof(double)*3*n));
     B2_CUDA(cudaMalloc(&ctx->massd, sizeof(double)*n));
     B2_CUDA(cudaMalloc(&ctx->invm, sizeof(float)*n));
@@ -588,6 +590,16 @@ static int upload_static(b2_context* ctx) {
     B2_CUDA(cudaMemcpy(ctx->massd, md.data(), sizeof(double)*n, cudaMemcpyHostToDevice));
     B2_CUDA(cudaMemcpy(ctx->invm, im.data(), sizeof(float)*n, cudaMemcpyHostToDevice));
     for (size_t k = 0; k < ctx->h_sets.size(); k++) B2_TRY(upload_param_set(ctx, (int)k));
+    // molecule table in the engine's order (molecules are contiguous): barostat moves, chunking
+    std::vector<int> mstart;
+    for (int s = 0; s < n; s++)
+        if (s == 0 || ctx->h_mol[ctx->h_orig[s]] != ctx->h_mol[ctx->h_orig[s-1]]) mstart.push_back(s);
+    ctx->nmol = (int)mstart.size();
+    mstart.push_back(n);
+    cudaFree(ctx->mol_start);
+    ctx->mol_start = nullptr;
+    B2_CUDA(cudaMalloc(&ctx->mol_start, sizeof(int)*mstart.size()));
+    B2_CUDA(cudaMemcpy(ctx->mol_start, mstart.data(), sizeof(int)*mstart.size(), cudaMemcpyHostToDevice));
     std::vector<unsigned long long> mask(n, 0ull);   // indexed by caller index first
     ctx->excl_span = 0;
     for (size_t k = 0; k + 1 < ctx->h_excl.size(); k += 2) {
@@ -917,12 +929,38 @@ extern "C" int b2_run(b2_context* ctx, int nsteps) {
     return program_run(ctx, nsteps);
 }
 
+void phase_mark(b2_context* ctx, int tag) {
+    if (!ctx->profiling) return;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, ctx->stream);
+    ctx->phase_events.push_back(e);
+    ctx->phase_tags.push_back(tag);
+}
+
+// milliseconds per phase (B2_PHASE_* order, 6 values) accumulated since profiling was switched on
+extern "C" int b2_get_phase_profile(b2_context* ctx, double out_ms[6]) {
+    if (!ctx || !out_ms) return B2_ERR_ARG;
+    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < B2_PHASE_COUNT; k++) out_ms[k] = 0;
+    for (size_t k = 0; k + 1 < ctx->phase_events.size(); k++) {
+        float t = 0;
+        B2_CUDA(cudaEventElapsedTime(&t, ctx->phase_events[k], ctx->phase_events[k+1]));
+        const int tag = ctx->phase_tags[k];
+        if (tag >= 0 && tag < B2_PHASE_COUNT) out_ms[tag] += t;
+    }
+    return B2_OK;
+}
+
 extern "C" int b2_set_profiling(b2_context* ctx, int on) {
     if (!ctx) return B2_ERR_ARG;
     B2_CUDA(cudaStreamSynchronize(ctx->stream));
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     ctx->prof_events.clear();
     ctx->prof_tags.clear();
+    for (cudaEvent_t e : ctx->phase_events) cudaEventDestroy(e);
+    ctx->phase_events.clear();
+    ctx->phase_tags.clear();
     ctx->profiling = on != 0;
     program_release(ctx);
     ctx->eager_steps = 0;

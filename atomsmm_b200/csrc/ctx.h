@@ -5,6 +5,7 @@
 // the caller's numbering):
 //
 //   x, v        double [n][3]   master state, never wrapped (molecules stay whole)
+//   xq          int4   [n]      x as 32-bit fixed-point fractions of the box, refreshed by the skin test
 //   xref        double [n][3]   positions at the last neighbour-list build (skin test)
 //   prel        float4 [n]      position relative to the centre of the atom's 8-atom group (list build)
 //   par[s]      float4 [n]      per parameter set: {charge, sigma/2, sqrt(epsilon), 0}
@@ -105,6 +106,7 @@ struct b2_context {
     int steps_since_order_check = 0;
     std::vector<int> h_orig;                      // sorted -> caller index
     double *x = nullptr, *v = nullptr, *xref = nullptr, *xsort = nullptr;
+    int4* xq = nullptr;                           // positions as 32-bit fixed-point fractions of the box (pair tiles)
     float4* par[B2_MAX_SETS] = {nullptr};
     double* pard[B2_MAX_SETS] = {nullptr};        // double [n][3]: charge, sigma, epsilon
     double* massd = nullptr;
@@ -170,6 +172,16 @@ struct b2_context {
     double* con_d2 = nullptr;                     // squared target distances
     double* xcon = nullptr;                       // [n][3] last constrained configuration
 
+    // ---- Monte Carlo barostat (barostat.cu) ------------------------------------------------------
+    bool baro_on = false;
+    double baro_pressure = 0, baro_kT = 0, baro_vscale = 0;     // kJ/mol/nm^3, kJ/mol, nm^3
+    int baro_frequency = 0, baro_steps = 0, baro_attempts = 0, baro_accepted = 0;
+    long long baro_total_attempts = 0, baro_total_accepted = 0;
+    unsigned long long baro_seed = 0, baro_counter = 0;
+    int nmol = 0;
+    int* mol_start = nullptr;                     // [nmol+1] first atom of every molecule, engine order
+    double* xbackup = nullptr;                    // positions before a trial move
+
     // ---- cutoff-band pairs settled in float64 (pair.cu) -----------------------------------
     int* band_pairs = nullptr;                    // [2 lanes][capacity] int2
     unsigned* band_count = nullptr;               // [2 lanes]
@@ -182,6 +194,8 @@ struct b2_context {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;         // start, stop, start, stop ...
     std::vector<int> prof_tags;                   // pair force handle per pair of events
+    std::vector<cudaEvent_t> phase_events;        // phase boundaries of the step (b2_get_phase_profile)
+    std::vector<int> phase_tags;                  // tag of the phase that STARTS at the event
 
     // ---- energies --------------------------------------------------------------------------
     double* d_energy = nullptr;  // [32] energy + [32] virial + [2] dE/dlambda + pad
@@ -207,6 +221,11 @@ struct b2_context {
     unsigned long long graph_entry_mask = 0, graph_exit_mask = 0;
     bool graph_entry_synced = true, graph_exit_synced = true;   // replicated positions consistent on all ranks
 };
+
+// position -> 32-bit fixed-point fraction of the box (scale = 2^32 / L); wraps like the periodic box
+#ifdef __CUDACC__
+__device__ __forceinline__ int b2_to_fixed(double x, double scale) { return (int)__double2ll_rn(x*scale); }
+#endif
 
 // ---- error helpers --------------------------------------------------------------------------
 int b2_fail(b2_context* ctx, int code, const char* fmt, ...);
@@ -272,6 +291,12 @@ int con_snapshot(b2_context* ctx);
 int con_positions(b2_context* ctx);
 int con_velocities(b2_context* ctx);
 int program_run(b2_context* ctx, int nsteps);
+int barostat_attempt(b2_context* ctx);
+int box_update(b2_context* ctx, const double box[3]);
 int program_release(b2_context* ctx);
+// profiling mode: the work enqueued from here on belongs to phase `tag` (B2_PHASE_*)
+enum { B2_PHASE_OTHER = 0, B2_PHASE_EXCHANGE = 1, B2_PHASE_REBUILD = 2, B2_PHASE_PAIR = 3, B2_PHASE_INTEGRATE = 4,
+       B2_PHASE_REDUCE = 5, B2_PHASE_COUNT = 6 };
+void phase_mark(b2_context* ctx, int tag);
 int state_permute_to_sorted(b2_context* ctx, const double* user, double* sorted);
 int state_permute_to_user(b2_context* ctx, const double* sorted, double* user);

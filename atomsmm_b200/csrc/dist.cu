@@ -214,6 +214,7 @@ __global__ void k_dd_post(DDPeers P, unsigned long long* state, const int* __res
 // atoms) out of the owners' memory; the last block to finish publishes the common rebuild
 // decision, resets the halo counter for the coming rebuild and acknowledges to the owners
 __global__ void __launch_bounds__(256) k_dd_pull(DDPeers P, unsigned long long* state, int* nl_flags, double* __restrict__ x,
+                                                 int4* __restrict__ xq, double sx, double sy, double sz,
                                                  int n, const int* __restrict__ halo_groups, int* halo_count) {
     __shared__ int s_flag;
     __shared__ unsigned long long s_epoch;
@@ -228,21 +229,17 @@ __global__ void __launch_bounds__(256) k_dd_pull(DDPeers P, unsigned long long* 
     __syncthreads();
     const long long stride = (long long)gridDim.x*blockDim.x;
     const long long first = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-    if (s_flag) {
-        for (long long d = first; d < 3ll*n; d += stride) {
-            const int o = dd_owner(P, (int)(d/3));
-            if (o != P.rank) x[d] = __ldcg(P.x[o] + d);
-        }
-    } else {
-        const long long total = 3ll*B2_GROUP*(*halo_count);
-        for (long long t = first; t < total; t += stride) {
-            const int g = halo_groups[t/(3*B2_GROUP)];
-            const long long d = 3ll*B2_GROUP*g + t % (3*B2_GROUP);
-            if (d < 3ll*n) {
-                const int o = dd_owner(P, (int)(d/3));
-                if (o != P.rank) x[d] = __ldcg(P.x[o] + d);
-            }
-        }
+    // one thread per atom: 24 B read from the owner, master copy and fixed-point copy written locally
+    const long long total = s_flag ? (long long)n : (long long)B2_GROUP*(*halo_count);
+    for (long long t = first; t < total; t += stride) {
+        const int a = s_flag ? (int)t : halo_groups[t/B2_GROUP]*B2_GROUP + (int)(t % B2_GROUP);
+        if (a >= n) continue;
+        const int o = dd_owner(P, a);
+        if (o == P.rank) continue;
+        const double* src = P.x[o] + 3ll*a;
+        const double px = __ldcg(src), py = __ldcg(src + 1), pz = __ldcg(src + 2);
+        x[3ll*a] = px; x[3ll*a+1] = py; x[3ll*a+2] = pz;
+        xq[a] = make_int4(b2_to_fixed(px, sx), b2_to_fixed(py, sy), b2_to_fixed(pz, sz), 0);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -291,7 +288,9 @@ int dist_exchange_halo(b2_context* ctx) {
     DDPeers P = make_peers(ctx);
     k_dd_post<<<1, 32, 0, ctx->stream>>>(P, ctx->dd_state, ctx->nl_flags);
     B2_LAUNCH_CHECK();
-    k_dd_pull<<<296, 256, 0, ctx->stream>>>(P, ctx->dd_state, ctx->nl_flags, ctx->x, ctx->n, ctx->halo_groups, ctx->halo_count);
+    k_dd_pull<<<296, 256, 0, ctx->stream>>>(P, ctx->dd_state, ctx->nl_flags, ctx->x, ctx->xq, 4294967296.0/ctx->box[0],
+                                            4294967296.0/ctx->box[1], 4294967296.0/ctx->box[2], ctx->n, ctx->halo_groups,
+                                            ctx->halo_count);
     B2_LAUNCH_CHECK();
     ctx->acks_pending = true;
     ctx->counters[7]++;

@@ -445,11 +445,13 @@ int forces_ensure(b2_context* ctx, uint32_t mask, int slot) {
         B2_TRY(nl_prepare(ctx, false));
     }
     bool written = false;
+    phase_mark(ctx, B2_PHASE_PAIR);
     for (const PairForce& pf : ctx->pair_forces) {
         if (!(mask & (1u << pf.group))) continue;
         B2_TRY(pair_eval_forces(ctx, pf, ctx->fbuf[slot], written));
         written = true;
     }
+    phase_mark(ctx, B2_PHASE_INTEGRATE);
     B2_TRY(dist_before_move(ctx));      // by now the peers have long finished reading: the wait costs nothing here
     if (!written) B2_CUDA(cudaMemsetAsync(ctx->fbuf[slot], 0, sizeof(float4)*ctx->n, ctx->stream));
     B2_TRY(bonded_eval_forces(ctx, mask, ctx->fbuf[slot]));
@@ -559,6 +561,7 @@ static int launch_vel(b2_context* ctx, const b2_op& op) {
                                           ctx->rng_state, ctx->d_energy);
     }
     B2_LAUNCH_CHECK();
+    if (split) phase_mark(ctx, B2_PHASE_REDUCE);
     if (split && ctx->p2p) {
         DDPeers P;
         dd_fill_peers(ctx, &P);
@@ -573,6 +576,7 @@ static int launch_vel(b2_context* ctx, const b2_op& op) {
             B2_LAUNCH_CHECK();
         }
     }
+    if (split) phase_mark(ctx, B2_PHASE_INTEGRATE);
     if (op.c >= 0) ctx->pos_version++;
     return B2_OK;
 }
@@ -582,7 +586,7 @@ static int launch_vel(b2_context* ctx, const b2_op& op) {
 static int try_fused_run(b2_context* ctx, size_t k, int* consumed) {
     *consumed = 0;
     static const bool allowed = getenv("B2_NO_FUSED_INNER") == nullptr;
-    if (!allowed || !ctx->inner_ok || ctx->profiling) return B2_OK;
+    if (!allowed || !ctx->inner_ok) return B2_OK;
     const std::vector<b2_op>& ops = ctx->ops;
     if (ops[k].kind != B2_OP_KICK || ops[k].e >= 0) return B2_OK;
     // the run: KICK (no reduction) and bonded-only EVAL ops, all evaluations into the same slot
@@ -661,6 +665,7 @@ static int run_one_step(b2_context* ctx) {
     cudaStream_t s = ctx->stream;
     // the step counter of the RNG streams is advanced by the first kernel of the step when that is the
     // scalar prologue, otherwise by a kernel of its own
+    phase_mark(ctx, B2_PHASE_INTEGRATE);
     const bool run_prologue = !ctx->ops.empty() && ctx->ops[0].kind == B2_OP_GLOBAL &&
                               !(ctx->ops[0].d == 1 && ctx->prologue_valid);
     const bool folded_begin = run_prologue;
@@ -816,6 +821,9 @@ int program_run(b2_context* ctx, int nsteps) {
     static const bool graph_allowed = getenv("B2_NO_GRAPH") == nullptr;
     const bool use_graph = graph_allowed && !ctx->profiling;
     static const int order_period = getenv("B2_ORDER_PERIOD") ? atoi(getenv("B2_ORDER_PERIOD")) : 250;
+    bool has_update_state = false;       // the step program contains the UpdateContextState hook
+    for (const b2_op& op : ctx->ops)
+        if (op.kind == B2_OP_UPDATE_STATE) has_update_state = true;
     for (int done = 0; done < nsteps; done++) {
         if (order_period > 0 && ++ctx->steps_since_order_check >= order_period) {
             ctx->steps_since_order_check = 0;
@@ -824,6 +832,10 @@ int program_run(b2_context* ctx, int nsteps) {
             B2_TRY(con_prepare(ctx));
         }
         B2_TRY(dist_before_move(ctx));
+        if (ctx->baro_on && has_update_state && ++ctx->baro_steps >= ctx->baro_frequency) {
+            ctx->baro_steps = 0;
+            B2_TRY(barostat_attempt(ctx));           // may release the graph (accepted move: new box)
+        }
         const unsigned long long entry = valid_mask(ctx);
         const bool synced = ctx->x_synced == ctx->pos_version;
         if (use_graph && ctx->graph_ready && (entry & ctx->graph_entry_mask) == ctx->graph_entry_mask &&

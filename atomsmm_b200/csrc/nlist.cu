@@ -56,13 +56,16 @@ __device__ __forceinline__ bool is_excluded(int oi, int oj, unsigned long long m
     return false;
 }
 
-// K8: skin test, one pass over x and xref (48 B/atom), before every pair-force evaluation.
+// K8: skin test, one pass over x and xref (48 B/atom), before every pair-force evaluation.  The same pass
+// refreshes the fixed-point copy of the positions that the pair tiles read (16 B/atom written).
 __global__ void k_skin_check(int lo, int n, const double* __restrict__ x, const double* __restrict__ xref, double limit2,
-                             int* flags, int have_ref) {
+                             int* flags, int have_ref, int4* __restrict__ xq, double sx, double sy, double sz) {
     int i = lo + blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const double px = x[3*i], py = x[3*i+1], pz = x[3*i+2];
+    xq[i] = make_int4(b2_to_fixed(px, sx), b2_to_fixed(py, sy), b2_to_fixed(pz, sz), 0);
     if (have_ref) {
-        double dx = x[3*i] - xref[3*i], dy = x[3*i+1] - xref[3*i+1], dz = x[3*i+2] - xref[3*i+2];
+        double dx = px - xref[3*i], dy = py - xref[3*i+1], dz = pz - xref[3*i+2];
         if (dx*dx + dy*dy + dz*dz > limit2) flags[0] = 1;
     } else {
         flags[0] = 1;
@@ -626,14 +629,21 @@ int nl_prepare(b2_context* ctx, bool force) {
     // ranks inside the halo exchange, which also brings in the positions the pair kernels (or, when the
     // verdict is "rebuild", the list build) are about to read.  Otherwise the test runs over all atoms
     // (single GPU; NCCL mode, where the caller has all-gathered the positions before).
-    const int t_lo = ctx->p2p ? ctx->a_lo : 0, t_hi = ctx->p2p ? ctx->a_hi : n;
+    // (forced builds follow b2_set_positions / a box change: positions are complete on every rank and nothing is
+    // pulled, so the pass covers all atoms then, too)
+    phase_mark(ctx, B2_PHASE_EXCHANGE);
+    const bool owned_only = ctx->p2p && !force;
+    const int t_lo = owned_only ? ctx->a_lo : 0, t_hi = owned_only ? ctx->a_hi : n;
     k_skin_check<<<std::max(1, (t_hi - t_lo + T - 1)/T), T, 0, s>>>(t_lo, t_hi, ctx->x, ctx->xref, limit*limit, ctx->nl_flags,
-                                                                  (ctx->lists_built && !force) ? 1 : 0);
+                                                                  (ctx->lists_built && !force) ? 1 : 0, ctx->xq,
+                                                                  4294967296.0/ctx->box[0], 4294967296.0/ctx->box[1],
+                                                                  4294967296.0/ctx->box[2]);
     B2_LAUNCH_CHECK();
     if (ctx->p2p) {
         if (!force) B2_TRY(dist_exchange_halo(ctx));     // forced builds follow b2_set_positions: x is complete everywhere
         else B2_CUDA(cudaMemsetAsync(ctx->halo_count, 0, sizeof(int), s));
     }
+    phase_mark(ctx, B2_PHASE_REBUILD);
     k_group_geom<<<(8*ng + T - 1)/T, T, 0, s>>>(n, ng, ctx->x, g, ctx->prel, ctx->gcen, ctx->ghalf, ctx->gcell,
                                                  ctx->cell_count, hmax, (float)(fat_factor*ctx->cellsize[0]),
                                                  ctx->fat_list, ng, ctx->nl_flags);
@@ -665,6 +675,7 @@ int nl_prepare(b2_context* ctx, bool force) {
     k_save_ref<<<std::max(1, (3*(t_hi - t_lo) + T - 1)/T), T, 0, s>>>(3*t_lo, 3*t_hi, ctx->x, ctx->xref, ctx->nl_flags, hmax);
     B2_LAUNCH_CHECK();
     ctx->lists_built = true;
+    phase_mark(ctx, B2_PHASE_OTHER);
     return B2_OK;
 }
 

@@ -6,8 +6,9 @@
 //
 // Mapping: one warp per i-group of 8 spatially adjacent atoms; lane = (i-atom 0..7) x (j-lane
 // 0..3).  The group's j-list is streamed 32 entries at a time: every lane gathers one j atom
-// (float64 position + float4 parameters, coalesced index read), forms its minimum-image position
-// relative to the group's first atom in float64, rounds to fp32 and stages it in shared memory; the warp then sweeps the 32 staged atoms in
+// (fixed-point position + float4 parameters, coalesced index read), forms its minimum-image position
+// relative to the group's first atom (integer wrap-around), converts to fp32 and stages it in shared
+// memory; the warp then sweeps the 32 staged atoms in
 // 8 steps of 4, each lane accumulating the force on its own i-atom in registers.  Forces are
 // reduced over the 4 j-lanes with two shuffles and written once per atom: no atomics, results
 // are bit-reproducible.  The full (both-directions) list means every pair is evaluated twice;
@@ -146,24 +147,27 @@ __device__ __forceinline__ void sweep_chunk(const POT& pot, const float4* __rest
     ax += (double)fx; ay += (double)fy; az += (double)fz;   // fp64 across chunks: no long fp32 sums
 }
 
-// relative position of atom a with respect to the group's reference point, minimum image, computed
-// in float64 from the unwrapped master coordinates and only then rounded: the fp32 error is that of
-// a ~1 nm relative vector (6e-8 nm), independent of the box size.
-__device__ __forceinline__ float3 rel_pos(const double* __restrict__ x, int a, double rx, double ry, double rz,
-                                          double bx, double by, double bz, double ibx, double iby, double ibz) {
-    double dx = x[3*a] - rx, dy = x[3*a+1] - ry, dz = x[3*a+2] - rz;
-    dx -= bx*rint(dx*ibx); dy -= by*rint(dy*iby); dz -= bz*rint(dz*ibz);
-    return make_float3((float)dx, (float)dy, (float)dz);
+// Positions reach the tiles as 32-bit FIXED-POINT fractions of the box (xq, maintained by the skin-test
+// kernel): one 16-byte load per staged atom instead of three strided doubles, and the difference of two
+// fixed-point coordinates wraps around exactly like the periodic box does -- the minimum image relative to the
+// group's reference atom costs nothing.  Resolution L/2^32 (8e-9 nm at L = 35 nm); the difference is exact,
+// its conversion to fp32 has the error of a ~1 nm vector (6e-8 nm), independent of the box size.
+__device__ __forceinline__ float3 rel_fixed(int4 q, int4 ref, float3 scale) {
+    return make_float3((float)(q.x - ref.x)*scale.x, (float)(q.y - ref.y)*scale.y, (float)(q.z - ref.z)*scale.z);
 }
 
+// The list of a group is streamed 32 entries at a time through a THREE-stage pipeline: while chunk c is swept
+// from shared memory, the gathers (fixed-point position, parameters) of chunk c+1 are in flight and so is the
+// index load of chunk c+2 -- the dependent chain entries -> gathers never sits on the critical path, and the
+// gathered values are first touched after the sweep.
 template <class POT>
-__global__ void __launch_bounds__(32*WPB, 8) k_pair_force(int n, int g_lo, int ngroups, const double* __restrict__ x,
+__global__ void __launch_bounds__(32*WPB, 8) k_pair_force(int n, int g_lo, int ngroups, const int4* __restrict__ xq,
                                                       const float4* __restrict__ par,
                                                       const int* __restrict__ entries,
                                                       const int* __restrict__ counts,
                                                       const unsigned char* __restrict__ gflags, int cap,
                                                       float4* __restrict__ out, int accumulate, POT pot,
-                                                      float rc2, BandBuffer bb, double bx, double by, double bz) {
+                                                      float rc2, BandBuffer bb, float3 box) {
     __shared__ float4 sx[WPB][2][32];
     __shared__ float4 sp[WPB][2][32];
     const int warp = g_lo + ((blockIdx.x*blockDim.x + threadIdx.x) >> 5);
@@ -172,13 +176,13 @@ __global__ void __launch_bounds__(32*WPB, 8) k_pair_force(int n, int g_lo, int n
     const int il = lane >> 2, jj = lane & 3;
     const int i = warp*B2_GROUP + il;
     const int ic = min(i, n - 1);
-    const double ibx = 1.0/bx, iby = 1.0/by, ibz = 1.0/bz;
-    const float3 box = make_float3((float)bx, (float)by, (float)bz);
-    const float3 inv = make_float3((float)ibx, (float)iby, (float)ibz);
+    const float3 inv = make_float3(1.f/box.x, 1.f/box.y, 1.f/box.z);
+    const float3 scale = make_float3(box.x*2.3283064365386963e-10f, box.y*2.3283064365386963e-10f,
+                                     box.z*2.3283064365386963e-10f);
     // reference point of the group: its first atom
     const int i0 = warp*B2_GROUP;
-    const double rx = x[3*i0], ry = x[3*i0+1], rz = x[3*i0+2];
-    const float3 xr = rel_pos(x, ic, rx, ry, rz, bx, by, bz, ibx, iby, ibz);
+    const int4 ref = xq[i0];
+    const float3 xr = rel_fixed(xq[ic], ref, scale);
     const float4 xi = make_float4(xr.x, xr.y, xr.z, 0.f);
     const float4 pi = par[ic];
     const bool minimg = gflags[warp] & 1;
@@ -188,19 +192,21 @@ __global__ void __launch_bounds__(32*WPB, 8) k_pair_force(int n, int g_lo, int n
     const int pad = (int)(0xff000000u | (unsigned)i0);
     double fx = 0.0, fy = 0.0, fz = 0.0;
     int buf = 0;
-    // software pipeline: gather chunk c+1 while chunk c is being swept
-    int e = lane < cnt ? base[lane] : pad;
-    float3 xj = rel_pos(x, e & 0xffffff, rx, ry, rz, bx, by, bz, ibx, iby, ibz);
+    int e = lane < cnt ? base[lane] : pad;                       // chunk 0
+    int e_next = 32 + lane < cnt ? base[32 + lane] : pad;        // chunk 1
+    int4 qj = xq[e & 0xffffff];
     float4 pj = par[e & 0xffffff];
     for (int c0 = 0; c0 < cnt; c0 += 32) {
+        const float3 xj = rel_fixed(qj, ref, scale);
         pj.w = __int_as_float(e);
         sx[wib][buf][lane] = make_float4(xj.x, xj.y, xj.z, 0.f);
         sp[wib][buf][lane] = pj;
-        const int nxt = c0 + 32 + lane;
         if (c0 + 32 < cnt) {
-            e = nxt < cnt ? base[nxt] : pad;
-            xj = rel_pos(x, e & 0xffffff, rx, ry, rz, bx, by, bz, ibx, iby, ibz);
+            e = e_next;
+            qj = xq[e & 0xffffff];
             pj = par[e & 0xffffff];
+            const int nxt = c0 + 64 + lane;
+            e_next = nxt < cnt ? base[nxt] : pad;
         }
         __syncwarp();
         if (minimg)
@@ -452,10 +458,10 @@ static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, POTD potd
         cudaEventCreate(&ev0); cudaEventCreate(&ev1);
         cudaEventRecord(ev0, stream);
     }
-    k_pair_force<POT><<<blocks, 32*WPB, 0, stream>>>(ctx->n, ctx->g_lo, ctx->g_hi, ctx->x, ctx->par[pf.set],
+    k_pair_force<POT><<<blocks, 32*WPB, 0, stream>>>(ctx->n, ctx->g_lo, ctx->g_hi, ctx->xq, ctx->par[pf.set],
                                                           L.entries, L.counts, L.gflags, L.cap, out,
-                                                          accumulate ? 1 : 0, pot, rc2, bb, ctx->box[0], ctx->box[1],
-                                                          ctx->box[2]);
+                                                          accumulate ? 1 : 0, pot, rc2, bb,
+                                                          make_float3((float)ctx->box[0], (float)ctx->box[1], (float)ctx->box[2]));
     if (ctx->profiling) {
         cudaEventRecord(ev1, stream);
         ctx->prof_events.push_back(ev0); ctx->prof_events.push_back(ev1);

@@ -26,7 +26,8 @@ enum {
     B2_OP_DRIFT = 6,
     // v *= g[a]                              fast scale
     B2_OP_SCALE = 7,
-    // UpdateContextState hook (no-op: no barostat / CMMotionRemover in the engine yet)
+    // UpdateContextState hook: where a MonteCarloBarostat of the System acts.  Executed by program_run
+    // BETWEEN steps (the hook is the first computation of every atomsmm step program, integrators.py:115-122)
     B2_OP_UPDATE_STATE = 8,
     // dE/d(parameter) of the soft-core pair forces -> device energy slots 64 (lambda_vdw) and 65
     // (lambda_coul), read by VM_PUSHE: the `deriv(energy, lambda)` of AFED (integrators.py:735-737)

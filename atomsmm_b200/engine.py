@@ -71,6 +71,12 @@ _SIGNATURES = {
     'b2_set_profiling': [c_void, ctypes.c_int],
     'b2_get_profile': [c_void, ctypes.c_int, c_double_p, ctypes.POINTER(ctypes.c_longlong),
                        ctypes.POINTER(ctypes.c_longlong)],
+    'b2_set_barostat': [c_void, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_ulonglong],
+    'b2_get_box': [c_void, c_double_p],
+    'b2_update_box': [c_void, c_double_p],
+    'b2_get_barostat_stats': [c_void, ctypes.POINTER(ctypes.c_longlong), c_double_p],
+    'b2_barostat_uniform': [ctypes.c_ulonglong, ctypes.c_ulonglong, c_double_p],
+    'b2_get_phase_profile': [c_void, c_double_p],
     'b2_comm_unique_id': [ctypes.c_char_p],
     'b2_comm_init': [c_void, ctypes.c_int, ctypes.c_int, ctypes.c_char_p],
     'b2_comm_export': [c_void, ctypes.c_char_p],
@@ -377,6 +383,13 @@ class Context(object):
             group = force.getForceGroup()
             if isinstance(force, mm.CMMotionRemover):
                 continue
+            if isinstance(force, mm.MonteCarloBarostat):
+                # bar -> kJ/mol/nm^3 (OpenMM: pressure*AVOGADRO*1e-25)
+                pressure = force._pressure*6.02214179e23*1e-25
+                kT = 8.314472471220217e-3*force._temperature
+                self._call('b2_set_barostat', pressure, kT, force._frequency, ctypes.c_ulonglong(force._seed & 0xffffffffffffffff))
+                self._barostat = force
+                continue
             self._all_groups |= 1 << group
             if isinstance(force, mm.CustomNonbondedForce):
                 if force.getNumParticles() != n:
@@ -664,7 +677,7 @@ class Context(object):
 
     def _pair_description(self, force):
         """(params, energy constant, particle table) of a pair force from its CURRENT description."""
-        volume = float(np.prod(self._box))
+        volume = float(np.prod(self._current_box()))
         if isinstance(force, mm.NonbondedForce):
             params, pme = self._nonbonded_params(force)
             if pme is not None:
@@ -734,9 +747,26 @@ class Context(object):
             self._set_global(name, self._parameters[name])
 
     def setPeriodicBoxVectors(self, a, b, c):
+        """OpenMM semantics: the box changes, the atoms are not moved.  Cells, neighbour lists, PME
+        influence function and long-range corrections follow; the captured step graph is released."""
         box = np.array([_md(a)[0], _md(b)[1], _md(c)[2]], dtype=np.float64)
-        if not np.allclose(box, self._box, rtol=0, atol=1e-12):
-            raise lowering.UnsupportedDescription('changing the box of a live context is not supported yet')
+        if not np.allclose(box, self._current_box(), rtol=0, atol=1e-14):
+            with self._torch.cuda.stream(self._stream):
+                self._call('b2_update_box', _dptr(box))
+            self._box = box
+
+    def _current_box(self):
+        """The box as the engine holds it (a Monte Carlo barostat moves it during a run)."""
+        out = (ctypes.c_double*3)()
+        self._call('b2_get_box', out)
+        self._box = np.array([out[0], out[1], out[2]], dtype=np.float64)
+        return self._box
+
+    def barostat_statistics(self):
+        out = (ctypes.c_longlong*2)()
+        scale = ctypes.c_double()
+        self._call('b2_get_barostat_stats', out, ctypes.byref(scale))
+        return dict(attempts=out[0], accepted=out[1], volume_scale=scale.value)
 
     def _upload(self, values, what):
         torch = self._torch
@@ -813,7 +843,7 @@ class Context(object):
         if need_state and not self._have_positions:
             raise mm.OpenMMException('Particle positions have not been set')
         fields = dict(_positions=None, _velocities=None, _forces=None, _potential=None, _kinetic=None,
-                      _box=self._box.copy(), _parameters=self.getParameters() if getParameters else {},
+                      _box=self._current_box().copy(), _parameters=self.getParameters() if getParameters else {},
                       _derivatives={}, _time=self._time)
         with torch.cuda.stream(self._stream):
             if getPositions:
@@ -821,9 +851,10 @@ class Context(object):
                 self._call('b2_synchronize')
                 pos = self._buffer.cpu().numpy()
                 if enforcePeriodicBox:
+                    box = fields['_box']
                     for group in self._molecule_groups:
                         centre = pos[group].mean(axis=0)
-                        pos[group] -= np.floor(centre/self._box)*self._box
+                        pos[group] -= np.floor(centre/box)*box
                 fields['_positions'] = pos
             if getVelocities or getEnergy:
                 self._call('b2_get_velocities', c_void(self._buffer.data_ptr()))
@@ -844,6 +875,10 @@ class Context(object):
                 if getForces:
                     fields['_forces'] = self._buffer.cpu().numpy()
                 if getEnergy:
+                    if not (math.isfinite(energy.value) and math.isfinite(fields['_kinetic'])):
+                        # OpenMM's behaviour: a blown-up trajectory is reported, not returned as numbers
+                        raise mm.OpenMMException('Energy is NaN (potential %r, kinetic %r): the simulation has become '
+                                                 'unstable' % (energy.value, fields['_kinetic']))
                     fields['_potential'] = energy.value
                     fields['_virial'] = virial.value
                 if getParameterDerivatives:
@@ -905,6 +940,13 @@ class Context(object):
             out.append(dict(name=info.get('name'), group=force.getForceGroup(), total_ms=ms.value,
                             launches=launches.value, entries=entries.value))
         return out
+
+    def phase_profile(self):
+        """Milliseconds per phase of the step accumulated in profiling mode (eager pass)."""
+        out = (ctypes.c_double*6)()
+        self._call('b2_get_phase_profile', out)
+        names = ('other', 'skin_test_and_exchange', 'list_rebuild', 'pair_kernels', 'integrator_kernels', 'reductions')
+        return dict(zip(names, [round(v, 3) for v in out]))
 
     def synchronize(self):
         self._call('b2_synchronize')

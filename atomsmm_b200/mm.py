@@ -581,6 +581,56 @@ class CMMotionRemover(Force):
         return self._frequency
 
 
+class MonteCarloBarostat(Force):
+    """openmm.MonteCarloBarostat: isotropic Monte Carlo volume moves applied where the integrator calls
+    UpdateContextState (the first computation of every atomsmm step program, integrators.py:115-122).
+    The reference has no barostat of its own; this is the OpenMM force a user adds to
+    the System for NPT runs."""
+
+    def __init__(self, defaultPressure, defaultTemperature, frequency=25):
+        Force.__init__(self)
+        self._pressure = float(_md(defaultPressure.value_in_unit(unit.bar)
+                                   if isinstance(defaultPressure, unit.Quantity) else defaultPressure))
+        self._temperature = float(_md(defaultTemperature))
+        self._frequency = int(frequency)
+        self._seed = 0
+
+    @staticmethod
+    def Pressure():
+        return 'MonteCarloPressure'
+
+    @staticmethod
+    def Temperature():
+        return 'MonteCarloTemperature'
+
+    def getDefaultPressure(self):
+        return self._pressure*unit.bar
+
+    def setDefaultPressure(self, pressure):
+        self._pressure = float(pressure.value_in_unit(unit.bar) if isinstance(pressure, unit.Quantity) else pressure)
+
+    def getDefaultTemperature(self):
+        return self._temperature*unit.kelvin
+
+    def setDefaultTemperature(self, temperature):
+        self._temperature = float(_md(temperature))
+
+    def getFrequency(self):
+        return self._frequency
+
+    def setFrequency(self, frequency):
+        self._frequency = int(frequency)
+
+    def getRandomNumberSeed(self):
+        return self._seed
+
+    def setRandomNumberSeed(self, seed):
+        self._seed = int(seed)
+
+    def usesPeriodicBoundaryConditions(self):
+        return True
+
+
 class System(object):
     def __init__(self):
         self._masses = []

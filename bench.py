@@ -462,6 +462,11 @@ def main():
         context.set_profiling(True)
         integrator.step(8)
         profile = context.pair_profile()
+        phases = context.phase_profile()
+        all_phases = [phases]
+        if world > 1:
+            all_phases = [None]*world
+            dist.all_gather_object(all_phases, phases)
         context.set_profiling(False)
         peak, peak_kind = measured_peak()
         used = [p for p in profile if p['launches'] > 0]
@@ -485,6 +490,9 @@ def main():
                         kernel='k_pair_force<%s> group %d' % (dominant['name'], dominant['group']),
                         avg_launch_us=avg_s*1e6, algorithmic_bytes_per_launch=bytes_per_launch,
                         list_entries=dominant['entries'],
+                        phases_ms_per_md_step={k: round(v/8.0, 4) for k, v in phases.items()},
+                        phases_ms_per_md_step_by_rank=([{k: round(v/8.0, 4) for k, v in p.items()} for p in all_phases]
+                                                       if world > 1 else None),
                         pair_kernels_share_of_step=pair_ms_per_md_step/(1e3*elapsed/(args.steps*md)),
                         whole_step=(dict(bytes_per_atom_step=step_bytes, achieved=step_bytes*value/world/1e9,
                                          frac=step_bytes*value/world/1e9/peak) if step_bytes else None),

@@ -210,6 +210,26 @@ B2_API int b2_get_list_stats(b2_context* ctx, long long out_host[4]);
  * reads per launch (for the algorithmic-bytes figure). */
 B2_API int b2_set_profiling(b2_context* ctx, int on);
 B2_API int b2_get_profile(b2_context* ctx, int handle, double* total_ms, long long* launches, long long* entries);
+/* the same eager pass split into phases of the step, milliseconds accumulated since profiling was switched
+ * on: [0] other, [1] skin test + halo exchange (includes waiting for the slowest peer), [2] list rebuild
+ * pipeline, [3] pair-force kernels, [4] integrator kernels, [5] cross-rank reductions + scalar programs */
+B2_API int b2_get_phase_profile(b2_context* ctx, double out_ms[6]);
+
+/* ---- NPT: Monte Carlo barostat behind the UpdateContextState hook ---------------------------- *
+ * The reference emits `addUpdateContextState()` as the first computation of every step program
+ * (integrators.py:115-122) and has no barostat of its own; this is openmm.MonteCarloBarostat (the force a
+ * user adds to the System) with OpenMM's algorithm: every `frequency` steps a trial volume change with
+ * rigid molecule-centre scaling, Metropolis acceptance on E' - E + P dV - N_mol kT ln(V'/V), step size
+ * adapted every 10 attempts.  pressure in kJ/mol/nm^3, kT in kJ/mol; frequency 0 switches it off.
+ * Random numbers are SplitMix64(seed, counter) -- b2_barostat_uniform exposes the stream (pure host
+ * function) so that a float64 oracle can replay the accept/reject sequence. */
+B2_API int b2_set_barostat(b2_context* ctx, double pressure, double kT, int frequency, unsigned long long seed);
+B2_API int b2_get_barostat_stats(b2_context* ctx, long long attempts_accepted_host[2], double* volume_scale);
+B2_API int b2_barostat_uniform(unsigned long long seed, unsigned long long counter, double* out);
+/* current periodic box (a barostat moves it) / Context.setPeriodicBoxVectors on a live context (OpenMM
+ * semantics: atoms are not moved; cells, lists, PME influence function and long-range corrections follow) */
+B2_API int b2_get_box(b2_context* ctx, double out[3]);
+B2_API int b2_update_box(b2_context* ctx, const double box[3]);
 
 /* ---- multi-GPU: spatial decomposition of ONE system over the GPUs of a node ---------------- *
  * The reference is single-process; these calls are the engine's own.  One process

@@ -181,7 +181,7 @@ class CPort(object):
                 atoms, prm = _columns(force, '_bonds', 2)
                 prm = np.concatenate([prm.reshape(len(atoms), 3), np.zeros((len(atoms), 1))], axis=1)
                 self._add_bonded(B_LJC, group, atoms, prm, [kc, 0.0])
-            elif kind == 'CMMotionRemover':
+            elif kind in ('CMMotionRemover', 'MonteCarloBarostat'):
                 continue
             else:
                 raise ValueError('C port: unsupported force %s' % kind)

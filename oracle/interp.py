@@ -80,6 +80,10 @@ class Interpreter(object):
                 np.full((self.n, 3), float(value)) if np.isscalar(value) else np.array(value, dtype=np.float64)
         self.steps = [tuple(integrator.getComputationStep(k)) for k in range(integrator.getNumComputations())]
         self.rng = np.random.default_rng(seed)
+        # openmm.MonteCarloBarostat forces act where the program calls UpdateContextState
+        self.barostats = [dict(force=f, steps=0, counter=0, scale=0.0, attempts=0, accepted=0, log=[])
+                          for f in system.getForces() if type(f).__name__ == 'MonteCarloBarostat']
+        self._molecules = None
         self._force_cache = {}
         self._version = 0
         self._compiled = {}
@@ -182,6 +186,67 @@ class Interpreter(object):
                         '<=': lhs <= rhs, '>=': lhs >= rhs}[op]
         raise ValueError('bad condition %r' % text)
 
+    # -- Monte Carlo barostat (OpenMM MonteCarloBarostatImpl::updateContextState, restated) -----------------
+    @staticmethod
+    def barostat_uniform(seed, counter):
+        """SplitMix64(seed, counter) -> [0, 1): the stream of csrc/barostat.cu (b2_barostat_uniform)."""
+        mask = (1 << 64) - 1
+        z = (seed + 0x9e3779b97f4a7c15*(counter + 1)) & mask
+        z = ((z ^ (z >> 30))*0xbf58476d1ce4e5b9) & mask
+        z = ((z ^ (z >> 27))*0x94d049bb133111eb) & mask
+        z ^= z >> 31
+        return (z >> 11)/9007199254740992.0
+
+    def _molecule_index(self):
+        if self._molecules is None:
+            from atomsmm_b200 import engine
+            self._molecules = engine._molecules(self.system)[0]
+        return self._molecules
+
+    def _barostat_move(self, b):
+        force = b['force']
+        b['steps'] += 1
+        if b['steps'] < force.getFrequency():
+            return
+        b['steps'] = 0
+        seed = force.getRandomNumberSeed() & ((1 << 64) - 1)
+        pressure = force.getDefaultPressure().value_in_unit(force.getDefaultPressure().unit)*6.02214179e23*1e-25
+        kT = 8.314472471220217e-3*force.getDefaultTemperature().value_in_md_units()
+        volume = float(np.prod(self.box))
+        if b['scale'] == 0.0:
+            b['scale'] = 0.01*volume
+        e0 = refmath.evaluate_system(self.system, self.x, self.box, None, self.parameters).energy
+        dv = b['scale']*2.0*(self.barostat_uniform(seed, b['counter']) - 0.5)
+        b['counter'] += 1
+        new_volume = volume + dv
+        scale = (new_volume/volume)**(1.0/3.0)
+        mol = self._molecule_index()
+        nmol = int(mol.max()) + 1
+        counts = np.bincount(mol, minlength=nmol)[:, None]
+        centres = np.stack([np.bincount(mol, self.x[:, k], nmol) for k in range(3)], axis=1)/counts
+        trial = self.x + (centres*(scale - 1.0))[mol]
+        new_box = self.box*scale
+        e1 = refmath.evaluate_system(self.system, trial, new_box, None, self.parameters).energy
+        w = e1 - e0 + pressure*dv - nmol*kT*np.log(new_volume/volume)
+        accept = True
+        if w > 0:
+            accept = self.barostat_uniform(seed, b['counter']) <= np.exp(-w/kT)
+        b['counter'] += 1
+        if accept:
+            self.x, self.box = trial, new_box
+            self._version += 1
+            self._force_cache = {}
+            b['accepted'] += 1
+        b['attempts'] += 1
+        b['log'].append((bool(accept), float(np.prod(self.box)), float(w)))
+        if b['attempts'] >= 10:
+            if b['accepted'] < 0.25*b['attempts']:
+                b['scale'] /= 1.1
+                b['attempts'] = b['accepted'] = 0
+            elif b['accepted'] > 0.75*b['attempts']:
+                b['scale'] = min(b['scale']*1.1, 0.3*float(np.prod(self.box)))
+                b['attempts'] = b['accepted'] = 0
+
     def step(self, count=1):
         massive = self.mass > 0
         for _ in range(count):
@@ -210,6 +275,9 @@ class Interpreter(object):
                 elif kind == 2:    # sum
                     value = np.broadcast_to(self._evaluate(expression, True), (self.n, 3))
                     self.globals[variable] = float(np.sum(value))
+                elif kind == 5:    # UpdateContextState
+                    for barostat in self.barostats:
+                        self._barostat_move(barostat)
                 elif kind == 3:
                     if self.system.getNumConstraints() > 0:
                         self.x = shake(self.constraints(), self.mass[:, 0], self.x, self.x_constrained)

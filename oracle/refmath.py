@@ -592,7 +592,8 @@ def eval_nonbonded(force, pos, box, part='all'):
 def _kind(force):
     for cls in type(force).__mro__:
         if cls.__name__ in ('NonbondedForce', 'CustomNonbondedForce', 'CustomBondForce', 'CustomAngleForce',
-                            'HarmonicBondForce', 'HarmonicAngleForce', 'PeriodicTorsionForce', 'CMMotionRemover'):
+                            'HarmonicBondForce', 'HarmonicAngleForce', 'PeriodicTorsionForce', 'CMMotionRemover',
+                            'MonteCarloBarostat'):
             return cls.__name__
     raise TypeError('unsupported force %r' % force)
 
@@ -623,7 +624,7 @@ def evaluate_system(system, pos, box=None, groups=None, params=None):
             part = 'all' if (want and want_r) else ('direct' if want else ('reciprocal' if want_r else None))
             if part:
                 res = eval_nonbonded(force, pos, box, part)
-        elif not want or kind == 'CMMotionRemover':
+        elif not want or kind in ('CMMotionRemover', 'MonteCarloBarostat'):
             res = None
         elif kind == 'CustomNonbondedForce':
             res = eval_custom_nonbonded(force, pos, box, params)

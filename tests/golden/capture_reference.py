@@ -26,39 +26,9 @@ REFERENCE = '/root/reference'
 
 
 def install_stub():
-    from atomsmm_b200 import app, mm, unit
-    simtk = types.ModuleType('simtk')
-    simtk.openmm = mm
-    simtk.unit = unit
-    mm.app = app
-    # classes the reference subclasses at import time but which are outside the hot path
-    for module, name in ((app, 'StateDataReporter'), (mm, 'CustomCVForce')):
-        if not hasattr(module, name):
-            setattr(module, name, type(name, (object,), {}))
-    sys.modules['simtk'] = simtk
-    sys.modules['simtk.openmm'] = mm
-    sys.modules['simtk.openmm.app'] = app
-    sys.modules['simtk.unit'] = unit
-    if not hasattr(np, 'int'):
-        np.int = int
-    sys.path.insert(0, os.path.join(REFERENCE, 'src'))
-    import sympy
-    from sympy.parsing import sympy_parser
-    original = sympy_parser.parse_expr
-
-    def safe_parse(text, *args, **kwargs):
-        import re
-        names = set(re.findall(r'[A-Za-z_][A-Za-z_0-9]*', text))
-        local = {n: sympy.Symbol(n) for n in names
-                 if n not in ('sqrt', 'exp', 'log', 'sin', 'cos', 'erf', 'erfc', 'step', 'select', 'deriv')}
-        kwargs.setdefault('local_dict', local)
-        return original(text, *args, **kwargs)
-    sympy_parser.parse_expr = safe_parse
-    import atomsmm
-    atomsmm.integrators.parse_expr = safe_parse
-    if hasattr(atomsmm.systems, 'parse_expr'):
-        atomsmm.systems.parse_expr = safe_parse
-    return atomsmm
+    """The product's own entry point for code written against simtk.openmm (atomsmm_b200/compat.py)."""
+    from atomsmm_b200 import compat
+    return compat.install(os.path.join(REFERENCE, 'src'))
 
 
 if __name__ == '__main__':

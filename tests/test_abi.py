@@ -80,3 +80,18 @@ def test_hilbert_order_keeps_groups_compact():
     # adjacent cells along the curve: a small step in space
     a = engine.hilbert_index([0.01, 0.01, 0.01], box)
     assert isinstance(a, int) and engine.hilbert_index([0.01 + 2.5, 0.01, 0.01 - 2.5], box) == a   # periodic
+
+
+def test_barostat_random_stream_is_the_oracles():
+    """b2_barostat_uniform (pure host function) and the oracle interpreter's restatement of SplitMix64 agree
+    bit for bit: the basis of replaying the engine's accept / reject sequence in float64."""
+    import ctypes
+    from atomsmm_b200 import engine
+    from oracle import interp
+    lib = engine.library()
+    for seed in (0, 1, 77, 2**63 + 12345):
+        for counter in (0, 1, 2, 1000, 2**40):
+            out = ctypes.c_double()
+            assert lib.b2_barostat_uniform(seed, counter, ctypes.byref(out)) == 0
+            assert out.value == interp.Interpreter.barostat_uniform(seed, counter)
+            assert 0.0 <= out.value < 1.0
