@@ -24,14 +24,18 @@ struct BondArgs {
     const double* consts;
 };
 
+// Forces go through a 64-bit fixed-point accumulator per degree of freedom (2^-32 kJ/mol/nm): integer
+// addition is associative, so the result does not depend on the order in which the terms of an atom arrive
+// (float atomics would make trajectories irreproducible); k_fixed_to_force adds the sums to the fp32 buffer.
+#define B2_FIXED_SCALE 4294967296.0
 struct GlobalGeo {
     const double* x;
-    float4* out;
+    unsigned long long* acc;     // [n][3]
     __device__ __forceinline__ double pos(int i, int k) const { return x[3*i+k]; }
     __device__ __forceinline__ void add(int i, double fx, double fy, double fz) const {
-        atomicAdd(&out[i].x, (float)fx);
-        atomicAdd(&out[i].y, (float)fy);
-        atomicAdd(&out[i].z, (float)fz);
+        atomicAdd(&acc[3*(size_t)i], (unsigned long long)__double2ll_rn(fx*B2_FIXED_SCALE));
+        atomicAdd(&acc[3*(size_t)i+1], (unsigned long long)__double2ll_rn(fy*B2_FIXED_SCALE));
+        atomicAdd(&acc[3*(size_t)i+2], (unsigned long long)__double2ll_rn(fz*B2_FIXED_SCALE));
     }
 };
 
@@ -47,9 +51,7 @@ struct GlobalGeo64 {
     }
 };
 
-// Forces are accumulated in 64-bit fixed point (2^-32 kJ/mol/nm resolution): integer addition is
-// associative, so the sum does not depend on the order in which threads arrive -- bit-reproducible.
-#define B2_FIXED_SCALE 4294967296.0
+// the same fixed-point accumulation in shared memory (fused inner loop)
 struct LocalGeo {
     const double* xs;            // [chunk][3] shared memory
     unsigned long long* fs;      // [chunk][3] shared memory, fixed point

@@ -90,13 +90,15 @@ struct b2_context {
     int n = 0, ngroups = 0;
     double box[3] = {0, 0, 0};
     int periodic = 1;
-    double skin = 0.1;
+    double skin = 0.15;           // measured optimum on B200 for RESPA water (profiles/round2_skin_sweep.txt)
     std::vector<double> h_mass;
     std::vector<int> h_mol;
+    std::vector<int> h_mol_ptr, h_mol_atoms;      // molecules in caller order (CSR), built once
     std::vector<std::vector<double>> h_sets;      // each 3*n: q, sigma, eps
     std::vector<int> h_excl;                      // pairs
     std::vector<PairForce> pair_forces;
     std::vector<BondedForce> bonded_forces;
+    unsigned long long* bond_acc = nullptr;       // [n][3] fixed-point force accumulators of the explicit-list kernels
     std::vector<PmeForce> pme_forces;
     bool excl_far = false;                        // some exclusion spans > 31 in index
     int excl_span = 0;                            // largest distance in the engine's order between excluded atoms

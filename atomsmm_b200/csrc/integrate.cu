@@ -12,7 +12,10 @@
 //   * the whole step is captured once into a CUDA graph and replayed.
 #include <math.h>
 
+#include <stdio.h>
+
 #include <algorithm>
+#include <chrono>
 
 #include "bonded.cuh"
 #include "dd.cuh"
@@ -827,9 +830,16 @@ int program_run(b2_context* ctx, int nsteps) {
     for (int done = 0; done < nsteps; done++) {
         if (order_period > 0 && ++ctx->steps_since_order_check >= order_period) {
             ctx->steps_since_order_check = 0;
+            static const bool timing = getenv("B2_DEBUG_TIMING") != nullptr;
+            const auto t0 = std::chrono::steady_clock::now();
             B2_TRY(order_refresh(ctx));          // may re-sort: chunks, clusters and the graph are rebuilt
+            const auto t1 = std::chrono::steady_clock::now();
             B2_TRY(inner_prepare(ctx));
             B2_TRY(con_prepare(ctx));
+            if (timing)
+                fprintf(stderr, "[b2 order check] refresh %.2f ms, chunk/cluster tables %.2f ms\n",
+                        std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
         }
         B2_TRY(dist_before_move(ctx));
         if (ctx->baro_on && has_update_state && ++ctx->baro_steps >= ctx->baro_frequency) {

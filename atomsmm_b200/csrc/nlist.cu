@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     if (warp >= ngroups) return;
-    __shared__ float sxi[NL_WARPS][B2_GROUP][3];
+    __shared__ float4 sxi[NL_WARPS][B2_GROUP];       // one 16-byte broadcast read per i-atom in the sweep
     __shared__ int soi[NL_WARPS][B2_GROUP];
     __shared__ unsigned long long smask[NL_WARPS][B2_GROUP];
     __shared__ float4 queue[NL_WARPS][NL_QUEUE];
@@ -284,8 +284,7 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
     const float box[3] = {(float)g.box[0], (float)g.box[1], (float)g.box[2]};
     const float ibox[3] = {(float)g.inv[0], (float)g.inv[1], (float)g.inv[2]};
     if (lane < B2_GROUP) {
-        const float4 p = prel[i0 + lane];
-        sxi[wib][lane][0] = p.x; sxi[wib][lane][1] = p.y; sxi[wib][lane][2] = p.z;
+        sxi[wib][lane] = prel[i0 + lane];
         const int i = i0 + lane;
         soi[wib][lane] = i < n ? orig[i] : -1;
         smask[wib][lane] = i < n ? exmask[i] : 0ull;
@@ -351,7 +350,8 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
                 const float xj = e.x + pj.x, yj = e.y + pj.y, zj = e.z + pj.z;
 #pragma unroll
                 for (int k = 0; k < B2_GROUP; k++) {
-                    float dx = xj - sxi[wib][k][0], dy = yj - sxi[wib][k][1], dz = zj - sxi[wib][k][2];
+                    const float4 pi = sxi[wib][k];
+                    float dx = xj - pi.x, dy = yj - pi.y, dz = zj - pi.z;
                     if (MI) {
                         if (all[0] || wide) dx -= box[0]*rintf(dx*ibox[0]);
                         if (all[1] || wide) dy -= box[1]*rintf(dy*ibox[1]);

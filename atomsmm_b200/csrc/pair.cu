@@ -231,8 +231,8 @@ __global__ void __launch_bounds__(32*WPB, 8) k_pair_force(int n, int g_lo, int n
 // scheduling, so the contributions are NOT added to the fp32 force buffer one by one (float addition
 // does not commute with re-ordering): every touched atom gets ONE fixed-point accumulator (claimed
 // by the first entry that reaches it; which entry wins only names the accumulator), all entries add
-// into it with 64-bit integer atomics -- associative, hence independent of the order -- and the last
-// block to finish adds every accumulator to the atom's force exactly once and cleans up.
+// into it with 64-bit integer atomics -- associative, hence independent of the order -- and a second
+// kernel adds every accumulator to the atom's force exactly once and cleans up.
 #define B2_BAND_SCALE 4294967296.0
 template <class POTD>
 __global__ void k_pair_band(const double* __restrict__ x, const double* __restrict__ pard, BandBuffer bb, POTD pot,
@@ -258,28 +258,23 @@ __global__ void k_pair_band(const double* __restrict__ x, const double* __restri
             atomicAdd(a + 2, (unsigned long long)__double2ll_rn(fr*dz*B2_BAND_SCALE));
         }
     }
-    __shared__ bool last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        last = atomicAdd(bb.ticket, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    for (unsigned k = threadIdx.x; k < total; k += blockDim.x) {
+}
+
+// second half of the settlement: every accumulator is added to its atom's force exactly once, then cleaned
+__global__ void k_pair_band_apply(BandBuffer bb, float4* __restrict__ out) {
+    const unsigned total = min(*bb.count, bb.capacity);
+    for (unsigned k = blockIdx.x*blockDim.x + threadIdx.x; k < total; k += gridDim.x*blockDim.x) {
         const int i = bb.pairs[2*k];
-        if (__ldcg(&bb.slot[i]) != (int)k) continue;          // not the entry that owns atom i's accumulator
+        if (bb.slot[i] != (int)k) continue;                   // not the entry that owns atom i's accumulator
         long long* a = bb.acc + 3*(size_t)k;
-        const double fx = (double)__ldcg(&a[0])*(1.0/B2_BAND_SCALE), fy = (double)__ldcg(&a[1])*(1.0/B2_BAND_SCALE),
-                     fz = (double)__ldcg(&a[2])*(1.0/B2_BAND_SCALE);
+        const double fx = (double)a[0]*(1.0/B2_BAND_SCALE), fy = (double)a[1]*(1.0/B2_BAND_SCALE),
+                     fz = (double)a[2]*(1.0/B2_BAND_SCALE);
         float4 f = out[i];
         f.x += (float)fx; f.y += (float)fy; f.z += (float)fz;
         out[i] = f;
         a[0] = 0; a[1] = 0; a[2] = 0;
         bb.slot[i] = -1;
     }
-    if (threadIdx.x == 0) *bb.ticket = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -469,8 +464,12 @@ static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, POTD potd
     }
     ctx->counters[2]++;
     B2_LAUNCH_CHECK();
-    k_pair_band<POTD><<<8, 128, 0, stream>>>(ctx->x, ctx->pard[pf.set], bb, potd, rcd*rcd, ctx->box[0],
-                                                  ctx->box[1], ctx->box[2], out);
+    // ~2e-3 band pairs per atom: one thread each, at least 8 blocks
+    const int band_blocks = std::min(296, std::max(8, ctx->n/16384));
+    k_pair_band<POTD><<<band_blocks, 128, 0, stream>>>(ctx->x, ctx->pard[pf.set], bb, potd, rcd*rcd, ctx->box[0],
+                                                      ctx->box[1], ctx->box[2], out);
+    B2_LAUNCH_CHECK();
+    k_pair_band_apply<<<band_blocks, 128, 0, stream>>>(bb, out);
     B2_LAUNCH_CHECK();
     return B2_OK;
 }

@@ -247,7 +247,7 @@ class State(object):
 
 class Context(object):
     """Execution context on one B200.  ``properties``: 'DeviceIndex' (default 0 or LOCAL_RANK),
-    'Skin' (neighbour-list skin in nm, default 0.1), 'FastPaths' ('false' routes every per-DOF step
+    'Skin' (neighbour-list skin in nm, default 0.15), 'FastPaths' ('false' routes every per-DOF step
     through the generic VM), 'Precision' ('mixed', the default: State forces are the fp32-tile forces the
     integrator uses; 'double': getState evaluates and accumulates every force contribution in float64 --
     report cadence only, time stepping is always mixed precision), 'DomainDecomposition' ('true': the ranks of the initialised
@@ -273,7 +273,7 @@ class Context(object):
         self._check(self._lib.b2_create(index, ctypes.byref(self._handle)), None)
         self._stream = torch.cuda.Stream(device=self._device)
         self._call('b2_set_stream', c_void(self._stream.cuda_stream))
-        self._skin = float(properties.get('Skin', 0.1))
+        self._skin = float(properties.get('Skin', 0.15))
         self._fast = str(properties.get('FastPaths', 'true')).lower() != 'false'
         precision = str(properties.get('Precision', 'mixed')).lower()
         if precision not in ('mixed', 'double'):

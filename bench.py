@@ -368,6 +368,8 @@ def main():
     dd = world > 1 and not args.replicas
     integrator.setRandomNumberSeed(1 if dd else 1 + rank)
     properties = {'DeviceIndex': local}
+    if os.environ.get('B2_SKIN'):
+        properties['Skin'] = float(os.environ['B2_SKIN'])       # neighbour-list skin sweep
     if dd:
         properties['DomainDecomposition'] = 'true'
     context = mm.Context(system, integrator, mm.Platform.getPlatformByName('B200'), properties)

@@ -195,4 +195,4 @@ def test_long_run_refreshes_the_spatial_order(cuda_platform):
     context._call('b2_get_counters', out)
     assert out[7] >= 1000000                             # at least one re-ordering happened
     stats = context.list_stats()
-    assert stats['largest_list'] < 1800
+    assert stats['largest_list'] < 2300

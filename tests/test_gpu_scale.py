@@ -55,8 +55,8 @@ def test_config2_first_frame_against_c_oracle(cuda_platform):
     # the far list of this box: ~204 pairs per atom within 1.0 nm, the near one ~69 within 0.7 nm
     far = next(f for f in pair_forces if f.getForceGroup() == 2)
     near = next(f for f in pair_forces if f.getForceGroup() == 1)
-    assert 190 < 2*port.pair_set(pos, far)[0]/98304 < 215
-    assert 60 < 2*port.pair_set(pos, near)[0]/98304 < 75
+    assert 190 < port.pair_set(pos, far)[0]/98304 < 215
+    assert 60 < port.pair_set(pos, near)[0]/98304 < 75
 
 
 def test_config2_after_dynamics_against_c_oracle(cuda_platform):
