@@ -88,7 +88,9 @@ __device__ __forceinline__ void block_accumulate(double e, double w, double* acc
 }
 
 // two-body families: E(r); force from dE/dr
-template <bool FORCE, bool ENERGY, class GEO>
+// CUSTOM = false compiles the bytecode interpreter of CustomBondForce / CustomAngleForce terms out (the fused
+// inner loop of systems without such terms: no evaluation stack in local memory, fewer registers)
+template <bool FORCE, bool ENERGY, bool CUSTOM = true, class GEO>
 __device__ __forceinline__ void term_bond2(const BondArgs& a, int t, const GEO& geo, double& e, double& w) {
     {
         const int i = a.inv[a.atoms[2*t]], j = a.inv[a.atoms[2*t+1]];
@@ -114,7 +116,7 @@ __device__ __forceinline__ void term_bond2(const BondArgs& a, int t, const GEO& 
                 e -= kq*er/r;
                 dedr -= kq*(2*al/sqrt(M_PI)*exp(-al*al*r2)/r - er/r2);
             }
-        } else {
+        } else if constexpr (CUSTOM) {
             double vars[10];
             vars[0] = r;
             for (int k = 0; k < a.stride && k < 9; k++) vars[1+k] = p[k];
@@ -130,7 +132,7 @@ __device__ __forceinline__ void term_bond2(const BondArgs& a, int t, const GEO& 
     }
 }
 
-template <bool FORCE, bool ENERGY, class GEO>
+template <bool FORCE, bool ENERGY, bool CUSTOM = true, class GEO>
 __device__ __forceinline__ void term_angle(const BondArgs& a, int t, const GEO& geo, double& e) {
     {
         const int i = a.inv[a.atoms[3*t]], j = a.inv[a.atoms[3*t+1]], k = a.inv[a.atoms[3*t+2]];
@@ -144,12 +146,12 @@ __device__ __forceinline__ void term_angle(const BondArgs& a, int t, const GEO& 
         double c = (u[0]*v[0] + u[1]*v[1] + u[2]*v[2])/(ru*rv);
         c = fmin(1.0, fmax(-1.0, c));
         const double theta = acos(c);
-        double dedt;
+        double dedt = 0;
         if (a.family == B2_ANGLE_HARMONIC) {
             const double dt = theta - p[0];
             e = 0.5*p[1]*dt*dt;
             dedt = p[1]*dt;
-        } else {
+        } else if constexpr (CUSTOM) {
             double vars[10];
             vars[0] = theta;
             for (int q = 0; q < a.stride && q < 9; q++) vars[1+q] = p[q];

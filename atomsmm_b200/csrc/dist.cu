@@ -229,17 +229,32 @@ __global__ void __launch_bounds__(256) k_dd_pull(DDPeers P, unsigned long long* 
     __syncthreads();
     const long long stride = (long long)gridDim.x*blockDim.x;
     const long long first = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-    // one thread per atom: 24 B read from the owner, master copy and fixed-point copy written locally
-    const long long total = s_flag ? (long long)n : (long long)B2_GROUP*(*halo_count);
+    // one thread per PAIR of consecutive atoms (48 B = three 16-byte peer loads when both belong to the same
+    // foreign owner, which is the case except at ownership boundaries); master copy and fixed-point copy are
+    // written locally.  Halo mode walks the pull list (groups of 8 atoms), rebuild mode all atoms.
+    const long long total = s_flag ? (long long)((n + 1)/2) : (long long)(B2_GROUP/2)*(*halo_count);
     for (long long t = first; t < total; t += stride) {
-        const int a = s_flag ? (int)t : halo_groups[t/B2_GROUP]*B2_GROUP + (int)(t % B2_GROUP);
-        if (a >= n) continue;
-        const int o = dd_owner(P, a);
-        if (o == P.rank) continue;
-        const double* src = P.x[o] + 3ll*a;
-        const double px = __ldcg(src), py = __ldcg(src + 1), pz = __ldcg(src + 2);
-        x[3ll*a] = px; x[3ll*a+1] = py; x[3ll*a+2] = pz;
-        xq[a] = make_int4(b2_to_fixed(px, sx), b2_to_fixed(py, sy), b2_to_fixed(pz, sz), 0);
+        const int a0 = s_flag ? (int)(2*t) : halo_groups[t/(B2_GROUP/2)]*B2_GROUP + 2*(int)(t % (B2_GROUP/2));
+        if (a0 >= n) continue;
+        const int o0 = dd_owner(P, a0);
+        const int o1 = a0 + 1 < n ? dd_owner(P, a0 + 1) : P.rank;
+        if (o0 == o1 && o0 != P.rank) {
+            const double2* src = reinterpret_cast<const double2*>(P.x[o0] + 3ll*a0);     // a0 even: 16-byte aligned
+            const double2 u = __ldcg(src), v = __ldcg(src + 1), w = __ldcg(src + 2);
+            double2* dst = reinterpret_cast<double2*>(x + 3ll*a0);
+            dst[0] = u; dst[1] = v; dst[2] = w;
+            xq[a0] = make_int4(b2_to_fixed(u.x, sx), b2_to_fixed(u.y, sy), b2_to_fixed(v.x, sz), 0);
+            xq[a0 + 1] = make_int4(b2_to_fixed(v.y, sx), b2_to_fixed(w.x, sy), b2_to_fixed(w.y, sz), 0);
+            continue;
+        }
+        for (int k = 0; k < 2; k++) {
+            const int a = a0 + k, o = k ? o1 : o0;
+            if (a >= n || o == P.rank) continue;
+            const double* src = P.x[o] + 3ll*a;
+            const double px = __ldcg(src), py = __ldcg(src + 1), pz = __ldcg(src + 2);
+            x[3ll*a] = px; x[3ll*a+1] = py; x[3ll*a+2] = pz;
+            xq[a] = make_int4(b2_to_fixed(px, sx), b2_to_fixed(py, sy), b2_to_fixed(pz, sz), 0);
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -292,7 +292,8 @@ struct InnerArgs {
     int batch_of[B2_INNER_MAX_FORCES];   // bonded-force index -> entry of a[] or -1
 };
 
-__global__ void __launch_bounds__(B2_CHUNK) k_inner(const int* __restrict__ chunk_start,
+template <bool CUSTOM>
+__global__ void __launch_bounds__(B2_CHUNK, 5) k_inner(const int* __restrict__ chunk_start,
                                                     const int* __restrict__ term_ptr,
                                                     const int2* __restrict__ terms, double* __restrict__ xg,
                                                     double* __restrict__ vg, const double* __restrict__ mass,
@@ -350,8 +351,8 @@ __global__ void __launch_bounds__(B2_CHUNK) k_inner(const int* __restrict__ chun
                 const int b = A.batch_of[rec.x];
                 if (b < 0) continue;
                 double e = 0, w = 0;
-                if (A.arity[b] == 2) term_bond2<true, false>(A.a[b], rec.y, geo, e, w);
-                else if (A.arity[b] == 3) term_angle<true, false>(A.a[b], rec.y, geo, e);
+                if (A.arity[b] == 2) term_bond2<true, false, CUSTOM>(A.a[b], rec.y, geo, e, w);
+                else if (A.arity[b] == 3) term_angle<true, false, CUSTOM>(A.a[b], rec.y, geo, e);
                 else term_torsion<true, false>(A.a[b], rec.y, geo, e);
             }
             __syncthreads();
@@ -652,9 +653,18 @@ static int try_fused_run(b2_context* ctx, size_t k, int* consumed) {
     for (int g = 0; g < B2_FSLOTS; g++) A.f[g] = ctx->fbuf[g];
     A.write_force = local_valid == version ? 1 : 0;
     B2_TRY(dist_before_move(ctx));
-    k_inner<<<ctx->nchunks, B2_CHUNK, 0, ctx->stream>>>(ctx->chunk_start, ctx->chunk_term_ptr, ctx->chunk_terms,
-                                                        ctx->x, ctx->v, ctx->massd, ctx->globals,
-                                                        ctx->fbuf[A.local_slot], A);
+    bool custom = false;
+    for (size_t f = 0; f < ctx->bonded_forces.size(); f++)
+        if (A.batch_of[f] >= 0 && (ctx->bonded_forces[f].family == B2_BOND_CUSTOM || ctx->bonded_forces[f].family == B2_ANGLE_CUSTOM))
+            custom = true;
+    if (custom)
+        k_inner<true><<<ctx->nchunks, B2_CHUNK, 0, ctx->stream>>>(ctx->chunk_start, ctx->chunk_term_ptr, ctx->chunk_terms,
+                                                                  ctx->x, ctx->v, ctx->massd, ctx->globals,
+                                                                  ctx->fbuf[A.local_slot], A);
+    else
+        k_inner<false><<<ctx->nchunks, B2_CHUNK, 0, ctx->stream>>>(ctx->chunk_start, ctx->chunk_term_ptr, ctx->chunk_terms,
+                                                                   ctx->x, ctx->v, ctx->massd, ctx->globals,
+                                                                   ctx->fbuf[A.local_slot], A);
     B2_LAUNCH_CHECK();
     ctx->pos_version = version;
     if (A.write_force) ctx->fvalid[A.local_slot] = version;

@@ -120,24 +120,40 @@ __global__ void k_group_geom(int n, int ngroups, const double* __restrict__ x, G
         c[d] = (float)cw;
         cell[d] = min(max((int)(cw*g.cs_inv[d]), 0), g.nc[d] - 1);
     }
-    if (!live) return;
-    prel[grp*B2_GROUP + a] = make_float4((float)u[0], (float)u[1], (float)u[2], 0.f);
-    if (a == 0) {
-        gcen[grp] = make_float4(c[0], c[1], c[2], 0.f);
-        ghalf[grp] = make_float4(h[0], h[1], h[2], 0.f);
-        // "fat" groups (atoms of molecules that have drifted apart, or a large molecule) stay out of
-        // the cells: every i-group tests them directly, so they do not inflate everybody's search region
-        if (fmaxf(h[0], fmaxf(h[1], h[2])) > fat_limit) {
-            gcell[grp] = -1;
-            const int slot = atomicAdd(&flags[11], 1);       // arrival order; sorted by k_cell_scan
-            if (slot < fat_capacity) fat_list[slot] = grp;
-        } else {
-            const int cidx = (cell[2]*g.nc[1] + cell[1])*g.nc[0] + cell[0];
-            gcell[grp] = cidx;
-            atomicAdd(&cell_count[cidx], 1);
-#pragma unroll
-            for (int d = 0; d < 3; d++) atomicMax(&hmax_bits[d], __float_as_int(h[d]));   // h > 0: int order = float order
+    float hm[3] = {0.f, 0.f, 0.f};          // half extents of this thread's group if it goes into the grid
+    if (live) {
+        prel[grp*B2_GROUP + a] = make_float4((float)u[0], (float)u[1], (float)u[2], 0.f);
+        if (a == 0) {
+            gcen[grp] = make_float4(c[0], c[1], c[2], 0.f);
+            ghalf[grp] = make_float4(h[0], h[1], h[2], 0.f);
+            // "fat" groups (atoms of molecules that have drifted apart, or a large molecule) stay out of the
+            // cells: every i-group tests them directly, so they do not inflate everybody's search region
+            if (fmaxf(h[0], fmaxf(h[1], h[2])) > fat_limit) {
+                gcell[grp] = -1;
+                const int slot = atomicAdd(&flags[11], 1);       // arrival order; sorted by k_cell_scan
+                if (slot < fat_capacity) fat_list[slot] = grp;
+            } else {
+                const int cidx = (cell[2]*g.nc[1] + cell[1])*g.nc[0] + cell[0];
+                gcell[grp] = cidx;
+                atomicAdd(&cell_count[cidx], 1);
+                hm[0] = h[0]; hm[1] = h[1]; hm[2] = h[2];
+            }
         }
+    }
+    // largest half extent of any gridded group: reduced over the block first (one atomic per block and
+    // axis instead of one per group -- 1.6 M atomics on three addresses at 4.2 M atoms)
+    __shared__ float smax[8][3];
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hm[d] = fmaxf(hm[d], __shfl_xor_sync(FULL, hm[d], o));
+    if (lane == 0)
+        for (int d = 0; d < 3; d++) smax[threadIdx.x >> 5][d] = hm[d];
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float m = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, smax[w][threadIdx.x]);
+        if (m > 0.f) atomicMax(&hmax_bits[threadIdx.x], __float_as_int(m));   // m > 0: int order = float order
     }
 }
 
@@ -172,16 +188,16 @@ __global__ void k_cell_scan(int ncells, int* cell_count, int* cell_start, int ng
     // case that there are more than the block can sort, fall back to a compaction pass over all groups.
     const int nfat = flags[11];
     if (nfat <= 2*(int)blockDim.x) {
+        // rank sort in shared memory (keys are distinct group ids): position = number of smaller keys
         __shared__ int keys[2048];
-        for (int k = t; k < 2*(int)blockDim.x; k += blockDim.x) keys[k] = k < nfat ? fat_list[k] : 0x7fffffff;
+        for (int k = t; k < nfat; k += blockDim.x) keys[k] = fat_list[k];
         __syncthreads();
-        const int rounds = nfat;
-        for (int r = 0; r < rounds; r++) {
-            const int i = 2*t + (r & 1);
-            if (i + 1 < 2*(int)blockDim.x && keys[i] > keys[i+1]) { const int tmp = keys[i]; keys[i] = keys[i+1]; keys[i+1] = tmp; }
-            __syncthreads();
+        for (int k = t; k < nfat; k += blockDim.x) {
+            const int key = keys[k];
+            int rank = 0;
+            for (int m = 0; m < nfat; m++) rank += keys[m] < key ? 1 : 0;
+            fat_list[rank] = key;
         }
-        for (int k = t; k < nfat; k += blockDim.x) fat_list[k] = keys[k];
         if (t == 0) { flags[8] = nfat; flags[11] = 0; }
         return;
     }
