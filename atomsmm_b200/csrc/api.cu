@@ -735,6 +735,7 @@ int order_refresh(b2_context* ctx) {
 
 extern "C" int b2_set_velocities(b2_context* ctx, const double* v_dev) {
     if (!ctx || !ctx->have_order) return b2_fail(ctx, B2_ERR_STATE, "set positions before velocities");
+    ctx->v_version++;
     return state_permute_to_sorted(ctx, v_dev, ctx->v);
 }
 
@@ -893,6 +894,7 @@ extern "C" int b2_load_program(b2_context* ctx, const int* ops, int nops, const 
     unsigned long long st[4] = {seed, 0ull, 0ull, 0ull};
     B2_CUDA(cudaMemcpy(ctx->rng_state, st, sizeof(st), cudaMemcpyHostToDevice));
     ctx->program_loaded = true;
+    ctx->mvv_index = -1; ctx->mvv_version = -1;
     ctx->eager_steps = 0;
     ctx->prologue_valid = false;
     ctx->uses_random = false;
@@ -905,6 +907,7 @@ extern "C" int b2_set_globals(b2_context* ctx, int first, int count, const doubl
     if (!ctx || first < 0 || first + count > ctx->nglobals) return b2_fail(ctx, B2_ERR_ARG, "global index out of range");
     B2_CUDA(cudaMemcpyAsync(ctx->globals + first, values_host, sizeof(double)*count, cudaMemcpyHostToDevice, ctx->stream));
     B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->mvv_version = -1;               // the caller may have overwritten the carried sum(m v.v)
     if (ctx->prologue_valid) {           // coefficients derived from globals must be recomputed
         ctx->prologue_valid = false;
         program_release(ctx);

@@ -120,6 +120,12 @@ struct b2_context {
     long long fvalid[B2_FSLOTS];                  // position version for which fbuf[g] is valid
     long long pos_version = 1;
     long long deriv_version = -1;                 // position version the parameter derivatives belong to
+    // sum(m v.v) carried across velocity rescalings: v_version counts modifications of v; when mvv_version ==
+    // v_version, globals[mvv_index] holds the sum of the CURRENT velocities (after v <- s v it is s^2 times
+    // its old value), so a thermostat block that follows another one -- also across the step boundary --
+    // needs neither a sweep over v nor, with several ranks, a reduction
+    long long v_version = 1, mvv_version = -1;
+    int mvv_index = -1, mvv_factor_hint = -1;     // hint: B2_OP_MVV_FACTOR seen right before the current op
     std::vector<double*> perdof;
     double* scratch3 = nullptr;                   // [n][3] staging for permuted copies
     std::vector<double*> carry_tmp;               // staging of v / per-DOF variables across a re-ordering
@@ -222,6 +228,8 @@ struct b2_context {
     long long graph_dpos = 0;
     unsigned long long graph_entry_mask = 0, graph_exit_mask = 0;
     bool graph_entry_synced = true, graph_exit_synced = true;   // replicated positions consistent on all ranks
+    bool graph_entry_mvv = false, graph_exit_mvv = false;       // carried sum(m v.v) valid at entry / exit of the graph
+    long long graph_dv = 0;
 };
 
 // position -> 32-bit fixed-point fraction of the box (scale = 2^32 / L); wraps like the periodic box

@@ -35,6 +35,9 @@ static PerDofTable make_table(b2_context* ctx) {
 
 __global__ void k_step_begin(unsigned long long* rng_state) { rng_state[2] += 1ull; }
 
+// after v <- s v the carried sum(m v.v) is s^2 times its old value
+__global__ void k_mvv_rescale(double* globals, int mvv, int factor) { globals[mvv] *= globals[factor]*globals[factor]; }
+
 __global__ void k_fold_derivatives(double* e) { e[64] += e[74]; e[65] += e[75]; }
 
 __global__ void k_perdof(int dof_lo, int dof_hi, PerDofTable tab, int target, const int* __restrict__ code, int len,
@@ -293,7 +296,7 @@ struct InnerArgs {
 };
 
 template <bool CUSTOM>
-__global__ void __launch_bounds__(B2_CHUNK, 5) k_inner(const int* __restrict__ chunk_start,
+__global__ void __launch_bounds__(B2_CHUNK, 6) k_inner(const int* __restrict__ chunk_start,
                                                     const int* __restrict__ term_ptr,
                                                     const int2* __restrict__ terms, double* __restrict__ xg,
                                                     double* __restrict__ vg, const double* __restrict__ mass,
@@ -552,6 +555,18 @@ static int launch_vel(b2_context* ctx, const b2_op& op) {
     B2_TRY(fill_kick(ctx, op, ka));
     if (op.c >= 0) B2_TRY(dist_before_move(ctx));
     cudaStream_t s = ctx->stream;
+    static const bool carry_allowed = getenv("B2_NO_MVV_CARRY") == nullptr;
+    const bool changes_v = ka.nterms > 0 || ka.prescale >= 0;
+    // (a) a pure "sum(m v.v), then the scalar program" block whose sum is already known: only the program runs
+    if (carry_allowed && ka.mvv >= 0 && !changes_v && ka.drift < 0 && ka.mvv == ctx->mvv_index &&
+        ctx->mvv_version == ctx->v_version) {
+        if (op.g > 0) {
+            k_global<<<1, 64, 0, s>>>(ctx->code + op.f, op.g, ctx->consts, ctx->nconsts, ctx->globals,
+                                       ctx->nglobals, ctx->rng_state, ctx->d_energy, 0);
+            B2_LAUNCH_CHECK();
+        }
+        return B2_OK;
+    }
     // with several ranks the sum must be all-reduced before the scalar program may consume it
     const bool split = ctx->nranks > 1 && ka.mvv >= 0;
     if (split) ka.code_len = 0;
@@ -582,6 +597,19 @@ static int launch_vel(b2_context* ctx, const b2_op& op) {
     }
     if (split) phase_mark(ctx, B2_PHASE_INTEGRATE);
     if (op.c >= 0) ctx->pos_version++;
+    // bookkeeping of the carried sum
+    const bool was_valid = ctx->mvv_index >= 0 && ctx->mvv_version == ctx->v_version;
+    if (changes_v) ctx->v_version++;
+    if (ka.mvv >= 0) {                                   // the kernel summed the NEW velocities
+        ctx->mvv_index = ka.mvv;
+        ctx->mvv_version = ctx->v_version;
+    } else if (carry_allowed && was_valid && ka.nterms == 0 && ka.prescale >= 0 && ctx->mvv_factor_hint >= 0) {
+        // (b) pure rescaling v <- s v announced by B2_OP_MVV_FACTOR: the carried sum follows
+        k_mvv_rescale<<<1, 1, 0, s>>>(ctx->globals, ctx->mvv_index, ctx->mvv_factor_hint);
+        B2_LAUNCH_CHECK();
+        ctx->mvv_version = ctx->v_version;
+    }
+    ctx->mvv_factor_hint = -1;
     return B2_OK;
 }
 
@@ -667,6 +695,7 @@ static int try_fused_run(b2_context* ctx, size_t k, int* consumed) {
                                                                    ctx->fbuf[A.local_slot], A);
     B2_LAUNCH_CHECK();
     ctx->pos_version = version;
+    ctx->v_version++;
     if (A.write_force) ctx->fvalid[A.local_slot] = version;
     *consumed = (int)(q - k);
     return B2_OK;
@@ -692,6 +721,7 @@ static int run_one_step(b2_context* ctx) {
         if (op.kind == B2_OP_CONSTRAIN_X) { B2_TRY(con_snapshot(ctx)); break; }
     for (size_t k = 0; k < ctx->ops.size(); k++) {
         const b2_op& op = ctx->ops[k];
+        if (k > 0 && ctx->ops[k-1].kind != B2_OP_MVV_FACTOR) ctx->mvv_factor_hint = -1;   // a hint lives for one op
         switch (op.kind) {
         case B2_OP_EVAL: {
             static const bool dual_allowed = getenv("B2_NO_DUAL") == nullptr;
@@ -721,6 +751,7 @@ static int run_one_step(b2_context* ctx) {
                                                       ctx->globals, ctx->rng_state, op.e, 0);
             B2_LAUNCH_CHECK();
             if (op.a == 0) ctx->pos_version++;
+            if (op.a == 1) ctx->v_version++;
             break;
         }
         case B2_OP_SUM: {
@@ -761,8 +792,12 @@ static int run_one_step(b2_context* ctx) {
         case B2_OP_SCALE:
             k_scale<<<std::max(1, (ndof + T - 1)/T), T, 0, s>>>(3*lo, 3*hi, ctx->v, ctx->globals, op.a);
             B2_LAUNCH_CHECK();
+            ctx->v_version++;
             break;
         case B2_OP_UPDATE_STATE:
+            break;
+        case B2_OP_MVV_FACTOR:
+            ctx->mvv_factor_hint = (op.a == ctx->mvv_index) ? op.b : -1;
             break;
         case B2_OP_CONSTRAIN_X:
             B2_TRY(dist_before_move(ctx));
@@ -770,6 +805,7 @@ static int run_one_step(b2_context* ctx) {
             break;
         case B2_OP_CONSTRAIN_V:
             B2_TRY(con_velocities(ctx));
+            ctx->v_version++;
             break;
         case B2_OP_INVALIDATE:
             for (int g = 0; g < B2_FSLOTS; g++) ctx->fvalid[g] = -1;
@@ -858,10 +894,13 @@ int program_run(b2_context* ctx, int nsteps) {
         }
         const unsigned long long entry = valid_mask(ctx);
         const bool synced = ctx->x_synced == ctx->pos_version;
+        const bool mvv_ok = ctx->mvv_index >= 0 && ctx->mvv_version == ctx->v_version;
         if (use_graph && ctx->graph_ready && (entry & ctx->graph_entry_mask) == ctx->graph_entry_mask &&
-            (synced || !ctx->graph_entry_synced)) {
+            (synced || !ctx->graph_entry_synced) && (mvv_ok || !ctx->graph_entry_mvv)) {
             B2_CUDA(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
             ctx->counters[5]++;
+            ctx->v_version += ctx->graph_dv;
+            if (ctx->graph_exit_mvv) ctx->mvv_version = ctx->v_version;
             ctx->pos_version += ctx->graph_dpos;
             if (ctx->graph_exit_synced) ctx->x_synced = ctx->pos_version;
             for (int g = 0; g < B2_FSLOTS; g++)
@@ -870,6 +909,7 @@ int program_run(b2_context* ctx, int nsteps) {
         }
         if (use_graph && !ctx->graph_ready && ctx->eager_steps >= 1) {
             const long long v0 = ctx->pos_version;
+            const long long vv0 = ctx->v_version;
             const long long launches0 = ctx->counters[0];
             B2_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
             const int r = run_one_step(ctx);
@@ -882,6 +922,9 @@ int program_run(b2_context* ctx, int nsteps) {
             if (e != cudaSuccess) return b2_fail(ctx, B2_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(e));
             ctx->graph_entry_mask = entry;
             ctx->graph_entry_synced = synced;
+            ctx->graph_entry_mvv = mvv_ok;
+            ctx->graph_exit_mvv = ctx->mvv_index >= 0 && ctx->mvv_version == ctx->v_version;
+            ctx->graph_dv = ctx->v_version - vv0;
             ctx->graph_exit_synced = ctx->x_synced == ctx->pos_version;
             ctx->graph_exit_mask = valid_mask(ctx);
             ctx->graph_dpos = ctx->pos_version - v0;

@@ -232,11 +232,27 @@ __global__ void __launch_bounds__(32*WPB, 8) k_pair_force(int n, int g_lo, int n
 // does not commute with re-ordering): every touched atom gets ONE fixed-point accumulator (claimed
 // by the first entry that reaches it; which entry wins only names the accumulator), all entries add
 // into it with 64-bit integer atomics -- associative, hence independent of the order -- and a second
-// kernel adds every accumulator to the atom's force exactly once and cleans up.
+// pass (the last block of the same kernel, or a kernel of its own for large systems) adds every accumulator to
+// the atom's force exactly once and cleans up.
 #define B2_BAND_SCALE 4294967296.0
+__device__ __forceinline__ void band_apply(const BandBuffer& bb, unsigned k, float4* __restrict__ out) {
+    const int i = bb.pairs[2*k];
+    if (__ldcg(&bb.slot[i]) != (int)k) return;                // not the entry that owns atom i's accumulator
+    long long* a = bb.acc + 3*(size_t)k;
+    const double fx = (double)__ldcg(&a[0])*(1.0/B2_BAND_SCALE), fy = (double)__ldcg(&a[1])*(1.0/B2_BAND_SCALE),
+                 fz = (double)__ldcg(&a[2])*(1.0/B2_BAND_SCALE);
+    float4 f = out[i];
+    f.x += (float)fx; f.y += (float)fy; f.z += (float)fz;
+    out[i] = f;
+    a[0] = 0; a[1] = 0; a[2] = 0;
+    bb.slot[i] = -1;
+}
+
+// fused_apply: the last block to finish also applies the accumulators (small systems: one launch instead of
+// two); large systems launch k_pair_band_apply over many blocks instead
 template <class POTD>
 __global__ void k_pair_band(const double* __restrict__ x, const double* __restrict__ pard, BandBuffer bb, POTD pot,
-                            double rc2d, double bx, double by, double bz, float4* __restrict__ out) {
+                            double rc2d, double bx, double by, double bz, float4* __restrict__ out, int fused_apply) {
     const unsigned found = *bb.count;
     const unsigned total = min(found, bb.capacity);
     if (found > bb.capacity && blockIdx.x == 0 && threadIdx.x == 0) bb.flags[10] = 1;   // reported by b2_synchronize
@@ -258,23 +274,24 @@ __global__ void k_pair_band(const double* __restrict__ x, const double* __restri
             atomicAdd(a + 2, (unsigned long long)__double2ll_rn(fr*dz*B2_BAND_SCALE));
         }
     }
+    if (!fused_apply) return;
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(bb.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (unsigned k = threadIdx.x; k < total; k += blockDim.x) band_apply(bb, k, out);
+    if (threadIdx.x == 0) *bb.ticket = 0;
 }
 
 // second half of the settlement: every accumulator is added to its atom's force exactly once, then cleaned
 __global__ void k_pair_band_apply(BandBuffer bb, float4* __restrict__ out) {
     const unsigned total = min(*bb.count, bb.capacity);
-    for (unsigned k = blockIdx.x*blockDim.x + threadIdx.x; k < total; k += gridDim.x*blockDim.x) {
-        const int i = bb.pairs[2*k];
-        if (bb.slot[i] != (int)k) continue;                   // not the entry that owns atom i's accumulator
-        long long* a = bb.acc + 3*(size_t)k;
-        const double fx = (double)a[0]*(1.0/B2_BAND_SCALE), fy = (double)a[1]*(1.0/B2_BAND_SCALE),
-                     fz = (double)a[2]*(1.0/B2_BAND_SCALE);
-        float4 f = out[i];
-        f.x += (float)fx; f.y += (float)fy; f.z += (float)fz;
-        out[i] = f;
-        a[0] = 0; a[1] = 0; a[2] = 0;
-        bb.slot[i] = -1;
-    }
+    for (unsigned k = blockIdx.x*blockDim.x + threadIdx.x; k < total; k += gridDim.x*blockDim.x) band_apply(bb, k, out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -465,12 +482,16 @@ static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, POTD potd
     ctx->counters[2]++;
     B2_LAUNCH_CHECK();
     // ~2e-3 band pairs per atom: one thread each, at least 8 blocks
-    const int band_blocks = std::min(296, std::max(8, ctx->n/16384));
+    const int owned = ctx->a_hi - ctx->a_lo;
+    const int band_blocks = std::min(296, std::max(8, owned/16384));
+    const bool fused_apply = owned < 400000;       // ~800 band pairs: the serial tail is shorter than a launch
     k_pair_band<POTD><<<band_blocks, 128, 0, stream>>>(ctx->x, ctx->pard[pf.set], bb, potd, rcd*rcd, ctx->box[0],
-                                                      ctx->box[1], ctx->box[2], out);
+                                                      ctx->box[1], ctx->box[2], out, fused_apply ? 1 : 0);
     B2_LAUNCH_CHECK();
-    k_pair_band_apply<<<band_blocks, 128, 0, stream>>>(bb, out);
-    B2_LAUNCH_CHECK();
+    if (!fused_apply) {
+        k_pair_band_apply<<<band_blocks, 128, 0, stream>>>(bb, out);
+        B2_LAUNCH_CHECK();
+    }
     return B2_OK;
 }
 

@@ -40,6 +40,10 @@ enum {
     // CustomIntegrator.addConstrainPositions / addConstrainVelocities (SHAKE / RATTLE, constraint.cu)
     B2_OP_CONSTRAIN_X = 12,
     B2_OP_CONSTRAIN_V = 13,
+    // hint: the NEXT op is a pure rescaling v <- s v after which  globals[a] * globals[b]^2  is the sum
+    // m v.v of the new velocities (a thermostat chain keeps every factor but the last in globals[a]): the engine
+    // carries the sum to the next thermostat block instead of sweeping v (and, with several ranks, reducing) again
+    B2_OP_MVV_FACTOR = 14,
 };
 
 // VM opcodes (two ints per instruction: opcode, argument)

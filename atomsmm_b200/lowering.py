@@ -26,7 +26,7 @@ from . import mm
 PAIR_NEAR, PAIR_DAMPED, PAIR_LJC, PAIR_LJ_VIRIAL, PAIR_SOFTCORE = 1, 2, 3, 4, 5
 BOND_HARMONIC, ANGLE_HARMONIC, TORSION_PERIODIC, BOND_LJC, BOND_CUSTOM, ANGLE_CUSTOM = 1, 2, 3, 4, 5, 6
 (OP_PERDOF, OP_SUM, OP_GLOBAL, OP_EVAL, OP_KICK, OP_DRIFT, OP_SCALE, OP_UPDATE_STATE, OP_ENERGY,
- OP_FUSED_INNER, OP_INVALIDATE, OP_CONSTRAIN_X, OP_CONSTRAIN_V) = range(1, 14)
+ OP_FUSED_INNER, OP_INVALIDATE, OP_CONSTRAIN_X, OP_CONSTRAIN_V, OP_MVV_FACTOR) = range(1, 15)
 ENERGY_SLOT_DLAMBDA_VDW, ENERGY_SLOT_DLAMBDA_COUL = 64, 65
 OP_WORDS = 8
 
@@ -857,11 +857,24 @@ def _chain_scale_blocks(P):
                 chain_head[6] = len(P.bc.code)
                 chain_head[7] = len(merged)//2
                 P.bc.code += merged
+                if op[1] == 0 and op[3] < 0 and op[5] < 0:
+                    # a pure rescaling closes the chain: X already contains every factor but this last one, so
+                    # after the kernel X*s*s is the sum of the new velocities -- the engine carries it to the
+                    # next thermostat block (also across the step boundary) instead of summing again
+                    out.append([OP_MVV_FACTOR, chain_head[5], op[4], 0, 0, 0, 0, 0])
             op[4] = vs
             product = None
             out.append(op)
             continue
         flush()
+        if kind == OP_KICK and op[1] == 0 and op[3] < 0 and op[4] >= 0 and op[5] < 0:
+            # unchained thermostat block: KICK(mvv -> X, program) ; v <- s v
+            for prev in reversed(out):
+                if prev[0] in (OP_EVAL, OP_UPDATE_STATE):
+                    continue
+                if prev[0] == OP_KICK and prev[5] >= 0:
+                    out.append([OP_MVV_FACTOR, prev[5], op[4], 0, 0, 0, 0, 0])
+                break
         out.append(op)
     flush()
     P.ops = out

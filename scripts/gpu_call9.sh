@@ -1,0 +1,19 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests -m gpu -q ) > gpurun_out/r2i_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/r2i_tests.log
+tail -8 gpurun_out/r2i_tests.log
+( time timeout 600 python bench.py --workload c2 --steps 5 --warmup 3 --no-cpu-baseline ) > gpurun_out/r2i_c2.json 2> gpurun_out/r2i_c2.err
+( time B2_NO_MVV_CARRY=1 timeout 600 python bench.py --workload c2 --steps 5 --warmup 3 --no-cpu-baseline --no-parity --no-e2e ) > gpurun_out/r2i_c2_nocarry.json 2> gpurun_out/r2i_c2_nocarry.err
+( time timeout 900 python bench.py --steps 4 --warmup 3 --no-cpu-baseline ) > gpurun_out/r2i_c5.json 2> gpurun_out/r2i_c5.err
+python - <<'PY'
+import json
+for f in ('r2i_c2', 'r2i_c2_nocarry', 'r2i_c5'):
+    try:
+        d = json.loads([l for l in open('gpurun_out/%s.json' % f) if l.startswith('{')][-1])
+        print(f, 'value %.4g' % d['value'], 'e2e', d['e2e'] and '%.4g' % d['e2e']['value'], 'kernels/step', d['engine']['kernels_per_md_step'],
+              d['roofline']['phases_ms_per_md_step'])
+    except Exception as e:
+        print(f, 'FAILED', e)
+PY

@@ -197,6 +197,8 @@ class Executor(object):
                     self.x = self.interp.shake(self.constraints(), self.mass, self.x, self.x_constrained)
                     self.x_constrained = self.x.copy()
                     self.version += 1
+                elif kind == L.OP_MVV_FACTOR:
+                    pass            # a hint for the engine's carried sum(m v.v); no effect on the state
                 elif kind == L.OP_CONSTRAIN_V:
                     self.v = self.interp.rattle(self.constraints(), self.mass, self.x, self.v)
                 else:
@@ -292,7 +294,7 @@ class DistributedExecutor(Executor):
                         self.globals[mvv] = self.all_reduced(self.mass[:, None]*self.v*self.v)
                         if clen > 0:
                             self.run_vm(cstart, clen)
-                elif kind == L.OP_UPDATE_STATE:
+                elif kind in (L.OP_UPDATE_STATE, L.OP_MVV_FACTOR):
                     pass
                 else:
                     raise NotImplementedError('op %d in the distributed executor' % kind)
