@@ -59,11 +59,14 @@ def build(force=False, verbose=False):
     with concurrent.futures.ThreadPoolExecutor(max_workers=8) as pool:
         objects = list(pool.map(lambda s: _compile(s, verbose), sources()))
     if _stale(LIBRARY, objects):
-        cmd = [NVCC, '-shared', '-o', LIBRARY] + objects + ['-gencode', 'arch=compute_100a,code=sm_100a',
+        # link under a temporary name and rename: a snapshot of the tree never sees a half-written library
+        staging = LIBRARY + '.tmp%d' % os.getpid()
+        cmd = [NVCC, '-shared', '-o', staging] + objects + ['-gencode', 'arch=compute_100a,code=sm_100a',
                                                             '-Xcompiler', '-fPIC', '-lcudart', '-lcufft']
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError('link failed:\n%s\n%s' % (proc.stdout, proc.stderr))
+        os.replace(staging, LIBRARY)
     return LIBRARY
 
 

@@ -57,10 +57,21 @@ struct LocalGeo {
     unsigned long long* fs;      // [chunk][3] shared memory, fixed point
     int base;                    // sorted index of the chunk's first atom
     __device__ __forceinline__ double pos(int i, int k) const { return xs[3*(i - base)+k]; }
+    // 64-bit integer atomics on shared memory compile to compare-and-swap loops; two native 32-bit adds with the
+    // carry of the low word forwarded to the high word give the same sum (every add contributes its carry exactly
+    // once, in whatever order the adds arrive) -- still associative, still order-independent
+    __device__ __forceinline__ void add1(unsigned long long* cell, double f) const {
+        const unsigned long long q = (unsigned long long)__double2ll_rn(f*B2_FIXED_SCALE);
+        const unsigned lo = (unsigned)q, hi = (unsigned)(q >> 32);
+        unsigned* w = reinterpret_cast<unsigned*>(cell);         // little endian: w[0] low word, w[1] high word
+        const unsigned old = atomicAdd(w, lo);
+        const unsigned carry = (old + lo) < old ? 1u : 0u;
+        if (hi + carry) atomicAdd(w + 1, hi + carry);
+    }
     __device__ __forceinline__ void add(int i, double fx, double fy, double fz) const {
-        atomicAdd(&fs[3*(i - base)], (unsigned long long)__double2ll_rn(fx*B2_FIXED_SCALE));
-        atomicAdd(&fs[3*(i - base)+1], (unsigned long long)__double2ll_rn(fy*B2_FIXED_SCALE));
-        atomicAdd(&fs[3*(i - base)+2], (unsigned long long)__double2ll_rn(fz*B2_FIXED_SCALE));
+        add1(&fs[3*(i - base)], fx);
+        add1(&fs[3*(i - base)+1], fy);
+        add1(&fs[3*(i - base)+2], fz);
     }
     __device__ __forceinline__ double force(int local, int k) const {
         return (double)(long long)fs[3*local+k]*(1.0/B2_FIXED_SCALE);
@@ -99,7 +110,8 @@ __device__ __forceinline__ void term_bond2(const BondArgs& a, int t, const GEO& 
         double d[3];
         delta(a, geo, i, j, d);
         const double r2 = d[0]*d[0] + d[1]*d[1] + d[2]*d[2];
-        const double r = sqrt(r2);
+        const double ir = rsqrt(r2);         // one reciprocal square root instead of a square root and divisions
+        const double r = r2*ir;
         double dedr = 0;
         if (a.family == B2_BOND_HARMONIC) {
             const double dr = r - p[0];
@@ -107,14 +119,14 @@ __device__ __forceinline__ void term_bond2(const BondArgs& a, int t, const GEO& 
             dedr = p[1]*dr;
         } else if (a.family == B2_BOND_LJC) {
             const double qq = p[0], sig = p[1], eps = p[2];
-            const double s2 = sig*sig/r2, s6 = s2*s2*s2;
-            e = 4*eps*s6*(s6 - 1) + a.g[0]*qq/r;
-            dedr = -(24*eps*s6*(2*s6 - 1) + a.g[0]*qq/r)/r;
+            const double s2 = sig*sig*ir*ir, s6 = s2*s2*s2;
+            e = 4*eps*s6*(s6 - 1) + a.g[0]*qq*ir;
+            dedr = -(24*eps*s6*(2*s6 - 1) + a.g[0]*qq*ir)*ir;
             if (a.g[1] > 0) {
                 const double al = a.g[1], kq = a.g[0]*p[3];
                 const double er = erf(al*r);
-                e -= kq*er/r;
-                dedr -= kq*(2*al/sqrt(M_PI)*exp(-al*al*r2)/r - er/r2);
+                e -= kq*er*ir;
+                dedr -= kq*(2*al/sqrt(M_PI)*exp(-al*al*r2)*ir - er*ir*ir);
             }
         } else if constexpr (CUSTOM) {
             double vars[10];
@@ -125,7 +137,7 @@ __device__ __forceinline__ void term_bond2(const BondArgs& a, int t, const GEO& 
         }
         w = -dedr*r;
         if (FORCE) {
-            const double s = dedr/r;   // force on j = -dE/dr * d/r
+            const double s = dedr*ir;   // force on j = -dE/dr * d/r
             geo.add(i, s*d[0], s*d[1], s*d[2]);
             geo.add(j, -s*d[0], -s*d[1], -s*d[2]);
         }
@@ -142,8 +154,9 @@ __device__ __forceinline__ void term_angle(const BondArgs& a, int t, const GEO& 
         delta(a, geo, j, i, u);
         delta(a, geo, j, k, v);
         const double ru2 = u[0]*u[0] + u[1]*u[1] + u[2]*u[2], rv2 = v[0]*v[0] + v[1]*v[1] + v[2]*v[2];
-        const double ru = sqrt(ru2), rv = sqrt(rv2);
-        double c = (u[0]*v[0] + u[1]*v[1] + u[2]*v[2])/(ru*rv);
+        const double iu = rsqrt(ru2), iv = rsqrt(rv2);       // division-free: three reciprocal square roots per angle
+        const double iuv = iu*iv;
+        double c = (u[0]*v[0] + u[1]*v[1] + u[2]*v[2])*iuv;
         c = fmin(1.0, fmax(-1.0, c));
         const double theta = acos(c);
         double dedt = 0;
@@ -159,14 +172,14 @@ __device__ __forceinline__ void term_angle(const BondArgs& a, int t, const GEO& 
             dedt = vm_run<2>(a.code_de, a.ncode_de, a.consts, nullptr, nullptr, 0, vars, nullptr, nullptr);
         }
         if (FORCE) {
-            const double s = sqrt(fmax(1.0 - c*c, 1e-30));
-            // d theta/d r_i = -(v/(ru rv) - c u/ru^2)/s
+            const double is = rsqrt(fmax(1.0 - c*c, 1e-30));
+            // d theta/d r_i = -(v/(ru rv) - c u/ru^2)/sin(theta);  force = -dE/dtheta * d theta/d r
+            const double g = dedt*is, ciu2 = c*iu*iu, civ2 = c*iv*iv;
             double fi[3], fk[3];
+#pragma unroll
             for (int q = 0; q < 3; q++) {
-                const double dti = -(v[q]/(ru*rv) - c*u[q]/ru2)/s;
-                const double dtk = -(u[q]/(ru*rv) - c*v[q]/rv2)/s;
-                fi[q] = -dedt*dti;
-                fk[q] = -dedt*dtk;
+                fi[q] = g*(v[q]*iuv - ciu2*u[q]);
+                fk[q] = g*(u[q]*iuv - civ2*v[q]);
             }
             geo.add(i, fi[0], fi[1], fi[2]);
             geo.add(k, fk[0], fk[1], fk[2]);

@@ -21,6 +21,7 @@
 #include <type_traits>
 
 #include "ctx.h"
+#include "packed.cuh"
 
 #define FULL 0xffffffffu
 
@@ -272,7 +273,7 @@ __global__ void k_cell_sort_pack(int ncells, const int* __restrict__ cell_start,
 #define NL_MARGIN 3e-4f
 #define NL_WARPS 4
 #define NL_QUEUE 40
-__global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, int ngroups, Grid g,
+__global__ void __launch_bounds__(32*NL_WARPS, 5) k_build_lists(int n, int g_lo, int ngroups, Grid g,
                                                              const int* __restrict__ cell_start,
                                                              const float4* __restrict__ cgc,
                                                              const float4* __restrict__ cgh,
@@ -296,11 +297,18 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
     __shared__ int soi[NL_WARPS][B2_GROUP];
     __shared__ unsigned long long smask[NL_WARPS][B2_GROUP];
     __shared__ float4 queue[NL_WARPS][NL_QUEUE];
+    // the NEGATED i positions as four atom PAIRS {(-x0,-x1,-y0,-y1), (-z0,-z1)} for the packed f32x2 distance test
+    __shared__ float4 sP[NL_WARPS][B2_GROUP/2];
+    __shared__ float2 sQ[NL_WARPS][B2_GROUP/2];
     const int i0 = warp*B2_GROUP;
     const float box[3] = {(float)g.box[0], (float)g.box[1], (float)g.box[2]};
     const float ibox[3] = {(float)g.inv[0], (float)g.inv[1], (float)g.inv[2]};
     if (lane < B2_GROUP) {
-        sxi[wib][lane] = prel[i0 + lane];
+        const float4 pi = prel[i0 + lane];
+        sxi[wib][lane] = pi;
+        float* P = reinterpret_cast<float*>(&sP[wib][lane >> 1]) + (lane & 1);
+        P[0] = -pi.x; P[2] = -pi.y;
+        reinterpret_cast<float*>(&sQ[wib][lane >> 1])[lane & 1] = -pi.z;
         const int i = i0 + lane;
         soi[wib][lane] = i < n ? orig[i] : -1;
         smask[wib][lane] = i < n ? exmask[i] : 0ull;
@@ -364,16 +372,27 @@ __global__ void __launch_bounds__(32*NL_WARPS) k_build_lists(int n, int g_lo, in
             if (have) {
                 const float4 pj = prel[j];
                 const float xj = e.x + pj.x, yj = e.y + pj.y, zj = e.z + pj.z;
+                if (MI) {
 #pragma unroll
-                for (int k = 0; k < B2_GROUP; k++) {
-                    const float4 pi = sxi[wib][k];
-                    float dx = xj - pi.x, dy = yj - pi.y, dz = zj - pi.z;
-                    if (MI) {
+                    for (int k = 0; k < B2_GROUP; k++) {
+                        const float4 pi = sxi[wib][k];
+                        float dx = xj - pi.x, dy = yj - pi.y, dz = zj - pi.z;
                         if (all[0] || wide) dx -= box[0]*rintf(dx*ibox[0]);
                         if (all[1] || wide) dy -= box[1]*rintf(dy*ibox[1]);
                         if (all[2] || wide) dz -= box[2]*rintf(dz*ibox[2]);
+                        d2min = fminf(d2min, dx*dx + dy*dy + dz*dz);
                     }
-                    d2min = fminf(d2min, dx*dx + dy*dy + dz*dz);
+                } else {
+                    // the common case: two i-atoms per instruction issue (FADD2 / FMUL2 / FFMA2)
+                    const F2 xj2 = f2(xj), yj2 = f2(yj), zj2 = f2(zj);
+#pragma unroll
+                    for (int k = 0; k < B2_GROUP/2; k++) {
+                        const float4 P = sP[wib][k];
+                        const float2 Q = sQ[wib][k];
+                        const F2 dx = xj2 + f2(P.x, P.y), dy = yj2 + f2(P.z, P.w), dz = zj2 + f2(Q.x, Q.y);
+                        const F2 d2 = fma2(dz, dz, fma2(dy, dy, dx*dx));
+                        d2min = fminf(d2min, fminf(d2.v.x, d2.v.y));
+                    }
                 }
                 if (j >= j_first && j <= j_last) {
                     const int oj = orig[j];

@@ -227,6 +227,130 @@ __global__ void __launch_bounds__(32*WPB, 8) k_pair_force(int n, int g_lo, int n
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed variant (the shipped one): every lane evaluates TWO list slots per step with the f32x2 instructions of
+// sm_100a (FADD2 / FMUL2 / FFMA2, potentials.cuh) -- the tiles are bound by instruction issue, and one issue now
+// carries the arithmetic of two pairs.  Shared-memory staging is laid out for that: per 32-entry chunk 16 slot
+// PAIRS, each {(x0,x1,y0,y1), (z0,z1,q0,q1), (hs0,hs1,se0,se1), (entry0,entry1)}, so an LDS.128 lands directly in
+// the aligned register pairs the packed instructions take.  Pipeline, band logic and reduction as above.
+// Differences are accumulated as x_j - x_i (one packed add against the negated i position) and the sign is
+// applied once at the end.
+__device__ __forceinline__ void band_record(const BandBuffer& bb, int i, unsigned entry) {
+    if (i < 0) return;                                  // padding lanes of the last group own no atom
+    const unsigned slot = atomicAdd(bb.count, 1u);
+    if (slot < bb.capacity) { bb.pairs[2*slot] = i; bb.pairs[2*slot+1] = (int)(entry & 0xffffffu); }
+}
+
+template <class POT2, bool MINIMG>
+__device__ __forceinline__ void sweep_chunk2(const POT2& pot, const float4* __restrict__ sA, const float4* __restrict__ sB,
+                                             const float4* __restrict__ sC, const uint2* __restrict__ sD, int jj,
+                                             unsigned ibit, F2 nx, F2 ny, F2 nz, F2 kqi, F2 hsi, F2 sei, float rc2_hi,
+                                             float rc2_lo, float3 box, float3 inv, int i, const BandBuffer& bb,
+                                             double& fx, double& fy, double& fz) {
+    F2 ax = f2(0.f), ay = f2(0.f), az = f2(0.f);      // fp32 partial sums over one chunk (<= 8 pairs per lane)
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const int pp = 4*t + jj;
+        const float4 A = sA[pp], B = sB[pp];
+        const uint2 D = sD[pp];
+        F2 dx = f2(A.x, A.y) + nx, dy = f2(A.z, A.w) + ny, dz = f2(B.x, B.y) + nz;
+        if (MINIMG) {
+            dx.v.x -= box.x*rintf(dx.v.x*inv.x); dx.v.y -= box.x*rintf(dx.v.y*inv.x);
+            dy.v.x -= box.y*rintf(dy.v.x*inv.y); dy.v.y -= box.y*rintf(dy.v.y*inv.y);
+            dz.v.x -= box.z*rintf(dz.v.x*inv.z); dz.v.y -= box.z*rintf(dz.v.y*inv.z);
+        }
+        const F2 r2 = fma2(dz, dz, fma2(dy, dy, dx*dx));
+        bool in0 = r2.v.x < rc2_hi && !(D.x & ibit);      // rc2_hi is the OUTER edge of the band
+        bool in1 = r2.v.y < rc2_hi && !(D.y & ibit);
+        if (!(in0 || in1)) continue;
+        if ((in0 && r2.v.x >= rc2_lo) || (in1 && r2.v.y >= rc2_lo)) {     // a few hundred pairs per launch
+            if (in0 && r2.v.x >= rc2_lo) { band_record(bb, i, D.x); in0 = false; }
+            if (in1 && r2.v.y >= rc2_lo) { band_record(bb, i, D.y); in1 = false; }
+        }
+        const float4 C = sC[pp];
+        F2 fr = pot(r2, kqi*f2(B.z, B.w), hsi + f2(C.x, C.y), sei*f2(C.z, C.w));
+        fr = f2(in0 ? fr.v.x : 0.f, in1 ? fr.v.y : 0.f);      // select, not multiply: masked slots may hold inf / NaN
+        ax = fma2(fr, dx, ax); ay = fma2(fr, dy, ay); az = fma2(fr, dz, az);
+    }
+    // d = x_j - x_i: the force on i is -sum.  fp64 across chunks: no long fp32 sums
+    fx -= (double)(ax.v.x + ax.v.y); fy -= (double)(ay.v.x + ay.v.y); fz -= (double)(az.v.x + az.v.y);
+}
+
+template <class POT2>
+__global__ void __launch_bounds__(32*WPB, 6) k_pair_force2(int n, int g_lo, int ngroups, const int4* __restrict__ xq,
+                                                       const float4* __restrict__ par,
+                                                       const int* __restrict__ entries,
+                                                       const int* __restrict__ counts,
+                                                       const unsigned char* __restrict__ gflags, int cap,
+                                                       float4* __restrict__ out, int accumulate, POT2 pot,
+                                                       float rc2, BandBuffer bb, float3 box) {
+    __shared__ float4 sA[WPB][2][16], sB[WPB][2][16], sC[WPB][2][16];
+    __shared__ uint2 sD[WPB][2][16];
+    const int warp = g_lo + ((blockIdx.x*blockDim.x + threadIdx.x) >> 5);
+    if (warp >= ngroups) return;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int il = lane >> 2, jj = lane & 3;
+    const int i = warp*B2_GROUP + il;
+    const int ic = min(i, n - 1);
+    const float3 inv = make_float3(1.f/box.x, 1.f/box.y, 1.f/box.z);
+    const float3 scale = make_float3(box.x*2.3283064365386963e-10f, box.y*2.3283064365386963e-10f,
+                                     box.z*2.3283064365386963e-10f);
+    const int i0 = warp*B2_GROUP;
+    const int4 ref = xq[i0];                      // reference point of the group: its first atom
+    const float3 xr = rel_fixed(xq[ic], ref, scale);
+    const float4 pi = par[ic];
+    const F2 nx = f2(-xr.x), ny = f2(-xr.y), nz = f2(-xr.z);
+    const F2 kqi = f2(pot.charge_scale()*pi.x), hsi = f2(pi.y), sei = f2(POT2::EPS_SCALE*pi.z);
+    const unsigned ibit = 1u << (24 + il);
+    const bool minimg = gflags[warp] & 1;
+    const float rc2_lo = rc2*(1.f - 2e-6f), rc2_hi = rc2*(1.f + 2e-6f);
+    const int cnt = counts[warp];
+    const int* __restrict__ base = entries + (size_t)warp*cap;
+    const int pad = (int)(0xff000000u | (unsigned)i0);
+    const int half = lane & 1, pr = lane >> 1;
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    int buf = 0;
+    int e = lane < cnt ? base[lane] : pad;                       // chunk 0
+    int e_next = 32 + lane < cnt ? base[32 + lane] : pad;        // chunk 1
+    int4 qj = xq[e & 0xffffff];
+    float4 pj = par[e & 0xffffff];
+    for (int c0 = 0; c0 < cnt; c0 += 32) {
+        const float3 xj = rel_fixed(qj, ref, scale);
+        float* a = reinterpret_cast<float*>(&sA[wib][buf][pr]) + half;
+        float* b = reinterpret_cast<float*>(&sB[wib][buf][pr]) + half;
+        float* c = reinterpret_cast<float*>(&sC[wib][buf][pr]) + half;
+        a[0] = xj.x; a[2] = xj.y;
+        b[0] = xj.z; b[2] = pj.x;
+        c[0] = pj.y; c[2] = pj.z;
+        reinterpret_cast<int*>(&sD[wib][buf][pr])[half] = e;
+        if (c0 + 32 < cnt) {
+            e = e_next;
+            qj = xq[e & 0xffffff];
+            pj = par[e & 0xffffff];
+            const int nxt = c0 + 64 + lane;
+            e_next = nxt < cnt ? base[nxt] : pad;
+        }
+        __syncwarp();
+        if (minimg)
+            sweep_chunk2<POT2, true>(pot, sA[wib][buf], sB[wib][buf], sC[wib][buf], sD[wib][buf], jj, ibit, nx, ny, nz, kqi,
+                                     hsi, sei, rc2_hi, rc2_lo, box, inv, i < n ? i : -1, bb, fx, fy, fz);
+        else
+            sweep_chunk2<POT2, false>(pot, sA[wib][buf], sB[wib][buf], sC[wib][buf], sD[wib][buf], jj, ibit, nx, ny, nz, kqi,
+                                      hsi, sei, rc2_hi, rc2_lo, box, inv, i < n ? i : -1, bb, fx, fy, fz);
+        buf ^= 1;
+    }
+    fx += __shfl_xor_sync(FULL, fx, 1); fy += __shfl_xor_sync(FULL, fy, 1); fz += __shfl_xor_sync(FULL, fz, 1);
+    fx += __shfl_xor_sync(FULL, fx, 2); fy += __shfl_xor_sync(FULL, fy, 2); fz += __shfl_xor_sync(FULL, fz, 2);
+    if (jj == 0 && i < n) {
+        float4 f = make_float4((float)fx, (float)fy, (float)fz, 0.f);
+        if (accumulate) {
+            const float4 o = out[i];
+            f.x += o.x; f.y += o.y; f.z += o.z;
+        }
+        out[i] = f;
+    }
+}
+
 // Settlement of the band pairs in float64.  The append order of the band buffer depends on warp
 // scheduling, so the contributions are NOT added to the fp32 force buffer one by one (float addition
 // does not commute with re-ordering): every touched atom gets ONE fixed-point accumulator (claimed
@@ -452,6 +576,13 @@ static double effective_cutoff(const PairForce& pf) {
     return rc;
 }
 
+template <class POT>
+struct PackedOf;
+template <int A, int B, int C, int D, int E>
+struct PackedOf<LJCPot<A, B, C, D, E, float>> { typedef LJCForce2<A, B, C, D, E> type; };
+template <>
+struct PackedOf<SoftcorePot<float>> { typedef SoftcoreForce2 type; };
+
 template <class POT, class POTD>
 static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, POTD potd, float rc2, float4* out,
                         bool accumulate, int lane) {
@@ -470,10 +601,16 @@ static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, POTD potd
         cudaEventCreate(&ev0); cudaEventCreate(&ev1);
         cudaEventRecord(ev0, stream);
     }
-    k_pair_force<POT><<<blocks, 32*WPB, 0, stream>>>(ctx->n, ctx->g_lo, ctx->g_hi, ctx->xq, ctx->par[pf.set],
-                                                          L.entries, L.counts, L.gflags, L.cap, out,
-                                                          accumulate ? 1 : 0, pot, rc2, bb,
-                                                          make_float3((float)ctx->box[0], (float)ctx->box[1], (float)ctx->box[2]));
+    const float3 boxf = make_float3((float)ctx->box[0], (float)ctx->box[1], (float)ctx->box[2]);
+    static const bool scalar_pair_tiles = getenv("B2_PAIR_SCALAR") != nullptr;
+    if (scalar_pair_tiles)            // B2_PAIR_SCALAR=1: the one-slot-per-lane tiles, kept for A/B measurements
+        k_pair_force<POT><<<blocks, 32*WPB, 0, stream>>>(ctx->n, ctx->g_lo, ctx->g_hi, ctx->xq, ctx->par[pf.set],
+                                                              L.entries, L.counts, L.gflags, L.cap, out,
+                                                              accumulate ? 1 : 0, pot, rc2, bb, boxf);
+    else
+        k_pair_force2<typename PackedOf<POT>::type><<<blocks, 32*WPB, 0, stream>>>(
+            ctx->n, ctx->g_lo, ctx->g_hi, ctx->xq, ctx->par[pf.set], L.entries, L.counts, L.gflags, L.cap, out,
+            accumulate ? 1 : 0, typename PackedOf<POT>::type{pot.p}, rc2, bb, boxf);
     if (ctx->profiling) {
         cudaEventRecord(ev1, stream);
         ctx->prof_events.push_back(ev0); ctx->prof_events.push_back(ev1);

@@ -16,6 +16,9 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <math.h>
+
+#include "packed.cuh"
 
 enum { COUL_NONE = 0, COUL_PLAIN = 1, COUL_RF = 2, COUL_ERFC = 3 };
 enum { LJ_STD = 0, LJ_VIRIAL = 1 };
@@ -23,30 +26,52 @@ enum { SW_NONE = 0, SW_ALL = 1, SW_LJ = 2 };
 enum { SWF_LINEAR = 0, SWF_POWER = 1 };
 enum { VAR_NONE = 0, VAR_SHIFT = 1, VAR_FSWITCH = 2 };
 
-__device__ __forceinline__ float b2_rsqrt(float x) { return rsqrtf(x); }
-__device__ __forceinline__ double b2_rsqrt(double x) { return 1.0/sqrt(x); }
+B2_HD float b2_rsqrt(float x) {
+#ifdef __CUDA_ARCH__
+    return rsqrtf(x);
+#else
+    return 1.0f/sqrtf(x);
+#endif
+}
+B2_HD double b2_rsqrt(double x) { return 1.0/sqrt(x); }
 // 1/r and 1/r^2 from r^2.  fp32: MUFU.RSQ (<= 2 ulp) refined by one Newton step (~0.5 ulp), because the
 // r^-12 term amplifies the relative error of 1/r twelve-fold.
-__device__ __forceinline__ void b2_inverse(float r2, float& rinv, float& rinv2) {
+B2_HD void b2_inverse(float r2, float& rinv, float& rinv2) {
     float y;
+#ifdef __CUDA_ARCH__
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(r2));   // r2 is never subnormal: no range fix-up code
+#else
+    y = 1.0f/sqrtf(r2);
+#endif
     const float e = fmaf(-r2*y, y, 1.0f);
     y = fmaf(0.5f*y, e, y);
     rinv = y;
     rinv2 = y*y;
 }
-__device__ __forceinline__ void b2_inverse(double r2, double& rinv, double& rinv2) {
+B2_HD void b2_inverse(double r2, double& rinv, double& rinv2) {
     rinv = 1.0/sqrt(r2);
     rinv2 = 1.0/r2;
 }
-__device__ __forceinline__ float b2_erfc(float x) { return erfcf(x); }
-__device__ __forceinline__ double b2_erfc(double x) { return erfc(x); }
-__device__ __forceinline__ float b2_exp(float x) { return __expf(x); }
-__device__ __forceinline__ double b2_exp(double x) { return exp(x); }
-__device__ __forceinline__ float b2_log(float x) { return __logf(x); }
-__device__ __forceinline__ double b2_log(double x) { return log(x); }
-__device__ __forceinline__ float b2_max(float a, float b) { return fmaxf(a, b); }
-__device__ __forceinline__ double b2_max(double a, double b) { return fmax(a, b); }
+B2_HD float b2_erfc(float x) { return erfcf(x); }
+B2_HD double b2_erfc(double x) { return erfc(x); }
+B2_HD float b2_exp(float x) {
+#ifdef __CUDA_ARCH__
+    return __expf(x);
+#else
+    return expf(x);
+#endif
+}
+B2_HD double b2_exp(double x) { return exp(x); }
+B2_HD float b2_log(float x) {
+#ifdef __CUDA_ARCH__
+    return __logf(x);
+#else
+    return logf(x);
+#endif
+}
+B2_HD double b2_log(double x) { return log(x); }
+B2_HD float b2_max(float a, float b) { return fmaxf(a, b); }
+B2_HD double b2_max(double a, double b) { return fmax(a, b); }
 
 template <typename T>
 struct PotParams {
@@ -67,7 +92,7 @@ struct PotParams {
 };
 
 template <typename T>
-__device__ __forceinline__ void switch_eval(const PotParams<T>& p, int swf, T r, T r2, T& S, T& rdS) {
+B2_HD void switch_eval(const PotParams<T>& p, int swf, T r, T r2, T& S, T& rdS) {
     T u, rdu;
     if (swf == SWF_LINEAR) {
         u = b2_max((r - p.rs)*p.iw, T(0));
@@ -89,7 +114,7 @@ struct LJCPot {
     PotParams<T> p;
 
     template <bool WANT_E>
-    __device__ __forceinline__ void operator()(T r2, T qq, T sig, T eps, T& rF, T& e, T& rinv2) const {
+    B2_HD void operator()(T r2, T qq, T sig, T eps, T& rF, T& e, T& rinv2) const {
         T rinv;
         b2_inverse(r2, rinv, rinv2);
         const T r = r2*rinv;
@@ -174,13 +199,13 @@ struct SoftcorePot {
     PotParams<T> p;
 
     template <bool WANT_E>
-    __device__ __forceinline__ void operator()(T r2, T qq, T sig, T eps, T& rF, T& e, T& rinv2) const {
+    B2_HD void operator()(T r2, T qq, T sig, T eps, T& rF, T& e, T& rinv2) const {
         T dv, dc;
         eval(r2, qq, sig, eps, rF, e, dv, dc);
         rinv2 = T(1)/r2;
     }
 
-    __device__ __forceinline__ void eval(T r2, T qq, T sig, T eps, T& rF, T& e, T& dEdlv, T& dEdlc) const {
+    B2_HD void eval(T r2, T qq, T sig, T eps, T& rF, T& e, T& dEdlv, T& dEdlc) const {
         const T lam_v = p.lam_v_dev ? T(*p.lam_v_dev) : p.lam_v;
         const T lam_c = p.lam_c_dev ? T(*p.lam_c_dev) : p.lam_c;
         T pair_scale = T(1);
@@ -209,4 +234,114 @@ struct SoftcorePot {
         dEdlc = S*p.kc*qq*rinv;
         rF *= pair_scale; e *= pair_scale; dEdlv *= pair_scale; dEdlc *= pair_scale;
     }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Packed fp32x2 force functor (hot path).  sm_100a has FFMA2 / FADD2 / FMUL2: one instruction issue does
+// the arithmetic of TWO pairs, and the pair tiles are bound by instruction issue.  Every lane of a tile
+// therefore evaluates two list slots at once; the closed forms above are restated on a two-wide value
+// type with explicit fused multiply-adds (the *_rn intrinsics are never contracted by the compiler).
+// Only what the force kernels need (no energies) -- energies / virials stay in the float64 functors.
+// Compiles for the host too (component-wise fmaf), so the restatement is checked against the
+// scalar functors without a GPU (tests/test_packed_potentials.py).
+// ---------------------------------------------------------------------------------------------
+
+template <int COUL, int LJ, int SW, int SWF, int VAR>
+struct LJCForce2 {
+    PotParams<float> p;
+    // the caller folds these into the i-atom's parameters once per tile
+    static constexpr float EPS_SCALE = (LJ == LJ_STD) ? 24.f : 144.f;
+    B2_HD float charge_scale() const { return p.kc; }      // Kc is folded into q_i as well
+
+    // r2: squared distances of two pairs; kqq = Kc q_i q_j; sig = (sigma_i + sigma_j)/2;
+    // eps = EPS_SCALE sqrt(eps_i eps_j).  Returns  -(dE/dr)/r  (times sign): force on i = result * (x_i - x_j).
+    B2_HD F2 operator()(F2 r2, F2 kqq, F2 sig, F2 eps) const {
+        // 1/r: MUFU.RSQ per half, one packed Newton step (the r^-12 term amplifies the error twelve-fold)
+        F2 y = f2(b2_rsqrt_approx(r2.v.x), b2_rsqrt_approx(r2.v.y));
+        const F2 t = r2*y;
+        const F2 e = fma2(t, y, f2(-1.f));             // r2 y^2 - 1
+        y = fma2(y*f2(-0.5f), e, y);
+        const F2 rinv = y, rinv2 = y*y;
+        const F2 sr = sig*y;
+        const F2 s2 = sr*sr;
+        const F2 s6 = s2*s2*s2;
+        const F2 es6 = eps*s6;
+        F2 rflj, elj;
+        if (LJ == LJ_STD) {
+            rflj = es6*fma2(s6, f2(2.f), f2(-1.f));                     // 24 eps s6 (2 s6 - 1)
+            elj = (es6*f2(1.f/6.f))*(s6 + f2(-1.f));                    // 4 eps s6 (s6 - 1)
+        } else {
+            rflj = es6*fma2(s6, f2(4.f), f2(-1.f));                     // 144 eps s6 (4 s6 - 1)
+            elj = (es6*f2(1.f/6.f))*fma2(s6, f2(2.f), f2(-1.f));        // 24 eps s6 (2 s6 - 1)
+        }
+        F2 ec = f2(0.f), rfc = f2(0.f);
+        if (COUL == COUL_PLAIN) {
+            ec = kqq*rinv;
+            rfc = ec;
+        } else if (COUL == COUL_RF) {
+            ec = kqq*(fma2(r2, f2(p.krf), rinv) + f2(-p.crf));
+            rfc = kqq*fma2(r2, f2(-2.f*p.krf), rinv);
+        } else if (COUL == COUL_ERFC) {
+            const F2 r = r2*rinv;
+            const F2 ar = r*f2(p.alpha);
+            const F2 erfc_r = f2(b2_erfc(ar.v.x), b2_erfc(ar.v.y))*rinv;
+            const F2 ar2 = ar*ar;
+            ec = kqq*erfc_r;
+            rfc = kqq*fma2(f2(p.tasp), f2(b2_exp(-ar2.v.x), b2_exp(-ar2.v.y)), erfc_r);
+        }
+        F2 rF;
+        if (SW == SW_NONE) {
+            rF = rflj + rfc;
+        } else {
+            // switching function S(u) = 1 - u^3 (10 - 15 u + 6 u^2) and r dS/dr = -30 u^2 (1-u)^2 r du/dr
+            const F2 r = r2*rinv;
+            F2 u, rdu;
+            if (SWF == SWF_LINEAR) {
+                u = max0(fma2(r, f2(p.iw), f2(-p.rs*p.iw)));
+                rdu = r*f2(p.iw);
+            } else {
+                F2 rd = r2;
+                for (int k = 2; k < p.degree; k++) rd = rd*r;
+                u = max0(fma2(rd, f2(p.iwd), f2(-p.rsd*p.iwd)));
+                rdu = rd*f2((float)p.degree*p.iwd);
+            }
+            const F2 u2 = u*u;
+            const F2 S = fma2(u2*u, fma2(fma2(u, f2(-6.f), f2(15.f)), u, f2(-10.f)), f2(1.f));
+            if (SW == SW_ALL && VAR == VAR_FSWITCH) {
+                rF = S*(rflj + rfc);
+            } else {
+                const F2 om = fma2(u, f2(-1.f), f2(1.f));
+                const F2 rdS = (u2*f2(-30.f))*(om*om)*rdu;
+                if (SW == SW_LJ) {
+                    rF = fma2(S, rflj, rfc) + (rdS*elj)*f2(-1.f);
+                } else if (VAR == VAR_NONE) {
+                    rF = fma2(S, rflj + rfc, (rdS*(elj + ec))*f2(-1.f));
+                } else {      // VAR_SHIFT: V - V(rc0)
+                    const float irc = p.inv_rc0;
+                    const F2 c2 = (sig*sig)*f2(irc*irc);
+                    const F2 c6 = c2*c2*c2;
+                    // eps here is EPS_SCALE * eps: 4 eps c6 (c6 - 1) = (eps/6) c6 (c6 - 1) for the standard form
+                    const F2 vshift = fma2(kqq, f2(irc), ((eps*f2(4.f/EPS_SCALE))*c6)*(c6 + f2(-1.f)));
+                    const F2 V = elj + ec + vshift*f2(-1.f);
+                    rF = fma2(S, rflj + rfc, (rdS*V)*f2(-1.f));
+                }
+            }
+        }
+        return (rF*rinv2)*f2(p.sign);
+    }
+};
+
+// scalar fall-back with the same interface (soft core: divisions and per-launch couplings, not worth packing)
+struct SoftcoreForce2 {
+    SoftcorePot<float> pot;
+    static constexpr float EPS_SCALE = 1.f;
+    B2_HD float charge_scale() const { return 1.f; }
+#ifdef __CUDACC__
+    __device__ __forceinline__ F2 operator()(F2 r2, F2 qq, F2 sig, F2 eps) const {
+        float rF0, rF1, e, ri0, ri1;
+        pot.template operator()<false>(r2.v.x, qq.v.x, sig.v.x, eps.v.x, rF0, e, ri0);
+        pot.template operator()<false>(r2.v.y, qq.v.y, sig.v.y, eps.v.y, rF1, e, ri1);
+        return f2(rF0*ri0, rF1*ri1);
+    }
+#endif
 };
