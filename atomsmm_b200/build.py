@@ -18,6 +18,9 @@ LIBRARY = os.path.join(HERE, 'libatomsmm_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '-Xptxas', '-v']
+# tuning experiments: B2_EXTRA_NVCC_FLAGS="-DB2_PAIR_MINB=6" python -m atomsmm_b200.build --force, B2_LIBRARY=<path> at run time
+FLAGS += os.environ.get('B2_EXTRA_NVCC_FLAGS', '').split()
+LIBRARY = os.environ.get('B2_BUILD_OUTPUT', LIBRARY)
 
 
 def sources():

@@ -142,6 +142,7 @@ extern "C" int b2_destroy(b2_context* ctx) {
     cudaFree(ctx->x); cudaFree(ctx->v); cudaFree(ctx->xref); cudaFree(ctx->xsort); cudaFree(ctx->xq);
     for (int s = 0; s < B2_MAX_SETS; s++) { cudaFree(ctx->par[s]); cudaFree(ctx->pard[s]); }
     cudaFree(ctx->massd); cudaFree(ctx->invm); cudaFree(ctx->orig); cudaFree(ctx->inv); cudaFree(ctx->exmask);
+    order_release(ctx);
     cudaFree(ctx->excl_ptr); cudaFree(ctx->excl_idx); cudaFree(ctx->scratch3);
     for (int g = 0; g < B2_FSLOTS; g++) cudaFree(ctx->fbuf[g]);
     for (double* p : ctx->perdof) cudaFree(p);
@@ -295,6 +296,7 @@ extern "C" int b2_set_exclusions(b2_context* ctx, int npairs, const int* pairs) 
     B2_CUDA(cudaMemcpy(ctx->excl_ptr, ptr.data(), sizeof(int)*(ctx->n + 1), cudaMemcpyHostToDevice));
     B2_CUDA(cudaMemcpy(ctx->excl_idx, idx.data(), sizeof(int)*idx.size(), cudaMemcpyHostToDevice));
     ctx->have_order = false;
+    ctx->order.valid = false;
     return B2_OK;
 }
 
@@ -378,6 +380,7 @@ extern "C" int b2_update_pair_particles(b2_context* ctx, int handle, const doubl
         ctx->h_sets[target] = s;
     }
     if (ctx->have_order) B2_TRY(upload_param_set(ctx, target));
+    ctx->order.valid = false;             // the caller-order copy the device ordering gathers from is stale
     for (int g = 0; g < B2_FSLOTS; g++) ctx->fvalid[g] = -1;
     ctx->deriv_version = -1;
     program_release(ctx);
@@ -533,6 +536,14 @@ extern "C" int b2_hilbert_index(const double position[3], const double box[3], u
     return B2_OK;
 }
 
+extern "C" int b2_get_order(b2_context* ctx, int* orig_host) {
+    if (!ctx || !orig_host) return B2_ERR_ARG;
+    if (!ctx->have_order) return b2_fail(ctx, B2_ERR_STATE, "positions have not been set");
+    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    B2_CUDA(cudaMemcpy(orig_host, ctx->orig, sizeof(int)*ctx->n, cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+
 static int compute_order(b2_context* ctx, const std::vector<double>& hx) {
     const int n = ctx->n;
     // molecules in caller order: a static CSR table, built once (config 5 has 1.4 M molecules; the order is
@@ -654,9 +665,7 @@ extern "C" int b2_set_positions(b2_context* ctx, const double* x_dev) {
         t_mark = t;
     };
     if (resort) {
-        std::vector<double> hx(3*(size_t)n);
         B2_CUDA(cudaStreamSynchronize(ctx->stream));
-        B2_CUDA(cudaMemcpy(hx.data(), x_dev, sizeof(double)*3*n, cudaMemcpyDeviceToHost));
         // carry velocities and per-DOF variables across the re-ordering (via caller order)
         std::vector<double*> carried;
         if (ctx->have_order) {
@@ -676,10 +685,18 @@ extern "C" int b2_set_positions(b2_context* ctx, const double* x_dev) {
         for (size_t k = 0; k < carried.size(); k++) B2_TRY(state_permute_to_user(ctx, carried[k], tmp[k]));
         B2_CUDA(cudaStreamSynchronize(ctx->stream));
         lap("download+carry");
-        B2_TRY(compute_order(ctx, hx));
-        lap("compute_order");
-        B2_TRY(upload_static(ctx));
-        lap("upload_static");
+        static const bool host_order = getenv("B2_HOST_ORDER") != nullptr;
+        if (host_order) {           // round 1's path, kept for A/B checks of the device ordering
+            std::vector<double> hx(3*(size_t)n);
+            B2_CUDA(cudaMemcpy(hx.data(), x_dev, sizeof(double)*3*n, cudaMemcpyDeviceToHost));
+            B2_TRY(compute_order(ctx, hx));
+            lap("compute_order");
+            B2_TRY(upload_static(ctx));
+            lap("upload_static");
+        } else {
+            B2_TRY(order_compute_device(ctx, x_dev));
+            lap("device order");
+        }
         B2_TRY(dist_partition(ctx));
         ctx->inner_built = false;
         ctx->con_built = false;

@@ -101,12 +101,13 @@ __device__ __forceinline__ void block_accumulate(double e, double w, double* acc
 // two-body families: E(r); force from dE/dr
 // CUSTOM = false compiles the bytecode interpreter of CustomBondForce / CustomAngleForce terms out (the fused
 // inner loop of systems without such terms: no evaluation stack in local memory, fewer registers)
+// Every term function comes in two parts: term_x() resolves the term (atom indices in the engine's order through
+// two dependent table look-ups, parameter pointer) and term_x_core() evaluates it.  The fused inner loop resolves
+// a thread's term ONCE per launch and evaluates it at every inner iteration from registers.
 template <bool FORCE, bool ENERGY, bool CUSTOM = true, class GEO>
-__device__ __forceinline__ void term_bond2(const BondArgs& a, int t, const GEO& geo, double& e, double& w) {
+__device__ __forceinline__ void term_bond2_core(const BondArgs& a, int i, int j, const double* p, const GEO& geo,
+                                                double& e, double& w) {
     {
-        const int i = a.inv[a.atoms[2*t]], j = a.inv[a.atoms[2*t+1]];
-        if (i < a.a_lo || i >= a.a_hi) return;
-        const double* p = a.params + (size_t)t*a.stride;
         double d[3];
         delta(a, geo, i, j, d);
         const double r2 = d[0]*d[0] + d[1]*d[1] + d[2]*d[2];
@@ -145,11 +146,16 @@ __device__ __forceinline__ void term_bond2(const BondArgs& a, int t, const GEO& 
 }
 
 template <bool FORCE, bool ENERGY, bool CUSTOM = true, class GEO>
-__device__ __forceinline__ void term_angle(const BondArgs& a, int t, const GEO& geo, double& e) {
+__device__ __forceinline__ void term_bond2(const BondArgs& a, int t, const GEO& geo, double& e, double& w) {
+    const int i = a.inv[a.atoms[2*t]], j = a.inv[a.atoms[2*t+1]];
+    if (i < a.a_lo || i >= a.a_hi) return;
+    term_bond2_core<FORCE, ENERGY, CUSTOM>(a, i, j, a.params + (size_t)t*a.stride, geo, e, w);
+}
+
+template <bool FORCE, bool ENERGY, bool CUSTOM = true, class GEO>
+__device__ __forceinline__ void term_angle_core(const BondArgs& a, int i, int j, int k, const double* p, const GEO& geo,
+                                                double& e) {
     {
-        const int i = a.inv[a.atoms[3*t]], j = a.inv[a.atoms[3*t+1]], k = a.inv[a.atoms[3*t+2]];
-        if (i < a.a_lo || i >= a.a_hi) return;
-        const double* p = a.params + (size_t)t*a.stride;
         double u[3], v[3];
         delta(a, geo, j, i, u);
         delta(a, geo, j, k, v);
@@ -188,6 +194,13 @@ __device__ __forceinline__ void term_angle(const BondArgs& a, int t, const GEO& 
     }
 }
 
+template <bool FORCE, bool ENERGY, bool CUSTOM = true, class GEO>
+__device__ __forceinline__ void term_angle(const BondArgs& a, int t, const GEO& geo, double& e) {
+    const int i = a.inv[a.atoms[3*t]], j = a.inv[a.atoms[3*t+1]], k = a.inv[a.atoms[3*t+2]];
+    if (i < a.a_lo || i >= a.a_hi) return;
+    term_angle_core<FORCE, ENERGY, CUSTOM>(a, i, j, k, a.params + (size_t)t*a.stride, geo, e);
+}
+
 __device__ __forceinline__ void cross3(const double (&a)[3], const double (&b)[3], double (&c)[3]) {
     c[0] = a[1]*b[2] - a[2]*b[1];
     c[1] = a[2]*b[0] - a[0]*b[2];
@@ -195,12 +208,9 @@ __device__ __forceinline__ void cross3(const double (&a)[3], const double (&b)[3
 }
 
 template <bool FORCE, bool ENERGY, class GEO>
-__device__ __forceinline__ void term_torsion(const BondArgs& a, int t, const GEO& geo, double& e) {
+__device__ __forceinline__ void term_torsion_core(const BondArgs& a, int a1, int a2, int a3, int a4, const double* p,
+                                                  const GEO& geo, double& e) {
     {
-        const int a1 = a.inv[a.atoms[4*t]], a2 = a.inv[a.atoms[4*t+1]], a3 = a.inv[a.atoms[4*t+2]],
-                  a4 = a.inv[a.atoms[4*t+3]];
-        if (a1 < a.a_lo || a1 >= a.a_hi) return;
-        const double* p = a.params + (size_t)t*a.stride;
         double F[3], G[3], H[3], A[3], B[3], C[3];
         delta(a, geo, a2, a1, F);   // r1 - r2
         delta(a, geo, a3, a2, G);   // r2 - r3
@@ -233,6 +243,13 @@ __device__ __forceinline__ void term_torsion(const BondArgs& a, int t, const GEO
             geo.add(a4, f4[0], f4[1], f4[2]);
         }
     }
+}
+
+template <bool FORCE, bool ENERGY, class GEO>
+__device__ __forceinline__ void term_torsion(const BondArgs& a, int t, const GEO& geo, double& e) {
+    const int a1 = a.inv[a.atoms[4*t]], a2 = a.inv[a.atoms[4*t+1]], a3 = a.inv[a.atoms[4*t+2]], a4 = a.inv[a.atoms[4*t+3]];
+    if (a1 < a.a_lo || a1 >= a.a_hi) return;
+    term_torsion_core<FORCE, ENERGY>(a, a1, a2, a3, a4, a.params + (size_t)t*a.stride, geo, e);
 }
 
 

@@ -77,6 +77,22 @@ struct NList {
     unsigned char* gflags = nullptr;  // [ngroups] bit0: group needs per-pair minimum image
 };
 
+// caller-order tables and scratch of the device-side ordering (order.cu)
+struct OrderDevice {
+    bool valid = false;
+    int nmol = 0, nmol_used = 0, nsets = 0, nexcl = 0;
+    int *mol_ptr = nullptr, *mol_atoms = nullptr;         // molecules in caller order (CSR)
+    unsigned long long* keys = nullptr;                   // [2][nmol] Hilbert keys, unsorted / sorted
+    int *ids = nullptr, *sizes = nullptr, *offsets = nullptr;
+    double* mass_user = nullptr;
+    unsigned long long* exmask_user = nullptr;
+    double* sets_user[B2_MAX_SETS] = {nullptr, nullptr, nullptr, nullptr};
+    int* excl_pairs = nullptr;
+    int* span = nullptr;
+    void* temp = nullptr;
+    size_t temp_bytes = 0;
+};
+
 struct b2_context {
     int device = 0;
     cudaStream_t stream = 0;
@@ -107,6 +123,7 @@ struct b2_context {
     bool have_order = false, have_positions = false, force_resort = false;
     int steps_since_order_check = 0;
     std::vector<int> h_orig;                      // sorted -> caller index
+    OrderDevice order;                            // device-side ordering (order.cu)
     double *x = nullptr, *v = nullptr, *xref = nullptr, *xsort = nullptr;
     int4* xq = nullptr;                           // positions as 32-bit fixed-point fractions of the box (pair tiles)
     float4* par[B2_MAX_SETS] = {nullptr};
@@ -296,6 +313,11 @@ void dist_release(b2_context* ctx);
 int forces_ensure(b2_context* ctx, uint32_t mask, int slot);
 int inner_prepare(b2_context* ctx);
 int order_refresh(b2_context* ctx);
+// order.cu: spatial order computed on the device from caller-order positions (orig, inv, static tables; h_orig on host)
+int order_compute_device(b2_context* ctx, const double* x_user);
+int order_refresh_param_set(b2_context* ctx, int k);
+void order_release(b2_context* ctx);
+int order_hilbert_bits(const double box[3]);
 int con_prepare(b2_context* ctx);
 int con_snapshot(b2_context* ctx);
 int con_positions(b2_context* ctx);

@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(256) k_dd_pull(DDPeers P, unsigned long long* 
     __shared__ unsigned long long s_epoch;
     __shared__ bool last;
     if (threadIdx.x == 0) { s_flag = nl_flags[0] != 0 ? 1 : 0; s_epoch = state[0]; }
+    const unsigned long long t_start = dd_now();
     __syncthreads();
     const unsigned long long e = s_epoch;
     if ((int)threadIdx.x < P.nranks && (int)threadIdx.x != P.rank) {
@@ -227,6 +228,8 @@ __global__ void __launch_bounds__(256) k_dd_pull(DDPeers P, unsigned long long* 
         if (v & 1ull) atomicOr(&s_flag, 1);
     }
     __syncthreads();
+    // exchange clock (b2_comm_timing): block 0 saw the whole wait; the last block closes the copy
+    if (blockIdx.x == 0 && threadIdx.x == 0) { state[4] += dd_now() - t_start; state[7] = dd_now(); }
     const long long stride = (long long)gridDim.x*blockDim.x;
     const long long first = (long long)blockIdx.x*blockDim.x + threadIdx.x;
     // one thread per PAIR of consecutive atoms (48 B = three 16-byte peer loads when both belong to the same
@@ -267,6 +270,10 @@ __global__ void __launch_bounds__(256) k_dd_pull(DDPeers P, unsigned long long* 
         *(unsigned*)(state + 3) = 0u;
         nl_flags[0] = s_flag;
         if (s_flag) *halo_count = 0;
+        const unsigned long long t_copy = *(volatile unsigned long long*)(state + 7);
+        const unsigned long long t_end = dd_now();
+        if (t_copy != 0ull && t_end > t_copy) state[5] += t_end - t_copy;
+        state[6] += 1ull;
     }
     if ((int)threadIdx.x < P.nranks && (int)threadIdx.x != P.rank) {
         __threadfence_system();
@@ -275,9 +282,12 @@ __global__ void __launch_bounds__(256) k_dd_pull(DDPeers P, unsigned long long* 
 }
 
 // an owner may move its atoms again only after every peer has finished reading them
-__global__ void k_dd_wait_acks(DDPeers P, unsigned long long* state) {
+__global__ void k_dd_wait_acks(DDPeers P, unsigned long long* state, unsigned long long* ack_ns) {
     const unsigned long long e = state[0];
+    const unsigned long long t0 = dd_now();
     if ((int)threadIdx.x < P.nranks && (int)threadIdx.x != P.rank) dd_wait(&P.sig[P.rank][DD_ACK + threadIdx.x], 0, e, state);
+    __syncwarp();
+    if (threadIdx.x == 0) *ack_ns += dd_now() - t0;
 }
 
 __global__ void k_halo_compact(int ngroups, unsigned char* __restrict__ mark, int* __restrict__ halo_groups, int* halo_count,
@@ -315,7 +325,7 @@ int dist_exchange_halo(b2_context* ctx) {
 int dist_before_move(b2_context* ctx) {
     if (!ctx->p2p || !ctx->acks_pending) return B2_OK;
     DDPeers P = make_peers(ctx);
-    k_dd_wait_acks<<<1, 32, 0, ctx->stream>>>(P, ctx->dd_state);
+    k_dd_wait_acks<<<1, 32, 0, ctx->stream>>>(P, ctx->dd_state, ctx->dd_state + 8);
     B2_LAUNCH_CHECK();
     ctx->acks_pending = false;
     return B2_OK;
@@ -397,8 +407,8 @@ extern "C" int b2_comm_import(b2_context* ctx, int nranks, const char* all256) {
         ctx->peer_sig[r] = (unsigned long long*)ps;
     }
     if (ctx->dd_state == nullptr) {
-        B2_CUDA(cudaMalloc(&ctx->dd_state, sizeof(unsigned long long)*8));
-        B2_CUDA(cudaMemset(ctx->dd_state, 0, sizeof(unsigned long long)*8));
+        B2_CUDA(cudaMalloc(&ctx->dd_state, sizeof(unsigned long long)*16));
+        B2_CUDA(cudaMemset(ctx->dd_state, 0, sizeof(unsigned long long)*16));
         B2_CUDA(cudaMalloc(&ctx->halo_mark, ctx->ngroups));
         B2_CUDA(cudaMemset(ctx->halo_mark, 0, ctx->ngroups));
         B2_CUDA(cudaMalloc(&ctx->halo_groups, sizeof(int)*ctx->ngroups));
@@ -407,6 +417,17 @@ extern "C" int b2_comm_import(b2_context* ctx, int nranks, const char* all256) {
     }
     ctx->p2p = true;
     program_release(ctx);
+    return B2_OK;
+}
+
+extern "C" int b2_comm_timing(b2_context* ctx, double out[4]) {
+    if (!ctx || !out) return B2_ERR_ARG;
+    out[0] = out[1] = out[2] = out[3] = 0.0;
+    if (!ctx->p2p || !ctx->dd_state) return B2_OK;
+    unsigned long long h[16];
+    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    B2_CUDA(cudaMemcpy(h, ctx->dd_state, sizeof(h), cudaMemcpyDeviceToHost));
+    out[0] = 1e-9*(double)h[4]; out[1] = 1e-9*(double)h[5]; out[2] = (double)h[6]; out[3] = 1e-9*(double)h[8];
     return B2_OK;
 }
 

@@ -295,8 +295,15 @@ struct InnerArgs {
     int batch_of[B2_INNER_MAX_FORCES];   // bonded-force index -> entry of a[] or -1
 };
 
+// tuning knobs (measured on B200: profiles/round2_pair_variants.txt)
+#ifndef B2_INNER_MINB
+#define B2_INNER_MINB 6         // resident blocks per SM the register budget is sized for
+#endif
+#ifndef B2_INNER_HOIST
+#define B2_INNER_HOIST 1        // resolve each thread's first term once per launch
+#endif
 template <bool CUSTOM>
-__global__ void __launch_bounds__(B2_CHUNK, 6) k_inner(const int* __restrict__ chunk_start,
+__global__ void __launch_bounds__(B2_CHUNK, B2_INNER_MINB) k_inner(const int* __restrict__ chunk_start,
                                                     const int* __restrict__ term_ptr,
                                                     const int2* __restrict__ terms, double* __restrict__ xg,
                                                     double* __restrict__ vg, const double* __restrict__ mass,
@@ -318,6 +325,32 @@ __global__ void __launch_bounds__(B2_CHUNK, 6) k_inner(const int* __restrict__ c
     const int t0 = term_ptr[c], t1 = term_ptr[c+1];
     const LocalGeo geo{xs, fs, base};
     bool have_local = false;
+    // This thread's first term, resolved once for the whole run when it belongs to a closed-form family (harmonic
+    // bond / angle, periodic torsion: <= 3 parameters, which travel in registers too).  The chunk's terms are dealt out
+    // one per thread; further terms of a thread (large molecules) and other families are resolved at every
+    // evaluation, as before.
+    int h_b = -1, h_ar = 0, h_a0 = 0, h_a1 = 0, h_a2 = 0, h_a3 = 0;
+    double h_p[3] = {0, 0, 0};
+    if (B2_INNER_HOIST && t0 + tid < t1) {
+        const int2 rec = terms[t0 + tid];
+        const int b = A.batch_of[rec.x];
+        if (b >= 0) {
+            const BondArgs& ba = A.a[b];
+            if (ba.family == B2_BOND_HARMONIC || ba.family == B2_ANGLE_HARMONIC || ba.family == B2_TORSION_PERIODIC) {
+                h_ar = A.arity[b];
+                const int* at = ba.atoms + (size_t)h_ar*rec.y;
+                h_a0 = ba.inv[at[0]];
+                h_a1 = ba.inv[at[1]];
+                if (h_ar > 2) h_a2 = ba.inv[at[2]];
+                if (h_ar > 3) h_a3 = ba.inv[at[3]];
+                const double* p = ba.params + (size_t)rec.y*ba.stride;
+                h_p[0] = p[0]; h_p[1] = p[1];
+                if (ba.stride > 2) h_p[2] = p[2];
+                h_b = (h_a0 >= ba.a_lo && h_a0 < ba.a_hi) ? b : -2;      // -2: resolved, owned by another rank
+            }
+        }
+    }
+    const int t_first = h_b == -1 ? t0 + tid : t0 + tid + B2_CHUNK;     // where the per-evaluation loop starts
     for (int q = 0; q < A.nops; q++) {
         const InnerOp& op = A.op[q];
         if (op.kind == 0) {
@@ -349,7 +382,14 @@ __global__ void __launch_bounds__(B2_CHUNK, 6) k_inner(const int* __restrict__ c
 #pragma unroll
             for (int k = 0; k < 3; k++) { xs[3*tid+k] = x[k]; fs[3*tid+k] = 0ull; }
             __syncthreads();
-            for (int t = t0 + tid; t < t1; t += B2_CHUNK) {
+            if (h_b >= 0) {
+                const BondArgs& ba = A.a[h_b];
+                double e = 0, w = 0;
+                if (h_ar == 2) term_bond2_core<true, false, false>(ba, h_a0, h_a1, h_p, geo, e, w);
+                else if (h_ar == 3) term_angle_core<true, false, false>(ba, h_a0, h_a1, h_a2, h_p, geo, e);
+                else term_torsion_core<true, false>(ba, h_a0, h_a1, h_a2, h_a3, h_p, geo, e);
+            }
+            for (int t = t_first; t < t1; t += B2_CHUNK) {
                 const int2 rec = terms[t];
                 const int b = A.batch_of[rec.x];
                 if (b < 0) continue;

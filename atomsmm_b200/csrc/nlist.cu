@@ -29,6 +29,7 @@ struct BuildArgs {
     int nlists;
     double rlist2[B2_MAX_LISTS];
     double rlist[B2_MAX_LISTS];
+    double rcore[B2_MAX_LISTS];      // entries beyond this distance from every atom of the i-group go to the list's tail
     int* entries[B2_MAX_LISTS];
     int* counts[B2_MAX_LISTS];
     unsigned char* gflags[B2_MAX_LISTS];
@@ -273,7 +274,17 @@ __global__ void k_cell_sort_pack(int ncells, const int* __restrict__ cell_start,
 #define NL_MARGIN 3e-4f
 #define NL_WARPS 4
 #define NL_QUEUE 40
-__global__ void __launch_bounds__(32*NL_WARPS, 5) k_build_lists(int n, int g_lo, int ngroups, Grid g,
+// tuning knobs (measured on B200: profiles/round2_pair_variants.txt)
+#ifndef B2_NL_MINB
+#define B2_NL_MINB 6            // resident blocks per SM the register budget is sized for
+#endif
+#ifndef B2_NL_FLAT
+#define B2_NL_FLAT 1            // group level: run table + flattened candidate walk (0 = nested row walk)
+#endif
+#ifndef B2_NL_PACKED
+#define B2_NL_PACKED 1          // f32x2 distance test in the atom-level sweep
+#endif
+__global__ void __launch_bounds__(32*NL_WARPS, B2_NL_MINB) k_build_lists(int n, int g_lo, int ngroups, Grid g,
                                                              const int* __restrict__ cell_start,
                                                              const float4* __restrict__ cgc,
                                                              const float4* __restrict__ cgh,
@@ -300,6 +311,10 @@ __global__ void __launch_bounds__(32*NL_WARPS, 5) k_build_lists(int n, int g_lo,
     // the NEGATED i positions as four atom PAIRS {(-x0,-x1,-y0,-y1), (-z0,-z1)} for the packed f32x2 distance test
     __shared__ float4 sP[NL_WARPS][B2_GROUP/2];
     __shared__ float2 sQ[NL_WARPS][B2_GROUP/2];
+    // run table of the group-level search: 32 rows per batch, up to two runs per row
+    __shared__ int seg_cb[NL_WARPS][64];
+    __shared__ int seg_pre[NL_WARPS][65];
+    __shared__ float4 seg_shift[NL_WARPS][64];
     const int i0 = warp*B2_GROUP;
     const float box[3] = {(float)g.box[0], (float)g.box[1], (float)g.box[2]};
     const float ibox[3] = {(float)g.inv[0], (float)g.inv[1], (float)g.inv[2]};
@@ -351,6 +366,16 @@ __global__ void __launch_bounds__(32*NL_WARPS, 5) k_build_lists(int n, int g_lo,
     }
     float rl2[B2_MAX_LISTS];
     for (int k = 0; k < B2_MAX_LISTS; k++) { const float r = (float)a.rlist[k] + NL_MARGIN; rl2[k] = r*r; }
+    // Every list is written in two parts: CORE entries (within cutoff + delta of some atom of the i-group at build
+    // time) from the front, SHELL entries (only within cutoff + skin) from the back of the group's capacity, joined
+    // at the end.  All entries are tested by the pair tiles as before -- but the shell entries, which are outside
+    // the cutoff of all eight i-atoms until something has moved by delta, sit together at the tail, where whole
+    // tile steps find no pair inside the cutoff and skip the force arithmetic (a warp-uniform branch).
+    float rc2[B2_MAX_LISTS];
+    for (int k = 0; k < B2_MAX_LISTS; k++) { const float r = (float)a.rcore[k] + NL_MARGIN; rc2[k] = r*r; }
+    int scount[B2_MAX_LISTS] = {0, 0, 0, 0};
+    int* ebase[B2_MAX_LISTS];
+    for (int k = 0; k < B2_MAX_LISTS; k++) ebase[k] = a.entries[k < a.nlists ? k : 0] + (size_t)warp*a.cap[k < a.nlists ? k : 0];
     const float rmax2 = rmax*rmax;
     int count[B2_MAX_LISTS] = {0, 0, 0, 0};
     const unsigned lt = (1u << lane) - 1u;
@@ -372,14 +397,16 @@ __global__ void __launch_bounds__(32*NL_WARPS, 5) k_build_lists(int n, int g_lo,
             if (have) {
                 const float4 pj = prel[j];
                 const float xj = e.x + pj.x, yj = e.y + pj.y, zj = e.z + pj.z;
-                if (MI) {
+                if (MI || !B2_NL_PACKED) {
 #pragma unroll
                     for (int k = 0; k < B2_GROUP; k++) {
                         const float4 pi = sxi[wib][k];
                         float dx = xj - pi.x, dy = yj - pi.y, dz = zj - pi.z;
-                        if (all[0] || wide) dx -= box[0]*rintf(dx*ibox[0]);
-                        if (all[1] || wide) dy -= box[1]*rintf(dy*ibox[1]);
-                        if (all[2] || wide) dz -= box[2]*rintf(dz*ibox[2]);
+                        if (MI) {
+                            if (all[0] || wide) dx -= box[0]*rintf(dx*ibox[0]);
+                            if (all[1] || wide) dy -= box[1]*rintf(dy*ibox[1]);
+                            if (all[2] || wide) dz -= box[2]*rintf(dz*ibox[2]);
+                        }
                         d2min = fminf(d2min, dx*dx + dy*dy + dz*dz);
                     }
                 } else {
@@ -407,16 +434,24 @@ __global__ void __launch_bounds__(32*NL_WARPS, 5) k_build_lists(int n, int g_lo,
                     }
                 }
             }
+            const int entry = (int)((m << 24) | (unsigned)j);
 #pragma unroll
             for (int k = 0; k < B2_MAX_LISTS; k++) {
                 if (k >= a.nlists) break;
                 const bool in = have && d2min < rl2[k];
+                const bool core = d2min < rc2[k];              // rc2 <= rl2: core implies in (for lanes that have an atom)
                 const unsigned ballot = __ballot_sync(FULL, in);
-                if (in) {
-                    const int pos = count[k] + __popc(ballot & lt);
-                    if (pos < a.cap[k]) a.entries[k][(size_t)warp*a.cap[k] + pos] = (int)((m << 24) | (unsigned)j);
+                if (ballot == 0u) continue;                    // warp-uniform: nothing of this sweep belongs to list k
+                const unsigned cballot = __ballot_sync(FULL, in && core);
+                const unsigned sballot = ballot & ~cballot;
+                const int nc = __popc(cballot), ns = __popc(sballot);
+                if (in && count[k] + scount[k] + nc + ns <= a.cap[k]) {
+                    const int pos = core ? count[k] + __popc(cballot & lt)
+                                         : a.cap[k] - 1 - (scount[k] + __popc(sballot & lt));
+                    ebase[k][pos] = entry;
                 }
-                count[k] += __popc(ballot);
+                count[k] += nc;
+                scount[k] += ns;
             }
         }
     };
@@ -426,6 +461,114 @@ __global__ void __launch_bounds__(32*NL_WARPS, 5) k_build_lists(int n, int g_lo,
         else sweep_t(nq, std::false_type());
     };
 
+#if B2_NL_FLAT
+    // Group level.  The search region is a set of ROWS of cells (fixed y/z cell, a range of x cells trimmed to the
+    // sphere cross-section); a row is one or two contiguous runs of the cell-ordered arrays (two when it crosses the
+    // periodic boundary).  The rows' runs are tabulated first -- one row per lane, so the ~140 instructions of index
+    // and trimming arithmetic per row are paid once per 32 rows instead of once per row by the whole warp -- and the
+    // candidates are then walked as ONE flattened index space over all runs: every step tests 32 candidates with all
+    // lanes busy, however short the individual runs are (which is what lets the cells be small in y and z too).
+    const int nrows = c_n[1]*c_n[2];
+    for (int r0 = 0; r0 < nrows; r0 += 32) {
+        const int r = r0 + lane;
+        int cb0 = 0, len0 = 0, cb1 = 0, len1 = 0;
+        float sx0 = 0.f, sx1 = 0.f, sy = 0.f, sz = 0.f;
+        if (r < nrows) {
+            const int cz = r/c_n[1], cy = r - cz*c_n[1];
+            const int uz = c_lo[2] + cz;
+            int iz = uz % g.nc[2]; if (iz < 0) iz += g.nc[2];
+            sz = all[2] ? 0.f : (float)((uz - iz)/g.nc[2])*box[2];      // periodic shift of this cell layer
+            const float gz = all[2] ? 0.f : fmaxf(0.f, fmaxf(lo[2] - (uz + 1)*cs[2], uz*cs[2] - up[2]));
+            const int uy = c_lo[1] + cy;
+            int iy = uy % g.nc[1]; if (iy < 0) iy += g.nc[1];
+            sy = all[1] ? 0.f : (float)((uy - iy)/g.nc[1])*box[1];
+            const float gy = all[1] ? 0.f : fmaxf(0.f, fmaxf(lo[1] - (uy + 1)*cs[1], uy*cs[1] - up[1]));
+            const float rem2 = rmax2 - gz*gz - gy*gy;
+            if (rem2 >= 0.f) {
+                // trim the x-range of this row of cells to the sphere cross-section
+                int u_first = c_lo[0], u_last = c_lo[0] + c_n[0] - 1;
+                if (!all[0]) {
+                    const float reach = sqrtf(rem2);
+                    u_first = max(u_first, (int)floorf((lo[0] - reach)/cs[0]));
+                    u_last = min(u_last, (int)floorf((up[0] + reach)/cs[0]));
+                }
+                if (u_first <= u_last) {
+                    const int row = (iz*g.nc[1] + iy)*g.nc[0];
+                    const int wrap = u_first >= 0 ? u_first/g.nc[0] : -((-u_first + g.nc[0] - 1)/g.nc[0]);
+                    const int ix0 = u_first - wrap*g.nc[0];
+                    const int run_end = min(u_last, u_first + (g.nc[0] - 1 - ix0));
+                    cb0 = cell_start[row + ix0];
+                    len0 = cell_start[row + ix0 + (run_end - u_first) + 1] - cb0;
+                    sx0 = all[0] ? 0.f : (float)wrap*box[0];
+                    if (run_end < u_last) {          // the row continues on the other side of the periodic boundary
+                        const int run_end2 = min(u_last, run_end + g.nc[0]);
+                        cb1 = cell_start[row];
+                        len1 = cell_start[row + (run_end2 - run_end - 1) + 1] - cb1;
+                        sx1 = (float)(wrap + 1)*box[0];
+                    }
+                }
+            }
+        }
+        __syncwarp();        // the previous batch's table has been consumed by every lane
+        seg_cb[wib][2*lane] = cb0; seg_cb[wib][2*lane+1] = cb1;
+        seg_shift[wib][2*lane] = make_float4(sx0, sy, sz, 0.f);
+        seg_shift[wib][2*lane+1] = make_float4(sx1, sy, sz, 0.f);
+        int incl = len0 + len1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up_ = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += up_;
+        }
+        const int excl = incl - (len0 + len1);
+        seg_pre[wib][2*lane] = excl; seg_pre[wib][2*lane+1] = excl + len0;
+        if (lane == 31) seg_pre[wib][64] = incl;
+        const int total = __shfl_sync(FULL, incl, 31);
+        __syncwarp();
+        int seg = 0;                                     // this lane's cursor into the run table (k only grows)
+        for (int kbase = 0; kbase < total; kbase += 32) {
+            const int k = kbase + lane;
+            bool pass = false;
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < total) {
+                while (seg_pre[wib][seg + 1] <= k) seg++;
+                const int idx = seg_cb[wib][seg] + (k - seg_pre[wib][seg]);
+                const float4 sh = seg_shift[wib][seg];
+                const float4 cj = cgc[idx], hj = cgh[idx];
+                float dx = cj.x + sh.x - ci[0], dy = cj.y + sh.y - ci[1], dz = cj.z + sh.z - ci[2];
+                if (all[0]) dx -= box[0]*rintf(dx*ibox[0]);
+                if (all[1]) dy -= box[1]*rintf(dy*ibox[1]);
+                if (all[2]) dz -= box[2]*rintf(dz*ibox[2]);
+                const float gx = fmaxf(fabsf(dx) - (hi[0] + hj.x), 0.f);
+                const float gyy = fmaxf(fabsf(dy) - (hi[1] + hj.y), 0.f);
+                const float gzz = fmaxf(fabsf(dz) - (hi[2] + hj.z), 0.f);
+                pass = gx*gx + gyy*gyy + gzz*gzz < rmax2;
+                e = make_float4(dx, dy, dz, cj.w);
+                // domain decomposition: a candidate group that this rank does not own entirely is halo
+                if (halo_mark && pass) {
+                    const int jg = __float_as_int(cj.w);
+                    if (jg*B2_GROUP < own_lo || (jg + 1)*B2_GROUP > own_hi) halo_mark[jg] = 1;
+                }
+            }
+            const unsigned ballot = __ballot_sync(FULL, pass);
+            if (pass) queue[wib][qn + __popc(ballot & lt)] = e;
+            qn += __popc(ballot);
+            __syncwarp();
+            if (qn >= 4) {
+                const int full = qn & ~3;
+                sweep(full);
+                // move the (< 4) left-over entries to the head of the queue
+                const int rest = qn - full;
+                float4 keep = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lane < rest) keep = queue[wib][full + lane];
+                __syncwarp();
+                if (lane < rest) queue[wib][lane] = keep;
+                qn = rest;
+                __syncwarp();
+            }
+        }
+    }
+#else
+    // the plain nested walk (kept for A/B measurements: -DB2_NL_FLAT=0)
     for (int cz = 0; cz < c_n[2]; cz++) {
         const int uz = c_lo[2] + cz;
         int iz = uz % g.nc[2]; if (iz < 0) iz += g.nc[2];
@@ -498,6 +641,7 @@ __global__ void __launch_bounds__(32*NL_WARPS, 5) k_build_lists(int n, int g_lo,
             }
         }
     }
+#endif
     if (qn > 0) sweep(qn);
     // fat groups: tested directly, minimum image per atom (valid because list radius < L/2)
     const int nfat = flags[8];
@@ -539,6 +683,26 @@ __global__ void __launch_bounds__(32*NL_WARPS, 5) k_build_lists(int n, int g_lo,
             }
         }
         if (qn > 0) sweep(qn);
+    }
+    // join the two parts: the shell entries move down behind the core entries.  Ascending addresses, a whole warp
+    // step read before it is written: safe even when the two regions overlap (the destination is never above the
+    // source).
+    for (int k = 0; k < a.nlists; k++) {
+        const int total = count[k] + scount[k];
+        if (total <= a.cap[k] && scount[k] > 0 && count[k] < a.cap[k] - scount[k]) {
+            int* base = a.entries[k] + (size_t)warp*a.cap[k];
+            const int src0 = a.cap[k] - scount[k];
+            __syncwarp();
+            for (int m0 = 0; m0 < scount[k]; m0 += 32) {
+                const int m = m0 + lane;
+                int v = 0;
+                if (m < scount[k]) v = base[src0 + m];
+                __syncwarp();
+                if (m < scount[k]) base[count[k] + m] = v;
+                __syncwarp();
+            }
+        }
+        count[k] = total;
     }
     if (lane == 0) {
         for (int k = 0; k < a.nlists; k++) {
@@ -595,10 +759,11 @@ int nl_setup(b2_context* ctx) {
             if (ctx->lists[k].cutoff > 0.5*ctx->box[d] + 1e-9)
                 return b2_fail(ctx, B2_ERR_ARG, "cutoff %g nm exceeds half the box length %g nm (minimum image)",
                                ctx->lists[k].cutoff, ctx->box[d]);
-        // cells are short along x (the contiguous direction of the cell-ordered arrays: the list build
-        // walks rows of cells along x) and as long as the list radius along y and z, so that a row is
-        // one long contiguous run of candidates instead of many short ones
-        double target = d == 0 ? std::max(0.5*rmax, 0.35) : std::max(rmax, 0.7);
+        // cells are short along x (the contiguous direction of the cell-ordered arrays) and as long as the list
+        // radius along y and z.  Measured (profiles/round2_build_variants.txt): halving the y/z size shrinks the
+        // searched volume but quadruples the cell count -- the single-block scan gives back what the search gains
+        static const double yz = getenv("B2_CELL_YZ") ? atof(getenv("B2_CELL_YZ")) : 1.0;
+        double target = d == 0 ? std::max(0.5*rmax, 0.35) : std::max(yz*rmax, 0.7*yz);
         int nc = std::max(1, (int)floor(ctx->box[d]/target));
         nc = std::min(nc, 160);
         ctx->ncell[d] = nc;
@@ -699,6 +864,9 @@ int nl_prepare(b2_context* ctx, bool force) {
         const NList& L = ctx->lists[k < ctx->nlists ? k : 0];
         double r = L.cutoff + ctx->skin;
         a.rlist[k] = r; a.rlist2[k] = r*r;
+        // B2_SHELL_DELTA (nm): 0 puts every entry into the core part (the lists of round 1)
+        static const double delta = getenv("B2_SHELL_DELTA") ? atof(getenv("B2_SHELL_DELTA")) : 0.02;
+        a.rcore[k] = delta > 0 ? std::min(r, L.cutoff + delta) : r + 1.0;
         a.entries[k] = L.entries; a.counts[k] = L.counts; a.gflags[k] = L.gflags; a.cap[k] = L.cap;
     }
     k_build_lists<<<std::max(1, (ctx->g_hi - ctx->g_lo + NL_WARPS - 1)/NL_WARPS), 32*NL_WARPS, 0, s>>>(

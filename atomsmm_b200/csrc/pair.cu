@@ -22,6 +22,13 @@
 
 #define FULL 0xffffffffu
 #define WPB 4   // warps per block
+// tuning knobs of the packed tiles (measured on B200: profiles/round2_pair_variants.txt)
+#ifndef B2_PAIR_MINB
+#define B2_PAIR_MINB 5          // resident blocks per SM the register budget is sized for
+#endif
+#ifndef B2_PAIR_UNROLL
+#define B2_PAIR_UNROLL 4        // steps of a chunk the scheduler may interleave
+#endif
 
 template <typename T>
 static PotParams<T> make_params(const b2_context* ctx, const PairForce& pf, float* rc2_out) {
@@ -228,9 +235,9 @@ __global__ void __launch_bounds__(32*WPB, 8) k_pair_force(int n, int g_lo, int n
 }
 
 // ---------------------------------------------------------------------------------------------
-// Packed variant (the shipped one): every lane evaluates TWO list slots per step with the f32x2 instructions of
-// sm_100a (FADD2 / FMUL2 / FFMA2, potentials.cuh) -- the tiles are bound by instruction issue, and one issue now
-// carries the arithmetic of two pairs.  Shared-memory staging is laid out for that: per 32-entry chunk 16 slot
+// Packed variant (B2_PAIR_PACKED=1; NOT the default, see launch_force): every lane evaluates TWO list slots per step
+// with the f32x2 instructions of sm_100a (FADD2 / FMUL2 / FFMA2, potentials.cuh) -- one issue carries the arithmetic
+// of two pairs.  Shared-memory staging is laid out for that: per 32-entry chunk 16 slot
 // PAIRS, each {(x0,x1,y0,y1), (z0,z1,q0,q1), (hs0,hs1,se0,se1), (entry0,entry1)}, so an LDS.128 lands directly in
 // the aligned register pairs the packed instructions take.  Pipeline, band logic and reduction as above.
 // Differences are accumulated as x_j - x_i (one packed add against the negated i position) and the sign is
@@ -241,18 +248,26 @@ __device__ __forceinline__ void band_record(const BandBuffer& bb, int i, unsigne
     if (slot < bb.capacity) { bb.pairs[2*slot] = i; bb.pairs[2*slot+1] = (int)(entry & 0xffffffu); }
 }
 
-template <class POT2, bool MINIMG>
+// MASKED = false: no entry of the chunk carries exclusion bits (decided once per chunk by a warp vote at staging
+// time; true for ~8 chunks in 10) -- the entry words are then read only by the rare band path.
+// The four steps of a chunk are straight-line code: band pairs are only FLAGGED inside the loop and recorded after
+// it, so that no branch separates the steps and their (long, dependent) arithmetic chains can be interleaved by
+// the scheduler -- with ~6 warps per scheduler the tiles are otherwise bound by dependent-issue latency.
+template <class POT2, bool MINIMG, bool MASKED>
 __device__ __forceinline__ void sweep_chunk2(const POT2& pot, const float4* __restrict__ sA, const float4* __restrict__ sB,
                                              const float4* __restrict__ sC, const uint2* __restrict__ sD, int jj,
                                              unsigned ibit, F2 nx, F2 ny, F2 nz, F2 kqi, F2 hsi, F2 sei, float rc2_hi,
                                              float rc2_lo, float3 box, float3 inv, int i, const BandBuffer& bb,
                                              double& fx, double& fy, double& fz) {
     F2 ax = f2(0.f), ay = f2(0.f), az = f2(0.f);      // fp32 partial sums over one chunk (<= 8 pairs per lane)
-#pragma unroll
+    unsigned bandbits = 0u;
+    constexpr int unroll = B2_PAIR_UNROLL;
+#pragma unroll unroll
     for (int t = 0; t < 4; t++) {
         const int pp = 4*t + jj;
-        const float4 A = sA[pp], B = sB[pp];
-        const uint2 D = sD[pp];
+        const float4 A = sA[pp], B = sB[pp], C = sC[pp];
+        uint2 D = make_uint2(0u, 0u);
+        if (MASKED) D = sD[pp];
         F2 dx = f2(A.x, A.y) + nx, dy = f2(A.z, A.w) + ny, dz = f2(B.x, B.y) + nz;
         if (MINIMG) {
             dx.v.x -= box.x*rintf(dx.v.x*inv.x); dx.v.y -= box.x*rintf(dx.v.y*inv.x);
@@ -260,24 +275,25 @@ __device__ __forceinline__ void sweep_chunk2(const POT2& pot, const float4* __re
             dz.v.x -= box.z*rintf(dz.v.x*inv.z); dz.v.y -= box.z*rintf(dz.v.y*inv.z);
         }
         const F2 r2 = fma2(dz, dz, fma2(dy, dy, dx*dx));
-        bool in0 = r2.v.x < rc2_hi && !(D.x & ibit);      // rc2_hi is the OUTER edge of the band
-        bool in1 = r2.v.y < rc2_hi && !(D.y & ibit);
-        if (!(in0 || in1)) continue;
-        if ((in0 && r2.v.x >= rc2_lo) || (in1 && r2.v.y >= rc2_lo)) {     // a few hundred pairs per launch
-            if (in0 && r2.v.x >= rc2_lo) { band_record(bb, i, D.x); in0 = false; }
-            if (in1 && r2.v.y >= rc2_lo) { band_record(bb, i, D.y); in1 = false; }
-        }
-        const float4 C = sC[pp];
+        // hit: inside the INNER edge of the band and not excluded -> evaluated here; band: settled in float64
+        const bool ex0 = D.x & ibit, ex1 = D.y & ibit;
+        const bool hit0 = r2.v.x < rc2_lo && !ex0, hit1 = r2.v.y < rc2_lo && !ex1;
+        const bool band0 = r2.v.x < rc2_hi && !ex0 && !hit0, band1 = r2.v.y < rc2_hi && !ex1 && !hit1;
+        bandbits |= (band0 ? 1u << (2*t) : 0u) | (band1 ? 2u << (2*t) : 0u);
         F2 fr = pot(r2, kqi*f2(B.z, B.w), hsi + f2(C.x, C.y), sei*f2(C.z, C.w));
-        fr = f2(in0 ? fr.v.x : 0.f, in1 ? fr.v.y : 0.f);      // select, not multiply: masked slots may hold inf / NaN
+        fr = f2(hit0 ? fr.v.x : 0.f, hit1 ? fr.v.y : 0.f);    // select, not multiply: masked slots may hold inf / NaN
         ax = fma2(fr, dx, ax); ay = fma2(fr, dy, ay); az = fma2(fr, dz, az);
+    }
+    if (bandbits) {                                            // a few hundred pairs per launch
+        for (int b = 0; b < 8; b++)
+            if (bandbits >> b & 1u) band_record(bb, i, reinterpret_cast<const unsigned*>(&sD[4*(b >> 1) + jj])[b & 1]);
     }
     // d = x_j - x_i: the force on i is -sum.  fp64 across chunks: no long fp32 sums
     fx -= (double)(ax.v.x + ax.v.y); fy -= (double)(ay.v.x + ay.v.y); fz -= (double)(az.v.x + az.v.y);
 }
 
 template <class POT2>
-__global__ void __launch_bounds__(32*WPB, 6) k_pair_force2(int n, int g_lo, int ngroups, const int4* __restrict__ xq,
+__global__ void __launch_bounds__(32*WPB, B2_PAIR_MINB) k_pair_force2(int n, int g_lo, int ngroups, const int4* __restrict__ xq,
                                                        const float4* __restrict__ par,
                                                        const int* __restrict__ entries,
                                                        const int* __restrict__ counts,
@@ -323,6 +339,7 @@ __global__ void __launch_bounds__(32*WPB, 6) k_pair_force2(int n, int g_lo, int 
         b[0] = xj.z; b[2] = pj.x;
         c[0] = pj.y; c[2] = pj.z;
         reinterpret_cast<int*>(&sD[wib][buf][pr])[half] = e;
+        const bool masked = __any_sync(FULL, ((unsigned)e >> 24) != 0u);     // exclusions, self pairs, padding
         if (c0 + 32 < cnt) {
             e = e_next;
             qj = xq[e & 0xffffff];
@@ -332,11 +349,14 @@ __global__ void __launch_bounds__(32*WPB, 6) k_pair_force2(int n, int g_lo, int 
         }
         __syncwarp();
         if (minimg)
-            sweep_chunk2<POT2, true>(pot, sA[wib][buf], sB[wib][buf], sC[wib][buf], sD[wib][buf], jj, ibit, nx, ny, nz, kqi,
-                                     hsi, sei, rc2_hi, rc2_lo, box, inv, i < n ? i : -1, bb, fx, fy, fz);
+            sweep_chunk2<POT2, true, true>(pot, sA[wib][buf], sB[wib][buf], sC[wib][buf], sD[wib][buf], jj, ibit, nx, ny, nz,
+                                           kqi, hsi, sei, rc2_hi, rc2_lo, box, inv, i < n ? i : -1, bb, fx, fy, fz);
+        else if (masked)
+            sweep_chunk2<POT2, false, true>(pot, sA[wib][buf], sB[wib][buf], sC[wib][buf], sD[wib][buf], jj, ibit, nx, ny, nz,
+                                            kqi, hsi, sei, rc2_hi, rc2_lo, box, inv, i < n ? i : -1, bb, fx, fy, fz);
         else
-            sweep_chunk2<POT2, false>(pot, sA[wib][buf], sB[wib][buf], sC[wib][buf], sD[wib][buf], jj, ibit, nx, ny, nz, kqi,
-                                      hsi, sei, rc2_hi, rc2_lo, box, inv, i < n ? i : -1, bb, fx, fy, fz);
+            sweep_chunk2<POT2, false, false>(pot, sA[wib][buf], sB[wib][buf], sC[wib][buf], sD[wib][buf], jj, ibit, nx, ny, nz,
+                                             kqi, hsi, sei, rc2_hi, rc2_lo, box, inv, i < n ? i : -1, bb, fx, fy, fz);
         buf ^= 1;
     }
     fx += __shfl_xor_sync(FULL, fx, 1); fy += __shfl_xor_sync(FULL, fy, 1); fz += __shfl_xor_sync(FULL, fz, 1);
@@ -602,8 +622,12 @@ static int launch_force(b2_context* ctx, const PairForce& pf, POT pot, POTD potd
         cudaEventRecord(ev0, stream);
     }
     const float3 boxf = make_float3((float)ctx->box[0], (float)ctx->box[1], (float)ctx->box[2]);
-    static const bool scalar_pair_tiles = getenv("B2_PAIR_SCALAR") != nullptr;
-    if (scalar_pair_tiles)            // B2_PAIR_SCALAR=1: the one-slot-per-lane tiles, kept for A/B measurements
+    // B2_PAIR_PACKED=1 selects the f32x2 tiles (two list slots per lane and step).  Measured on B200
+    // (profiles/round2_pair_variants.txt): FFMA2 / FMUL2 / FADD2 issue at HALF the rate of their scalar forms, so the
+    // fp32 pipe sees the same work and the packed tiles are 4-13 % SLOWER than the one-slot-per-lane tiles in every
+    // register / unrolling variant tried; they stay in the build as the measured alternative, not as the default.
+    static const bool scalar_pair_tiles = getenv("B2_PAIR_PACKED") == nullptr;
+    if (scalar_pair_tiles)
         k_pair_force<POT><<<blocks, 32*WPB, 0, stream>>>(ctx->n, ctx->g_lo, ctx->g_hi, ctx->xq, ctx->par[pf.set],
                                                               L.entries, L.counts, L.gflags, L.cap, out,
                                                               accumulate ? 1 : 0, pot, rc2, bb, boxf);

@@ -237,9 +237,9 @@ struct SoftcorePot {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Packed fp32x2 force functor (hot path).  sm_100a has FFMA2 / FADD2 / FMUL2: one instruction issue does
-// the arithmetic of TWO pairs, and the pair tiles are bound by instruction issue.  Every lane of a tile
-// therefore evaluates two list slots at once; the closed forms above are restated on a two-wide value
+// Packed fp32x2 force functor (the B2_PAIR_PACKED=1 tiles; measured slower than the scalar tiles on B200, see
+// pair.cu).  sm_100a has FFMA2 / FADD2 / FMUL2: one instruction issue does the arithmetic of TWO pairs.  Every
+// lane of a packed tile evaluates two list slots at once; the closed forms above are restated on a two-wide value
 // type with explicit fused multiply-adds (the *_rn intrinsics are never contracted by the compiler).
 // Only what the force kernels need (no energies) -- energies / virials stay in the float64 functors.
 // Compiles for the host too (component-wise fmaf), so the restatement is checked against the

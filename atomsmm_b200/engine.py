@@ -21,7 +21,8 @@ from . import unit
 from .unit import md_value as _md
 
 _LIB = None
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libatomsmm_b200.so')
+# B2_LIBRARY selects another build of the same engine (kernel tuning experiments, scripts/build_variants.sh)
+_LIB_PATH = os.environ.get('B2_LIBRARY') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libatomsmm_b200.so')
 
 c_int_p = ctypes.POINTER(ctypes.c_int)
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -82,6 +83,8 @@ _SIGNATURES = {
     'b2_comm_export': [c_void, ctypes.c_char_p],
     'b2_comm_import': [c_void, ctypes.c_int, ctypes.c_char_p],
     'b2_comm_mode': [c_void, c_int_p, ctypes.POINTER(ctypes.c_longlong)],
+    'b2_comm_timing': [c_void, c_double_p],
+    'b2_get_order': [c_void, c_int_p],
     'b2_partition_ranges': [ctypes.c_int, c_int_p, ctypes.c_int, c_int_p],
     'b2_hilbert_index': [c_double_p, c_double_p, ctypes.POINTER(ctypes.c_ulonglong)],
     'b2_comm_info': [c_void, c_int_p, c_int_p, c_int_p, c_int_p, ctypes.POINTER(ctypes.c_longlong)],
@@ -356,6 +359,12 @@ class Context(object):
                 warnings.warn('peer-memory exchange unavailable on some rank (%s, codes %r): using the NCCL all-gather path'
                               % (message.decode() if message else 'ok here', verdicts))
 
+    def spatial_order(self):
+        """Diagnostic: caller index of the atom at every position of the engine's spatial order."""
+        out = np.empty(self._n, dtype=np.int32)
+        self._call('b2_get_order', out.ctypes.data_as(c_int_p))
+        return out
+
     def comm_info(self):
         rank, nranks, lo, hi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         exchanges = ctypes.c_longlong()
@@ -363,9 +372,14 @@ class Context(object):
                    ctypes.byref(exchanges))
         p2p, halo = ctypes.c_int(), ctypes.c_longlong()
         self._call('b2_comm_mode', ctypes.byref(p2p), ctypes.byref(halo))
+        timing = (ctypes.c_double*4)()
+        self._call('b2_comm_timing', timing)
         return dict(rank=rank.value, nranks=nranks.value, lo=lo.value, hi=hi.value, exchanges=exchanges.value,
                     exchange=getattr(self, '_exchange', 'none') if nranks.value > 1 else 'none',
-                    halo_atoms=halo.value)
+                    halo_atoms=halo.value,
+                    # device-side clock of the peer-memory exchange (seconds since the context was created)
+                    exchange_clock=dict(wait_for_posts_s=round(timing[0], 6), halo_copy_s=round(timing[1], 6),
+                                        exchanges=int(timing[2]), wait_for_acks_s=round(timing[3], 6)))
 
     # -- description -> C ABI ----------------------------------------------------------------------
     def _describe(self):

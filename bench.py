@@ -418,6 +418,17 @@ def main():
     elapsed = float(t.item())
     value = replicas*n*md*args.steps/elapsed
     comm = context.comm_info()
+    if dd:
+        # where the exchanges spend their time, per rank: microseconds per exchange waiting for the slowest
+        # peer's post, copying the halo out of peer memory, and waiting for the readers' acknowledgements
+        clock = comm.get('exchange_clock') or {}
+        k = max(1, clock.get('exchanges', 0))
+        mine = dict(rank=rank, wait_for_posts_us=round(1e6*clock.get('wait_for_posts_s', 0.0)/k, 1),
+                    halo_copy_us=round(1e6*clock.get('halo_copy_s', 0.0)/k, 1),
+                    wait_for_acks_us=round(1e6*clock.get('wait_for_acks_s', 0.0)/k, 1), exchanges=clock.get('exchanges', 0))
+        every = [None]*world
+        dist.all_gather_object(every, mine)
+        comm['exchange_clock_by_rank'] = every
 
     # ---- end to end through the public API with host buffers --------------------------------------
     host_x = torch.from_numpy(pos.copy()).pin_memory()
@@ -487,11 +498,29 @@ def main():
         except (OSError, ValueError, KeyError):
             pass
         step_bytes = 1176.0 if args.workload in ('c2', 'c5') else None      # [4,2,1] + SY3-NH
+        # throughput of every pair kernel in list slots (8 per entry) and, where the first-frame
+        # gate counted the interacting pairs, in useful pair evaluations (every pair is evaluated in both tiles),
+        # beside what one SM sub-partition issuing one warp instruction per cycle would allow per slot
+        pair_sets = (parity or {}).get('pair_sets') if isinstance(parity, dict) else None
+        pair_kernels = []
+        for p in used:
+            t = p['total_ms']*1e-3/p['launches']
+            rec = dict(kernel=p['name'], group=p['group'], launches=p['launches'], avg_launch_us=round(t*1e6, 1),
+                       list_entries=p['entries'], slots_per_s=8.0*p['entries']/t)
+            rec['issue_cycles_per_warp_step'] = round(148*4*clocks['sm_mhz']*1e6*t/(8.0*p['entries']/32.0), 1) \
+                if clocks and clocks.get('sm_mhz') else None
+            if isinstance(pair_sets, dict) and world == 1:
+                # the near list serves group 1, the far list group 2 (RESPASystem layout)
+                counted = pair_sets.get(str(p['group']))
+                if counted:
+                    rec['useful_pair_evaluations_per_s'] = 2.0*counted['pairs']/t
+                    rec['slots_inside_cutoff'] = round(2.0*counted['pairs']/(8.0*p['entries']), 3)
+            pair_kernels.append(rec)
         roofline = dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved/peak, traffic=traffic,
                         traffic_source=traffic_source, peak_kind=peak_kind,
                         kernel='k_pair_force<%s> group %d' % (dominant['name'], dominant['group']),
                         avg_launch_us=avg_s*1e6, algorithmic_bytes_per_launch=bytes_per_launch,
-                        list_entries=dominant['entries'],
+                        list_entries=dominant['entries'], pair_kernels=pair_kernels,
                         phases_ms_per_md_step={k: round(v/8.0, 4) for k, v in phases.items()},
                         phases_ms_per_md_step_by_rank=([{k: round(v/8.0, 4) for k, v in p.items()} for p in all_phases]
                                                        if world > 1 else None),

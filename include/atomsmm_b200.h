@@ -247,6 +247,10 @@ B2_API int b2_partition_ranges(int n, const int* molecule_sorted, int nranks, in
  * orders molecules; consecutive indices are face-adjacent cells, so runs of consecutive atoms -- the
  * 8-atom i-groups, the molecule chunks, the ranks' ownership ranges -- are spatially compact. */
 B2_API int b2_hilbert_index(const double position[3], const double box[3], unsigned long long* out_key);
+/* diagnostic: the engine's current spatial order, orig_host[s] = caller index of the atom at position s (n ints).
+ * The order is computed on the device (csrc/order.cu: Hilbert keys, radix sort, gathers); tests compare it with the
+ * order b2_hilbert_index defines.  It never leaks through any other entry point. */
+B2_API int b2_get_order(b2_context* ctx, int* orig_host);
 /* Peer-memory halo exchange over NVLink / NVSwitch (the default when the GPUs of the node can map each
  * other's memory).  After b2_comm_init every rank exports a 256-byte record (cudaIpc handles of its
  * position array and of its signal block), the host side all-gathers the records (rank order) and every
@@ -264,6 +268,11 @@ B2_API int b2_comm_mode(b2_context* ctx, int* peer_memory, long long* halo_atoms
 /* ownership range [lo, hi) of this rank in the engine's spatial order, and the number of
  * position exchanges performed so far */
 B2_API int b2_comm_info(b2_context* ctx, int* rank, int* nranks, int* lo, int* hi, long long* exchanges);
+/* device-side clock of the peer-memory exchange, accumulated since the context was created (measurement aid,
+ * no reference counterpart): out[0] = seconds spent waiting for the peers' "positions final" posts,
+ * out[1] = seconds copying halo positions out of the owners' memory, out[2] = number of exchanges,
+ * out[3] = seconds owners waited for the readers' acknowledgements before moving their atoms */
+B2_API int b2_comm_timing(b2_context* ctx, double out[4]);
 
 #ifdef __cplusplus
 }

@@ -19,3 +19,4 @@ for f in ('r2j_c5', 'r2j_c5_scalar', 'r2j_c2'):
     except Exception as e:
         print(f, 'FAILED', e)
 PY
+bash scripts/gpu_call11.sh

@@ -10,12 +10,13 @@ import bench  # noqa: E402
 import torch  # noqa: E402
 from atomsmm_b200 import mm, unit  # noqa: E402
 
-system, pos, vel = bench.build_workload(4)
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+system, pos, vel = bench.build_workload(reps)
 integrator, dof = bench.make_integrator(system)
 context = mm.Context(system, integrator, mm.Platform.getPlatformByName('B200'))
 context.setPositions(pos)
 context.setVelocities(vel)
-integrator.step(1300)
+integrator.step(1300 if reps <= 4 else 100)
 host_x = torch.from_numpy(pos.copy()).pin_memory()
 host_v = torch.from_numpy(vel.copy()).pin_memory()
 
