@@ -30,6 +30,7 @@ struct BuildArgs {
     double rlist2[B2_MAX_LISTS];
     double rlist[B2_MAX_LISTS];
     double rcore[B2_MAX_LISTS];      // entries beyond this distance from every atom of the i-group go to the list's tail
+    float rl2f[B2_MAX_LISTS], rc2f[B2_MAX_LISTS];   // (rlist + margin)^2, (rcore + margin)^2 in the sweep's fp32 arithmetic
     int* entries[B2_MAX_LISTS];
     int* counts[B2_MAX_LISTS];
     unsigned char* gflags[B2_MAX_LISTS];
@@ -155,7 +156,10 @@ __global__ void k_group_geom(int n, int ngroups, const double* __restrict__ x, G
     if (threadIdx.x < 3) {
         float m = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, smax[w][threadIdx.x]);
-        if (m > 0.f) atomicMax(&hmax_bits[threadIdx.x], __float_as_int(m));   // m > 0: int order = float order
+        // m > 0: int order = float order.  Read first: after the first few blocks hardly any block raises the maximum,
+        // and 16 k blocks hammering three addresses with atomics serialise in the L2 (the kernel's former bottleneck)
+        if (m > 0.f && __float_as_int(m) > *(volatile int*)&hmax_bits[threadIdx.x])
+            atomicMax(&hmax_bits[threadIdx.x], __float_as_int(m));
     }
 }
 
@@ -315,6 +319,7 @@ __global__ void __launch_bounds__(32*NL_WARPS, B2_NL_MINB) k_build_lists(int n, 
     __shared__ int seg_cb[NL_WARPS][64];
     __shared__ int seg_pre[NL_WARPS][65];
     __shared__ float4 seg_shift[NL_WARPS][64];
+    __shared__ int* s_ebase[NL_WARPS][B2_MAX_LISTS];     // this group's slice of every list
     const int i0 = warp*B2_GROUP;
     const float box[3] = {(float)g.box[0], (float)g.box[1], (float)g.box[2]};
     const float ibox[3] = {(float)g.inv[0], (float)g.inv[1], (float)g.inv[2]};
@@ -364,18 +369,19 @@ __global__ void __launch_bounds__(32*NL_WARPS, B2_NL_MINB) k_build_lists(int n, 
             a.gflags[k][warp] = f;
         }
     }
-    float rl2[B2_MAX_LISTS];
-    for (int k = 0; k < B2_MAX_LISTS; k++) { const float r = (float)a.rlist[k] + NL_MARGIN; rl2[k] = r*r; }
     // Every list is written in two parts: CORE entries (within cutoff + delta of some atom of the i-group at build
     // time) from the front, SHELL entries (only within cutoff + skin) from the back of the group's capacity, joined
     // at the end.  All entries are tested by the pair tiles as before -- but the shell entries, which are outside
     // the cutoff of all eight i-atoms until something has moved by delta, sit together at the tail, where whole
     // tile steps find no pair inside the cutoff and skip the force arithmetic (a warp-uniform branch).
-    float rc2[B2_MAX_LISTS];
-    for (int k = 0; k < B2_MAX_LISTS; k++) { const float r = (float)a.rcore[k] + NL_MARGIN; rc2[k] = r*r; }
+    // (squared radii come precomputed from the host and the lists' base pointers live in shared memory: with 80
+    // registers the compiler otherwise re-derives both at every emission)
     int scount[B2_MAX_LISTS] = {0, 0, 0, 0};
-    int* ebase[B2_MAX_LISTS];
-    for (int k = 0; k < B2_MAX_LISTS; k++) ebase[k] = a.entries[k < a.nlists ? k : 0] + (size_t)warp*a.cap[k < a.nlists ? k : 0];
+    if (lane < B2_MAX_LISTS) {
+        const int k = lane < a.nlists ? lane : 0;
+        s_ebase[wib][lane] = a.entries[k] + (size_t)warp*a.cap[k];
+    }
+    __syncwarp();
     const float rmax2 = rmax*rmax;
     int count[B2_MAX_LISTS] = {0, 0, 0, 0};
     const unsigned lt = (1u << lane) - 1u;
@@ -438,8 +444,8 @@ __global__ void __launch_bounds__(32*NL_WARPS, B2_NL_MINB) k_build_lists(int n, 
 #pragma unroll
             for (int k = 0; k < B2_MAX_LISTS; k++) {
                 if (k >= a.nlists) break;
-                const bool in = have && d2min < rl2[k];
-                const bool core = d2min < rc2[k];              // rc2 <= rl2: core implies in (for lanes that have an atom)
+                const bool in = have && d2min < a.rl2f[k];
+                const bool core = d2min < a.rc2f[k];           // rc2 <= rl2: core implies in (for lanes that have an atom)
                 const unsigned ballot = __ballot_sync(FULL, in);
                 if (ballot == 0u) continue;                    // warp-uniform: nothing of this sweep belongs to list k
                 const unsigned cballot = __ballot_sync(FULL, in && core);
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(32*NL_WARPS, B2_NL_MINB) k_build_lists(int n, 
                 if (in && count[k] + scount[k] + nc + ns <= a.cap[k]) {
                     const int pos = core ? count[k] + __popc(cballot & lt)
                                          : a.cap[k] - 1 - (scount[k] + __popc(sballot & lt));
-                    ebase[k][pos] = entry;
+                    s_ebase[wib][k][pos] = entry;
                 }
                 count[k] += nc;
                 scount[k] += ns;
@@ -867,6 +873,8 @@ int nl_prepare(b2_context* ctx, bool force) {
         // B2_SHELL_DELTA (nm): 0 puts every entry into the core part (the lists of round 1)
         static const double delta = getenv("B2_SHELL_DELTA") ? atof(getenv("B2_SHELL_DELTA")) : 0.02;
         a.rcore[k] = delta > 0 ? std::min(r, L.cutoff + delta) : r + 1.0;
+        const float rl = (float)a.rlist[k] + NL_MARGIN, rc = (float)a.rcore[k] + NL_MARGIN;
+        a.rl2f[k] = rl*rl; a.rc2f[k] = rc*rc;
         a.entries[k] = L.entries; a.counts[k] = L.counts; a.gflags[k] = L.gflags; a.cap[k] = L.cap;
     }
     k_build_lists<<<std::max(1, (ctx->g_hi - ctx->g_lo + NL_WARPS - 1)/NL_WARPS), 32*NL_WARPS, 0, s>>>(

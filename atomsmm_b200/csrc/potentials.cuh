@@ -49,8 +49,13 @@ B2_HD void b2_inverse(float r2, float& rinv, float& rinv2) {
     rinv2 = y*y;
 }
 B2_HD void b2_inverse(double r2, double& rinv, double& rinv2) {
+#ifdef __CUDA_ARCH__
+    rinv = rsqrt(r2);              // one reciprocal square root (<= 1 ulp) instead of a square root and two divisions
+    rinv2 = rinv*rinv;
+#else
     rinv = 1.0/sqrt(r2);
     rinv2 = 1.0/r2;
+#endif
 }
 B2_HD float b2_erfc(float x) { return erfcf(x); }
 B2_HD double b2_erfc(double x) { return erfc(x); }
