@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'csrc', '_obj')
 LIBRARY = os.path.join(HERE, 'libatomsmm_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-I', OBJ,
          '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '-Xptxas', '-v']
 # tuning experiments: B2_EXTRA_NVCC_FLAGS="-DB2_PAIR_MINB=6" python -m atomsmm_b200.build --force, B2_LIBRARY=<path> at run time
 FLAGS += os.environ.get('B2_EXTRA_NVCC_FLAGS', '').split()
@@ -54,8 +54,23 @@ def _compile(src, verbose):
     return obj
 
 
+def _embed_rng_source():
+    """csrc/_obj/vm_rng_embed.h: the Philox / RngStream section of vm.cuh as a string constant, so that the kernels
+    csrc/jit.cu generates at run time draw from the very same stream as the precompiled ones."""
+    with open(os.path.join(CSRC, 'vm.cuh')) as handle:
+        text = handle.read()
+    begin = text.index('// ---- Philox4x32-10')
+    end = text.index('// ---- variable access')
+    body = 'static const char* B2_RNG_SOURCE = R"B2RNG(\n' + text[begin:end] + ')B2RNG";\n'
+    path = os.path.join(OBJ, 'vm_rng_embed.h')
+    if not os.path.exists(path) or open(path).read() != body:
+        with open(path, 'w') as handle:
+            handle.write(body)
+
+
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
+    _embed_rng_source()
     if force:
         for f in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, f))
@@ -65,7 +80,7 @@ def build(force=False, verbose=False):
         # link under a temporary name and rename: a snapshot of the tree never sees a half-written library
         staging = LIBRARY + '.tmp%d' % os.getpid()
         cmd = [NVCC, '-shared', '-o', staging] + objects + ['-gencode', 'arch=compute_100a,code=sm_100a',
-                                                            '-Xcompiler', '-fPIC', '-lcudart', '-lcufft']
+                                                            '-Xcompiler', '-fPIC', '-lcudart', '-lcufft', '-ldl']
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError('link failed:\n%s\n%s' % (proc.stdout, proc.stderr))

@@ -143,6 +143,7 @@ extern "C" int b2_destroy(b2_context* ctx) {
     for (int s = 0; s < B2_MAX_SETS; s++) { cudaFree(ctx->par[s]); cudaFree(ctx->pard[s]); }
     cudaFree(ctx->massd); cudaFree(ctx->invm); cudaFree(ctx->orig); cudaFree(ctx->inv); cudaFree(ctx->exmask);
     order_release(ctx);
+    jit_release(ctx);
     cudaFree(ctx->excl_ptr); cudaFree(ctx->excl_idx); cudaFree(ctx->scratch3);
     for (int g = 0; g < B2_FSLOTS; g++) cudaFree(ctx->fbuf[g]);
     for (double* p : ctx->perdof) cudaFree(p);
@@ -536,6 +537,23 @@ extern "C" int b2_hilbert_index(const double position[3], const double box[3], u
     return B2_OK;
 }
 
+extern "C" int b2_set_jit(b2_context* ctx, int enabled) {
+    if (!ctx) return B2_ERR_ARG;
+    if (ctx->jit_enabled != (enabled != 0)) {
+        program_release(ctx);
+        jit_release(ctx);
+        ctx->jit_enabled = enabled != 0;
+    }
+    return B2_OK;
+}
+
+extern "C" int b2_get_jit_stats(b2_context* ctx, long long out_host[2]) {
+    if (!ctx || !out_host) return B2_ERR_ARG;
+    out_host[0] = ctx->jit_compiled;
+    out_host[1] = ctx->jit_launches;
+    return B2_OK;
+}
+
 extern "C" int b2_get_order(b2_context* ctx, int* orig_host) {
     if (!ctx || !orig_host) return B2_ERR_ARG;
     if (!ctx->have_order) return b2_fail(ctx, B2_ERR_STATE, "positions have not been set");
@@ -885,6 +903,7 @@ extern "C" int b2_load_program(b2_context* ctx, const int* ops, int nops, const 
     if (!ctx || ctx->n == 0) return b2_fail(ctx, B2_ERR_STATE, "set particles first");
     if (nperdof > B2_MAX_PERDOF) return b2_fail(ctx, B2_ERR_UNSUPPORTED, "at most %d per-DOF variables", B2_MAX_PERDOF);
     program_release(ctx);
+    jit_release(ctx);
     for (PairForce& pf : ctx->pair_forces)
         for (int k = 0; k < B2_MAX_PAIR_PARAMS; k++) pf.bind[k] = -1;
     ctx->ops.resize(nops);

@@ -230,6 +230,13 @@ struct b2_context {
     std::vector<b2_op> ops;
     int *code = nullptr; int ncode = 0;
     std::vector<int> h_code;                      // host copy (kick term tables live in the code pool)
+    // run-time compiled per-DOF / sum steps (jit.cu): module, one kernel per op (or null: interpreter), statistics
+    void* jit_module = nullptr;
+    std::vector<void*> jit_fn;
+    bool jit_ready = false;
+    bool jit_enabled = true;                      // b2_set_jit
+    int jit_compiled = 0;
+    long long jit_launches = 0;
     double *consts = nullptr; int nconsts = 0;
     double *globals = nullptr; int nglobals = 0;
     double* sum_partial = nullptr;                // per-block partial sums (sized by ensure_partials)
@@ -313,6 +320,10 @@ void dist_release(b2_context* ctx);
 int forces_ensure(b2_context* ctx, uint32_t mask, int slot);
 int inner_prepare(b2_context* ctx);
 int order_refresh(b2_context* ctx);
+// jit.cu: NVRTC compilation of the generic per-DOF / sum steps of the loaded program
+int jit_prepare(b2_context* ctx);
+void jit_release(b2_context* ctx);
+int jit_launch(b2_context* ctx, int op_index, unsigned blocks, unsigned threads, void** args);
 // order.cu: spatial order computed on the device from caller-order positions (orig, inv, static tables; h_orig on host)
 int order_compute_device(b2_context* ctx, const double* x_user);
 int order_refresh_param_set(b2_context* ctx, int k);

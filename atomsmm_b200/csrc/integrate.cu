@@ -787,9 +787,18 @@ static int run_one_step(b2_context* ctx) {
         case B2_OP_PERDOF: {
             PerDofTable tab = make_table(ctx);
             if (op.a == 0) B2_TRY(dist_before_move(ctx));
-            k_perdof<<<std::max(1, (ndof + T - 1)/T), T, 0, s>>>(3*lo, 3*hi, tab, op.a, ctx->code + op.b, op.c, ctx->consts,
-                                                      ctx->globals, ctx->rng_state, op.e, 0);
-            B2_LAUNCH_CHECK();
+            if (k < ctx->jit_fn.size() && ctx->jit_fn[k]) {
+                // the step's own kernel, compiled from its bytecode at program load (jit.cu)
+                int dof_lo = 3*lo, dof_hi = 3*hi, target = op.a, serial = op.e;
+                const double* consts = ctx->consts; const double* globals = ctx->globals;
+                const unsigned long long* rng_state = ctx->rng_state;
+                void* args[] = {&dof_lo, &dof_hi, &tab, &target, &consts, &globals, &rng_state, &serial};
+                B2_TRY(jit_launch(ctx, (int)k, (unsigned)std::max(1, (ndof + T - 1)/T), T, args));
+            } else {
+                k_perdof<<<std::max(1, (ndof + T - 1)/T), T, 0, s>>>(3*lo, 3*hi, tab, op.a, ctx->code + op.b, op.c, ctx->consts,
+                                                          ctx->globals, ctx->rng_state, op.e, 0);
+                B2_LAUNCH_CHECK();
+            }
             if (op.a == 0) ctx->pos_version++;
             if (op.a == 1) ctx->v_version++;
             break;
@@ -800,8 +809,17 @@ static int run_one_step(b2_context* ctx) {
                 k_mvv_partial<<<blocks, T, 0, s>>>(lo, hi, ctx->v, ctx->massd, ctx->sum_partial);
             } else {
                 PerDofTable tab = make_table(ctx);
-                k_sum_partial<<<blocks, T, 0, s>>>(3*lo, 3*hi, tab, ctx->code + op.b, op.c, ctx->consts, ctx->globals,
-                                                    ctx->sum_partial);
+                if (k < ctx->jit_fn.size() && ctx->jit_fn[k]) {
+                    int dof_lo = 3*lo, dof_hi = 3*hi;
+                    const double* consts = ctx->consts; const double* globals = ctx->globals;
+                    double* partial = ctx->sum_partial;
+                    void* args[] = {&dof_lo, &dof_hi, &tab, &consts, &globals, &partial};
+                    B2_TRY(jit_launch(ctx, (int)k, blocks, T, args));
+                    ctx->counters[0]--;          // counted once, by the check below
+                } else {
+                    k_sum_partial<<<blocks, T, 0, s>>>(3*lo, 3*hi, tab, ctx->code + op.b, op.c, ctx->consts, ctx->globals,
+                                                        ctx->sum_partial);
+                }
             }
             B2_LAUNCH_CHECK();
             k_sum_final<<<1, 256, 0, s>>>(blocks, ctx->sum_partial, ctx->globals, op.a);
@@ -878,6 +896,26 @@ static int run_one_step(b2_context* ctx) {
     return B2_OK;
 }
 
+// 0.5 sum m v.v over all atoms (report cadence: State.getKineticEnergy).  Fixed reduction tree over the owned range,
+// rank-ordered sum across ranks: the same bits on every rank and in every run.
+extern "C" int b2_kinetic_energy(b2_context* ctx, double* out_host) {
+    if (!ctx || !out_host) return B2_ERR_ARG;
+    if (!ctx->have_order) return b2_fail(ctx, B2_ERR_STATE, "positions have not been set");
+    const int blocks = 296, T = 256;
+    B2_TRY(ensure_partials(ctx, blocks + 1));
+    k_mvv_partial<<<blocks, T, 0, ctx->stream>>>(ctx->a_lo, ctx->a_hi, ctx->v, ctx->massd, ctx->sum_partial);
+    B2_LAUNCH_CHECK();
+    double* slot = ctx->d_energy + 81;
+    k_sum_final<<<1, 256, 0, ctx->stream>>>(blocks, ctx->sum_partial, slot, 0);
+    B2_LAUNCH_CHECK();
+    B2_TRY(dist_reduce_value(ctx, slot));
+    double mvv = 0;
+    B2_CUDA(cudaMemcpyAsync(&mvv, slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B2_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out_host = 0.5*mvv;
+    return B2_OK;
+}
+
 int program_release(b2_context* ctx) {
     if (ctx->graph_exec) {
         cudaStreamSynchronize(ctx->stream);      // b2_run is asynchronous: the graph may still be in flight
@@ -906,6 +944,7 @@ int program_run(b2_context* ctx, int nsteps) {
     // all lazy allocations, which are illegal during capture).
     B2_TRY(inner_prepare(ctx));
     B2_TRY(con_prepare(ctx));
+    B2_TRY(jit_prepare(ctx));            // generic per-DOF / sum steps become kernels of their own (once per program)
     B2_TRY(ensure_partials(ctx, (ctx->a_hi - ctx->a_lo + 255)/256 + 1));
     static const bool graph_allowed = getenv("B2_NO_GRAPH") == nullptr;
     const bool use_graph = graph_allowed && !ctx->profiling;

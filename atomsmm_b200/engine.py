@@ -85,6 +85,10 @@ _SIGNATURES = {
     'b2_comm_mode': [c_void, c_int_p, ctypes.POINTER(ctypes.c_longlong)],
     'b2_comm_timing': [c_void, c_double_p],
     'b2_get_order': [c_void, c_int_p],
+    'b2_get_jit_stats': [c_void, ctypes.POINTER(ctypes.c_longlong)],
+    'b2_set_jit': [c_void, ctypes.c_int],
+    'b2_jit_check': [c_int_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int],
+    'b2_kinetic_energy': [c_void, c_double_p],
     'b2_partition_ranges': [ctypes.c_int, c_int_p, ctypes.c_int, c_int_p],
     'b2_hilbert_index': [c_double_p, c_double_p, ctypes.POINTER(ctypes.c_ulonglong)],
     'b2_comm_info': [c_void, c_int_p, c_int_p, c_int_p, c_int_p, ctypes.POINTER(ctypes.c_longlong)],
@@ -251,7 +255,8 @@ class State(object):
 class Context(object):
     """Execution context on one B200.  ``properties``: 'DeviceIndex' (default 0 or LOCAL_RANK),
     'Skin' (neighbour-list skin in nm, default 0.15), 'FastPaths' ('false' routes every per-DOF step
-    through the generic VM), 'Precision' ('mixed', the default: State forces are the fp32-tile forces the
+    through the generic path), 'PerDofCompiler' ('false': generic per-DOF steps run on the device-side bytecode
+    interpreter instead of as NVRTC-compiled kernels), 'Precision' ('mixed', the default: State forces are the fp32-tile forces the
     integrator uses; 'double': getState evaluates and accumulates every force contribution in float64 --
     report cadence only, time stepping is always mixed precision), 'DomainDecomposition' ('true': the ranks of the initialised
     torch.distributed world integrate ONE system together, each owning a spatial range of whole
@@ -283,6 +288,8 @@ class Context(object):
             raise mm.OpenMMException("Precision must be 'mixed' or 'double' on this platform")
         self._double_forces = precision == 'double'
         self._call('b2_set_skin', self._skin)
+        if str(properties.get('PerDofCompiler', 'true')).lower() == 'false':
+            self._call('b2_set_jit', 0)          # generic per-DOF steps stay on the bytecode interpreter
         box = _md(system.getDefaultPeriodicBoxVectors())
         self._box = np.array([box[0][0], box[1][1], box[2][2]], dtype=np.float64)
         self._periodic = system.usesPeriodicBoundaryConditions()
@@ -793,6 +800,16 @@ class Context(object):
             t = torch.from_numpy(np.ascontiguousarray(array)).to(self._device, non_blocking=False)
         return t
 
+    def _download(self):
+        """The [n][3] device buffer as a fresh numpy array, through a pinned staging buffer (DMA at full PCIe rate
+        instead of a pageable copy; the array the caller receives is its own)."""
+        torch = self._torch
+        if getattr(self, '_staging', None) is None:
+            self._staging = torch.empty(self._buffer.shape, dtype=self._buffer.dtype, pin_memory=True)
+        self._staging.copy_(self._buffer)
+        self._stream.synchronize()
+        return self._staging.numpy().copy()
+
     def setPositions(self, positions):
         torch = self._torch
         with torch.cuda.stream(self._stream):
@@ -863,21 +880,21 @@ class Context(object):
             if getPositions:
                 self._call('b2_get_positions', c_void(self._buffer.data_ptr()))
                 self._call('b2_synchronize')
-                pos = self._buffer.cpu().numpy()
+                pos = self._download()
                 if enforcePeriodicBox:
                     box = fields['_box']
                     for group in self._molecule_groups:
                         centre = pos[group].mean(axis=0)
                         pos[group] -= np.floor(centre/box)*box
                 fields['_positions'] = pos
-            if getVelocities or getEnergy:
+            if getVelocities:
                 self._call('b2_get_velocities', c_void(self._buffer.data_ptr()))
                 self._call('b2_synchronize')
-                vel = self._buffer.cpu().numpy()
-                if getVelocities:
-                    fields['_velocities'] = vel
-                if getEnergy:
-                    fields['_kinetic'] = 0.5*float(np.sum(self._masses[:, None]*vel*vel))
+                fields['_velocities'] = self._download()
+            if getEnergy:
+                kinetic = ctypes.c_double()
+                self._call('b2_kinetic_energy', ctypes.byref(kinetic))      # reduced on the device
+                fields['_kinetic'] = kinetic.value
             flags = (1 if getForces else 0) | (2 if (getEnergy or getParameterDerivatives) else 0) | \
                 (4 if (getForces and self._double_forces) else 0)
             if flags:
@@ -887,7 +904,7 @@ class Context(object):
                            ctypes.byref(energy), ctypes.byref(virial))
                 self._call('b2_synchronize')
                 if getForces:
-                    fields['_forces'] = self._buffer.cpu().numpy()
+                    fields['_forces'] = self._download()
                 if getEnergy:
                     if not (math.isfinite(energy.value) and math.isfinite(fields['_kinetic'])):
                         # OpenMM's behaviour: a blown-up trajectory is reported, not returned as numbers
@@ -936,6 +953,12 @@ class Context(object):
         self._call('b2_get_counters', out)
         return dict(launches=out[0], rebuilds=out[1], pair_launches=out[2], list_capacity=out[3],
                     list_max=out[4], graph_launches=out[5], kernels_per_step=out[6])
+
+    def jit_stats(self):
+        """Run-time compiled per-DOF / sum steps of the loaded program (csrc/jit.cu) and their launches so far."""
+        out = (ctypes.c_longlong*2)()
+        self._call('b2_get_jit_stats', out)
+        return dict(compiled_steps=out[0], launches=out[1])
 
     def list_stats(self):
         out = (ctypes.c_longlong*4)()

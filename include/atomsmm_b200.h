@@ -170,6 +170,9 @@ B2_API int b2_get_velocities(b2_context* ctx, double* v_dev);
  * per-pair virial); per-group values via b2_get_group_energies. */
 B2_API int b2_eval(b2_context* ctx, uint32_t group_mask, int flags, double* forces_dev,
             double* energy_host, double* virial_host);
+/* kinetic energy 0.5 sum m v.v of the current velocities (State.getKineticEnergy, computers.py:86-88), reduced on the
+ * device in a fixed order (and over the ranks of a decomposed system in rank order) */
+B2_API int b2_kinetic_energy(b2_context* ctx, double* out_host);
 B2_API int b2_get_group_energies(b2_context* ctx, double energy_host[32], double virial_host[32]);
 /* dE/dlambda of the softcore pair forces evaluated by the last b2_eval with B2_EVAL_ENERGY:
  * out[0] = d/d lambda_vdw, out[1] = d/d lambda_coul (Context.getState(getParameterDerivatives)) */
@@ -195,6 +198,16 @@ B2_API int b2_set_perdof(b2_context* ctx, int var, const double* values_dev);
 B2_API int b2_get_perdof(b2_context* ctx, int var, double* values_dev);
 /* CustomIntegrator.step(n) (integrators.py:163).  Asynchronous. */
 B2_API int b2_run(b2_context* ctx, int nsteps);
+/* Generic per-DOF / sum steps (ComputePerDof / ComputeSum expressions that are not a recognised kick, drift or
+ * rescaling: integrators.py:129,145) are compiled at run time -- bytecode -> CUDA C -> NVRTC for sm_100a -> one kernel
+ * per step (csrc/jit.cu); without libnvrtc / libcuda, or with B2_NO_JIT=1, the device-side bytecode interpreter runs
+ * them.  out_host[0] = steps of the loaded program that run as compiled kernels, out_host[1] = their launches so far. */
+B2_API int b2_get_jit_stats(b2_context* ctx, long long out_host[2]);
+/* enabled = 0: keep the bytecode interpreter for this context (A/B checks: both paths give identical bits) */
+B2_API int b2_set_jit(b2_context* ctx, int enabled);
+/* pure host check (no GPU): translate one per-DOF expression (VM bytecode, two ints per instruction) and compile it
+ * with NVRTC for sm_100a; `out` receives the generated statements, or the compiler's log on failure */
+B2_API int b2_jit_check(const int* code, int len, char* out, int out_size);
 /* counters: [0] kernel launches since creation, [1] neighbour-list rebuilds, [2] pair-kernel
  * launches, [3] list capacity (entries per 8-atom group, largest list), [4] largest count seen */
 B2_API int b2_get_counters(b2_context* ctx, long long out_host[8]);

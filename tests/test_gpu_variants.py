@@ -145,6 +145,34 @@ def test_massive_nose_hoover_langevin_through_the_per_dof_vm(cuda_platform):
     ours = np.array(integrator.getPerDofVariableByName('v2'))
     theirs = reference.perdof['v2']
     assert np.max(np.abs(ours - theirs)) < 2e-4*float(np.max(np.abs(theirs)))
+    # the generic per-DOF steps ran as kernels compiled from their bytecode at run time (csrc/jit.cu), not through
+    # the interpreter: NVRTC and the driver library are part of the CUDA installation on a GPU box
+    stats = context.jit_stats()
+    assert stats['compiled_steps'] > 0 and stats['launches'] > 0, stats
+
+
+def test_compiled_per_dof_steps_give_the_bits_of_the_interpreter(cuda_platform):
+    """The kernels csrc/jit.cu compiles from per-DOF bytecode (NVRTC, --fmad=false, the interpreter's Philox stream)
+    against the device-side interpreter they replace: a massive Nose-Hoover-Langevin thermostat WITH friction --
+    per-DOF expressions with exponentials, square roots and Gaussian draws -- must give bit-identical positions,
+    velocities and thermostat variables with the compiler on and off."""
+    respa, pdb = systems.respa_water()
+    pos = positions_of(pdb)
+    vel = thermal_velocities(respa, 300.0, 4321)
+    results = []
+    for compiler in ('true', 'false'):
+        integrator = atomsmm.NHL_R_Integrator(2*fs, [2, 1, 1], 300*K, 50*fs, 10/ps)
+        integrator.setRandomNumberSeed(99)
+        context = mm.Context(respa, integrator, cuda_platform, {'PerDofCompiler': compiler})
+        context.setPositions(pos)
+        context.setVelocities(vel)
+        integrator.step(6)
+        state = context.getState(getPositions=True, getVelocities=True)
+        stats = context.jit_stats()
+        assert (stats['compiled_steps'] > 0) == (compiler == 'true'), stats
+        results.append((state._positions, state._velocities, np.array(integrator.getPerDofVariableByName('v2'))))
+    for a, b in zip(*results):
+        assert np.array_equal(a, b)
 
 
 def test_nve_drift_no_worse_than_the_float64_oracle(cuda_platform):
