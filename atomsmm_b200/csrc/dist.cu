@@ -210,6 +210,7 @@ __global__ void k_dd_post(DDPeers P, unsigned long long* state, const int* __res
     }
 }
 
+#define DD_TILE 21            // groups per block and pass: 21 x 12 words = 252 of 256 threads busy
 // wait for every peer's post, then copy the halo (or, when anybody wants a rebuild, all foreign
 // atoms) out of the owners' memory; the last block to finish publishes the common rebuild
 // decision, resets the halo counter for the coming rebuild and acknowledges to the owners
@@ -230,34 +231,64 @@ __global__ void __launch_bounds__(256) k_dd_pull(DDPeers P, unsigned long long* 
     __syncthreads();
     // exchange clock (b2_comm_timing): block 0 saw the whole wait; the last block closes the copy
     if (blockIdx.x == 0 && threadIdx.x == 0) { state[4] += dd_now() - t_start; state[7] = dd_now(); }
-    const long long stride = (long long)gridDim.x*blockDim.x;
-    const long long first = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-    // one thread per PAIR of consecutive atoms (48 B = three 16-byte peer loads when both belong to the same
-    // foreign owner, which is the case except at ownership boundaries); master copy and fixed-point copy are
-    // written locally.  Halo mode walks the pull list (groups of 8 atoms), rebuild mode all atoms.
-    const long long total = s_flag ? (long long)((n + 1)/2) : (long long)(B2_GROUP/2)*(*halo_count);
-    for (long long t = first; t < total; t += stride) {
-        const int a0 = s_flag ? (int)(2*t) : halo_groups[t/(B2_GROUP/2)]*B2_GROUP + 2*(int)(t % (B2_GROUP/2));
-        if (a0 >= n) continue;
-        const int o0 = dd_owner(P, a0);
-        const int o1 = a0 + 1 < n ? dd_owner(P, a0 + 1) : P.rank;
-        if (o0 == o1 && o0 != P.rank) {
-            const double2* src = reinterpret_cast<const double2*>(P.x[o0] + 3ll*a0);     // a0 even: 16-byte aligned
-            const double2 u = __ldcg(src), v = __ldcg(src + 1), w = __ldcg(src + 2);
-            double2* dst = reinterpret_cast<double2*>(x + 3ll*a0);
-            dst[0] = u; dst[1] = v; dst[2] = w;
-            xq[a0] = make_int4(b2_to_fixed(u.x, sx), b2_to_fixed(u.y, sy), b2_to_fixed(v.x, sz), 0);
-            xq[a0 + 1] = make_int4(b2_to_fixed(v.y, sx), b2_to_fixed(w.x, sy), b2_to_fixed(w.y, sz), 0);
-            continue;
+    // COALESCED copy.  A group of 8 atoms is 192 contiguous, 64-byte aligned bytes = twelve 16-byte words; a block
+    // takes DD_TILE groups per pass and thread t copies word t % 12 of group t / 12, so that consecutive lanes read
+    // consecutive addresses of the owner's memory (round 2c gave every thread a 48-byte atom pair: three loads with
+    // a 48-byte stride between lanes, i.e. every 128-byte line crossed NVLink three times -- 124 GB/s of useful
+    // data).  Two passes are in flight per thread.  A word can straddle two atoms with different owners at an
+    // ownership boundary (cuts fall on molecules, not on groups): then its two doubles are handled one by one.
+    // After a barrier the block converts the atoms it has just copied to the fixed-point copy the pair tiles read.
+    // Halo mode walks the pull list, rebuild mode all groups.
+    const int ngroups_all = (n + B2_GROUP - 1)/B2_GROUP;
+    const int units = s_flag ? ngroups_all : *halo_count;
+    const long long ndoubles = 3ll*n;
+    const int t = threadIdx.x, gi = t/12, w = t - 12*gi;
+    for (int base = blockIdx.x*DD_TILE*2; base < units; base += gridDim.x*DD_TILE*2) {
+        double2 val[2];
+        long long d0[2];
+        int own[2][2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int unit = base + u*DD_TILE + gi;
+            d0[u] = -1;
+            own[u][0] = own[u][1] = P.rank;
+            if (gi < DD_TILE && unit < units) {
+                const int g = s_flag ? unit : halo_groups[unit];
+                const long long d = 24ll*g + 2*w;
+                if (d < ndoubles) {
+                    d0[u] = d;
+                    own[u][0] = dd_owner(P, (int)(d/3));
+                    own[u][1] = d + 1 < ndoubles ? dd_owner(P, (int)((d + 1)/3)) : P.rank;
+                    if (own[u][0] == own[u][1]) {
+                        if (own[u][0] != P.rank) val[u] = __ldcg(reinterpret_cast<const double2*>(P.x[own[u][0]] + d));
+                    } else {
+                        if (own[u][0] != P.rank) val[u].x = __ldcg(P.x[own[u][0]] + d);
+                        if (own[u][1] != P.rank) val[u].y = __ldcg(P.x[own[u][1]] + d + 1);
+                    }
+                }
+            }
         }
-        for (int k = 0; k < 2; k++) {
-            const int a = a0 + k, o = k ? o1 : o0;
-            if (a >= n || o == P.rank) continue;
-            const double* src = P.x[o] + 3ll*a;
-            const double px = __ldcg(src), py = __ldcg(src + 1), pz = __ldcg(src + 2);
-            x[3ll*a] = px; x[3ll*a+1] = py; x[3ll*a+2] = pz;
-            xq[a] = make_int4(b2_to_fixed(px, sx), b2_to_fixed(py, sy), b2_to_fixed(pz, sz), 0);
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (d0[u] < 0) continue;
+            if (own[u][0] == own[u][1]) {
+                if (own[u][0] != P.rank) *reinterpret_cast<double2*>(x + d0[u]) = val[u];
+            } else {
+                if (own[u][0] != P.rank) x[d0[u]] = val[u].x;
+                if (own[u][1] != P.rank) x[d0[u] + 1] = val[u].y;
+            }
         }
+        __syncthreads();
+        // fixed-point copy of the atoms of this pass: 2 x DD_TILE groups x 8 atoms
+        for (int k = t; k < 2*DD_TILE*B2_GROUP; k += blockDim.x) {
+            const int unit = base + k/B2_GROUP;
+            if (unit >= units) continue;
+            const int g = s_flag ? unit : halo_groups[unit];
+            const int a = g*B2_GROUP + (k & (B2_GROUP - 1));
+            if (a >= n || dd_owner(P, a) == P.rank) continue;
+            xq[a] = make_int4(b2_to_fixed(x[3ll*a], sx), b2_to_fixed(x[3ll*a+1], sy), b2_to_fixed(x[3ll*a+2], sz), 0);
+        }
+        __syncthreads();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
