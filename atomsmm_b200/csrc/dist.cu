@@ -344,7 +344,7 @@ int dist_exchange_halo(b2_context* ctx) {
     DDPeers P = make_peers(ctx);
     k_dd_post<<<1, 32, 0, ctx->stream>>>(P, ctx->dd_state, ctx->nl_flags);
     B2_LAUNCH_CHECK();
-    k_dd_pull<<<296, 256, 0, ctx->stream>>>(P, ctx->dd_state, ctx->nl_flags, ctx->x, ctx->xq, 4294967296.0/ctx->box[0],
+    k_dd_pull<<<592, 256, 0, ctx->stream>>>(P, ctx->dd_state, ctx->nl_flags, ctx->x, ctx->xq, 4294967296.0/ctx->box[0],
                                             4294967296.0/ctx->box[1], 4294967296.0/ctx->box[2], ctx->n, ctx->halo_groups,
                                             ctx->halo_count);
     B2_LAUNCH_CHECK();
