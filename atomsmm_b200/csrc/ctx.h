@@ -29,7 +29,9 @@
 #define B2_MAX_LISTS 4
 #define B2_FSLOTS 33          // force buffers: groups 0..31 and 32 = total
 #define B2_MAX_PAIR_PARAMS 16
-#define B2_CHUNK 128           // atoms per molecule chunk of the fused inner-loop kernel
+#ifndef B2_CHUNK
+#define B2_CHUNK 96            // atoms per molecule chunk of the fused inner-loop kernel (measured: 96 beats 128, 64, 32)
+#endif
 #define B2_INNER_MAX_FORCES 16
 #define B2_MAX_RANKS 16
 

@@ -297,7 +297,7 @@ struct InnerArgs {
 
 // tuning knobs (measured on B200: profiles/round2_pair_variants.txt)
 #ifndef B2_INNER_MINB
-#define B2_INNER_MINB 6         // resident blocks per SM the register budget is sized for
+#define B2_INNER_MINB 8         // resident blocks per SM the register budget is sized for (80 registers at 96 threads)
 #endif
 #ifndef B2_INNER_HOIST
 #define B2_INNER_HOIST 1        // resolve each thread's first term once per launch
