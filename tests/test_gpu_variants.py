@@ -115,10 +115,11 @@ def test_nose_hoover_langevin(cuda_platform):
     assert np.std(p) > 0 and abs(np.mean(p)) < 3*np.std(p)
 
 
-def test_massive_nose_hoover_langevin_through_the_per_dof_vm(cuda_platform):
+def test_massive_nose_hoover_langevin_through_the_generic_per_dof_path(cuda_platform):
     """NHL_R_Integrator (integrators.py:349-352 family): a MASSIVE thermostat -- one Nose-Hoover-Langevin
     variable per degree of freedom, i.e. per-DOF expressions that no dedicated kernel matches and that run
-    through the generic per-DOF virtual machine -- against the float64 oracle interpreter, in the limit of
+    through the generic per-DOF path (kernels compiled from the bytecode at run time, csrc/jit.cu; the device-side
+    virtual machine without NVRTC) -- against the float64 oracle interpreter, in the limit of
     vanishing friction where the two random streams cannot matter."""
     from oracle import interp
     respa, pdb = systems.respa_water()
