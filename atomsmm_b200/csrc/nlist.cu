@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(32*NL_WARPS, B2_NL_MINB) k_build_lists(int n, 
     __shared__ int seg_pre[NL_WARPS][65];
     __shared__ float4 seg_shift[NL_WARPS][64];
     __shared__ int* s_ebase[NL_WARPS][B2_MAX_LISTS];     // this group's slice of every list
+    __shared__ int s_good[NL_WARPS][B2_MAX_LISTS];
     const int i0 = warp*B2_GROUP;
     const float box[3] = {(float)g.box[0], (float)g.box[1], (float)g.box[2]};
     const float ibox[3] = {(float)g.inv[0], (float)g.inv[1], (float)g.inv[2]};
@@ -380,6 +381,7 @@ __global__ void __launch_bounds__(32*NL_WARPS, B2_NL_MINB) k_build_lists(int n, 
     if (lane < B2_MAX_LISTS) {
         const int k = lane < a.nlists ? lane : 0;
         s_ebase[wib][lane] = a.entries[k] + (size_t)warp*a.cap[k];
+        s_good[wib][lane] = -1;          // core entries in place when the list first overflowed (-1: it has not)
     }
     __syncwarp();
     const float rmax2 = rmax*rmax;
@@ -451,10 +453,17 @@ __global__ void __launch_bounds__(32*NL_WARPS, B2_NL_MINB) k_build_lists(int n, 
                 const unsigned cballot = __ballot_sync(FULL, in && core);
                 const unsigned sballot = ballot & ~cballot;
                 const int nc = __popc(cballot), ns = __popc(sballot);
-                if (in && count[k] + scount[k] + nc + ns <= a.cap[k]) {
-                    const int pos = core ? count[k] + __popc(cballot & lt)
-                                         : a.cap[k] - 1 - (scount[k] + __popc(sballot & lt));
-                    s_ebase[wib][k][pos] = entry;
+                if (count[k] + scount[k] + nc + ns <= a.cap[k]) {
+                    if (in) {
+                        const int pos = core ? count[k] + __popc(cballot & lt)
+                                             : a.cap[k] - 1 - (scount[k] + __popc(sballot & lt));
+                        s_ebase[wib][k][pos] = entry;
+                    }
+                } else if (lane == 0 && s_good[wib][k] < 0) {
+                    // capacity exceeded (reported through flags[1]; the host re-fits the lists): from here on nothing
+                    // is written, and the list handed to the pair tiles ends with the core entries written so far --
+                    // a contiguous, fully initialised prefix (the gap between the two parts never is)
+                    s_good[wib][k] = count[k];
                 }
                 count[k] += nc;
                 scount[k] += ns;
@@ -710,9 +719,10 @@ __global__ void __launch_bounds__(32*NL_WARPS, B2_NL_MINB) k_build_lists(int n, 
         }
         count[k] = total;
     }
+    __syncwarp();
     if (lane == 0) {
         for (int k = 0; k < a.nlists; k++) {
-            a.counts[k][warp] = min(count[k], a.cap[k]);
+            a.counts[k][warp] = count[k] <= a.cap[k] ? count[k] : max(s_good[wib][k], 0);
             if (count[k] > a.cap[k]) flags[1] = 1;
             if (count[k] > flags[3]) atomicMax(&flags[3], count[k]);
         }
